@@ -1,0 +1,235 @@
+/*
+ * weedgpu.h — C ABI of libweedgpu.so, the B200-native replacement for the WeedJS
+ * (brotochola/MultithreadedGameEngine) spatial_worker + physics_worker hot path.
+ *
+ * The reference has no FFI: its seam is the *worker contract* (an "init" message with
+ * SharedArrayBuffers + config, then update() once per frame).  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; device pointers travel as void*.
+ *   - every call returns 0 (WEED_OK) or a negative WEED_E_* code; nothing throws or aborts
+ *     across the boundary.  weed_last_error() gives the text of the last failure.
+ *   - a context is NOT thread-safe (the reference workers are single-threaded too); the
+ *     caller serialises calls.  Host buffers are owned by the caller (the JS engine owns
+ *     the SABs: src/core/gameEngine.js:534-777) and are never freed here.
+ *   - there is no CPU fallback: without a CUDA device weed_create fails with WEED_E_CUDA.
+ */
+#ifndef WEEDGPU_H
+#define WEEDGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WEED_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------- */
+enum {
+  WEED_OK            =  0,
+  WEED_E_INVALID     = -1,  /* bad argument / config                                   */
+  WEED_E_CUDA        = -2,  /* CUDA runtime failure (context becomes sticky-failed)    */
+  WEED_E_NOT_BOUND   = -3,  /* a required host buffer was not bound                    */
+  WEED_E_SIZE        = -4,  /* bound buffer smaller than the layout requires           */
+  WEED_E_OVERFLOW    = -5,  /* internal explicit-pair capacity exceeded (see stats)    */
+  WEED_E_STATE       = -6,  /* call order violated (e.g. weed_physics before spatial)  */
+  WEED_E_NOMEM       = -7
+};
+
+/* ---- buffers: the SharedArrayBuffers of the "init" payload ------------------------
+ * src/core/gameEngine.js:1049-1125 (buffers.componentData.{Transform,RigidBody,Collider},
+ * buffers.neighborData, buffers.distanceData, buffers.collisionData).               */
+typedef enum weed_buffer_id {
+  WEED_BUF_TRANSFORM = 0,   /* src/components/Transform.js:8-17   (14 B / entity)       */
+  WEED_BUF_RIGIDBODY = 1,   /* src/components/RigidBody.js:9-47   (83 B / entity)       */
+  WEED_BUF_COLLIDER  = 2,   /* src/components/Collider.js:8-46    (51 B / entity)       */
+  WEED_BUF_NEIGHBOR  = 3,   /* Int32   [N*(1+maxNeighbors)]  gameEngine.js:552-555      */
+  WEED_BUF_DISTANCE  = 4,   /* Float32 [N*(1+maxNeighbors)]  gameEngine.js:557-559      */
+  WEED_BUF_COLLISION = 5,   /* Int32   [1+2*maxCollisionPairs] gameEngine.js:689-696    */
+  WEED_BUF_COUNT     = 6
+} weed_buffer_id;
+
+/* ---- columns the hot path reads or writes --------------------------
+ * Bits for upload_mask / download_mask.  Only these columns are mirrored on the device;
+ * the remaining schema columns (mass, drag, friction, aabb*, ...) are declared by the
+ * reference but never read by either worker, so they are never touched.               */
+enum {
+  WEED_COL_T_ACTIVE    = 1u << 0,   /* Transform.active        u8  */
+  WEED_COL_T_X         = 1u << 1,   /* Transform.x             f32 */
+  WEED_COL_T_Y         = 1u << 2,   /* Transform.y             f32 */
+  WEED_COL_RB_ACTIVE   = 1u << 3,   /* RigidBody.active        u8  */
+  WEED_COL_RB_STATIC   = 1u << 4,   /* RigidBody.static        u8  */
+  WEED_COL_RB_VX       = 1u << 5,
+  WEED_COL_RB_VY       = 1u << 6,
+  WEED_COL_RB_AX       = 1u << 7,
+  WEED_COL_RB_AY       = 1u << 8,
+  WEED_COL_RB_PX       = 1u << 9,
+  WEED_COL_RB_PY       = 1u << 10,
+  WEED_COL_RB_MAXVEL   = 1u << 11,
+  WEED_COL_RB_VELANGLE = 1u << 12,  /* RigidBody.velocityAngle f32 */
+  WEED_COL_RB_SPEED    = 1u << 13,
+  WEED_COL_RB_COLLCNT  = 1u << 14,  /* RigidBody.collisionCount u8 */
+  WEED_COL_C_ACTIVE    = 1u << 15,
+  WEED_COL_C_RADIUS    = 1u << 16,
+  WEED_COL_C_ISTRIGGER = 1u << 17,
+  WEED_COL_C_VISRANGE  = 1u << 18,  /* Collider.visualRange    f32 */
+  /* pseudo-columns: whole output buffers (download only) */
+  WEED_COL_NEIGHBORS   = 1u << 24,  /* all of neighborData + distanceData (large!)      */
+  WEED_COL_COLLISIONS  = 1u << 25   /* collisionData                                    */
+};
+#define WEED_COLS_INPUT_ALL  0x0007FFFFu  /* every mirrored component column             */
+/* what the reference's two workers write every frame (physics_worker.js:301-314,596-601,
+ * 176,551) */
+#define WEED_COLS_OUTPUT_ALL (WEED_COL_T_X | WEED_COL_T_Y | WEED_COL_RB_VX | WEED_COL_RB_VY | \
+                              WEED_COL_RB_AX | WEED_COL_RB_AY | WEED_COL_RB_PX | WEED_COL_RB_PY | \
+                              WEED_COL_RB_VELANGLE | WEED_COL_RB_SPEED | WEED_COL_RB_COLLCNT)
+
+/* ---- configuration ----------------------------------------------------------------
+ * config.physics of the engine; defaults as src/core/gameEngine.js:39-49 and
+ * src/workers/physics_worker.js:33-40.  weed_set_physics applies the clamps of
+ * validatePhysicsConfig (src/core/utils.js:269-301).                                   */
+typedef struct weed_physics_config {
+  int32_t subStepCount;               /* >= 1 after validation; default 4              */
+  int32_t _pad0;
+  double  boundaryElasticity;         /* clamp01; default 0.8                          */
+  double  collisionResponseStrength;  /* clamp01; default 0.5                          */
+  double  verletDamping;              /* clamp01; default 0.995                        */
+  double  minSpeedForRotation;        /* default 0.1                                   */
+  double  gravityX;                   /* default 0                                     */
+  double  gravityY;                   /* default 0                                     */
+} weed_physics_config;
+
+/* collision resolution order (DESIGN.md "J-order") */
+enum {
+  WEED_ORDER_JACOBI = 0   /* documented deterministic order of the GPU path            */
+};
+
+enum {
+  WEED_FLAG_NONE          = 0,
+  WEED_FLAG_NO_GRAPH      = 1u << 0,  /* launch kernels directly, no CUDA graph         */
+  WEED_FLAG_KERNEL_TIMING = 1u << 1,  /* per-kernel cudaEvent timing into weed_stats    */
+  WEED_FLAG_NO_NEIGHBOR_ROWS = 1u << 2 /* do not allocate/write neighborData/distanceData
+                                          (physics-only consumers); rows then unavailable */
+};
+
+/* The "init" message: gameEngine.js:1049-1125 (entityCount, config.worldWidth/Height,
+ * config.spatial.{cellSize,maxNeighbors}, config.physics.*, config.seed).             */
+typedef struct weed_config {
+  uint32_t struct_size;          /* sizeof(weed_config), ABI check                      */
+  uint32_t entityCount;          /* totalEntityCount, includes Mouse at index 0         */
+  double   worldWidth;
+  double   worldHeight;
+  double   cellSize;             /* config.spatial.cellSize  (spatial_worker.js:80)     */
+  uint32_t maxNeighbors;         /* config.spatial.maxNeighbors (spatial_worker.js:85)  */
+  uint32_t maxCollisionPairs;    /* physics_worker.js:74-77; the JS `|| 10000`
+                                    fall-through for 0 is applied by the host wrapper   */
+  double   seed;                 /* config.seed (AbstractWorker.js:287-292)             */
+  weed_physics_config physics;
+  int32_t  device;               /* CUDA ordinal                                        */
+  uint32_t flags;                /* WEED_FLAG_*                                         */
+  void*    stream;               /* cudaStream_t to run on, or NULL for a private one   */
+  /* world-space slab owned by this context (multi-GPU, SURVEY §8 e): entities whose
+   * clamped cell row lies in [slabRowBegin, slabRowEnd) are owned; 0,0 = whole world. */
+  uint32_t slabRowBegin;
+  uint32_t slabRowEnd;
+} weed_config;
+
+typedef struct weed_stats {
+  uint64_t frames;               /* steps executed                                      */
+  uint32_t gridCols, gridRows;   /* spatial_worker.js:82-83                             */
+  uint32_t activeInGrid;         /* entities inserted in the grid last frame            */
+  uint32_t maxCellOccupancy;
+  uint64_t neighborsTotal;       /* sum of row counts last frame  (k-bar = /active)     */
+  uint32_t cappedRows;           /* rows that hit maxNeighbors last frame               */
+  uint32_t explicitPairs;        /* pairs routed through the explicit (asymmetric) path */
+  uint32_t explicitOverflow;     /* !=0: explicit-pair capacity exceeded (result invalid) */
+  uint32_t collisionPairs;       /* pairs found in the last substep (uncapped)          */
+  uint32_t kernelLaunchesPerStep;
+  uint32_t _pad;
+  float    ms[12];               /* per-kernel ms of the last step (KERNEL_TIMING only) */
+} weed_stats;
+
+typedef struct weed_ctx weed_ctx;
+
+/* ---- layout: Component.initializeArrays / getBufferSize (src/core/Component.js:20-42,
+ * 77-93).  Column index = position in the component's ARRAY_SCHEMA.                    */
+size_t weed_buffer_bytes(weed_buffer_id id, uint32_t entityCount, uint32_t maxNeighbors,
+                         uint32_t maxCollisionPairs);
+/* byte offset of schema column `column` of component buffer `id`; (size_t)-1 if invalid */
+size_t weed_column_offset(weed_buffer_id id, uint32_t column, uint32_t entityCount);
+/* number of schema columns of a component buffer (5 / 23 / 16)                         */
+uint32_t weed_column_count(weed_buffer_id id);
+/* schema name of a column ("x", "velocityAngle", ...) or NULL                          */
+const char* weed_column_name(weed_buffer_id id, uint32_t column);
+
+/* fills *cfg with the engine defaults (gameEngine.js:34-49; maxNeighbors 100,
+ * maxCollisionPairs 10000)                                                             */
+void weed_default_config(weed_config* cfg);
+
+/* replaces: new Worker(spatial_worker.js) + new Worker(physics_worker.js) and their
+ * initialize(data) (spatial_worker.js:49-116, physics_worker.js:50-97)                 */
+int  weed_create(const weed_config* cfg, weed_ctx** out);
+void weed_destroy(weed_ctx* ctx);
+
+/* replaces: the typed-array views the workers create over the SABs
+ * (Component.js:36, AbstractWorker.js:176-285).  bytes must be >= weed_buffer_bytes(). */
+int weed_bind(weed_ctx* ctx, weed_buffer_id id, void* host_base, size_t bytes);
+
+/* host SAB columns -> device mirror / device mirror -> host SAB columns               */
+int weed_upload(weed_ctx* ctx, uint32_t column_mask);
+int weed_download(weed_ctx* ctx, uint32_t column_mask);
+
+/* replaces: SpatialWorker.update (spatial_worker.js:283-294): rebuildGrid+findAllNeighbors */
+int weed_spatial(weed_ctx* ctx);
+/* replaces: PhysicsWorker.update (physics_worker.js:103-108): updateVerlet.  Uses the
+ * neighbor rows of the preceding weed_spatial (lockstep order of SURVEY Appendix B).    */
+int weed_physics(weed_ctx* ctx, double dtRatio);
+/* one lockstep frame = upload(upload_mask); spatial; physics(dtRatio); download(mask). */
+int weed_step(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, uint32_t download_mask);
+/* `frames` lockstep frames back to back with no host interaction (device-resident run) */
+int weed_run(weed_ctx* ctx, double dtRatio, uint32_t frames);
+
+/* replaces: {msg:"updatePhysicsConfig"} -> applyPhysicsConfig (physics_worker.js:114-129) */
+int weed_set_physics(weed_ctx* ctx, const weed_physics_config* p);
+int weed_get_physics(weed_ctx* ctx, weed_physics_config* out);
+
+/* replaces: GameObject.updateNeighbors reading row i (src/core/gameObject.js:700-729):
+ * copies rows [first, first+count) of neighborData and distanceData to the bound SABs.  */
+int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t count);
+
+int weed_sync(weed_ctx* ctx);
+int weed_get_stats(weed_ctx* ctx, weed_stats* out);
+const char* weed_last_error(weed_ctx* ctx);   /* ctx may be NULL: last create() failure */
+
+/* device-resident access for in-process consumers (bench harness, multi-GPU plumbing):
+ * raw device pointers of the API-visible mirrors.                                      */
+typedef enum weed_devptr_id {
+  WEED_DEV_NEIGHBOR  = 0,  /* int32  [N*(1+M)] */
+  WEED_DEV_DISTANCE  = 1,  /* float  [N*(1+M)] */
+  WEED_DEV_COLLISION = 2,  /* int32  [1+2*maxPairs] */
+  WEED_DEV_STATE     = 3,  /* 32 B per-entity state record, see DESIGN.md               */
+  WEED_DEV_ATTR      = 4,  /* 16 B per-entity attribute record                          */
+  WEED_DEV_VEL       = 5   /* 16 B per-entity velocity record                           */
+} weed_devptr_id;
+int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
+
+/* ---- multi-GPU slabs (SURVEY §8 e) --------------------------------------------------
+ * The context owns the entities whose cell row is inside its slab; rows within `halo`
+ * of the slab are replicated read-only.  Exchange buffers are plain device memory so the
+ * host (torch.distributed / NCCL send-recv) moves them; see INTEGRATION.md.            */
+typedef enum weed_side { WEED_SIDE_LOW = 0, WEED_SIDE_HIGH = 1 } weed_side;
+/* pack records of entities leaving through `side` (migration) or lying in the boundary
+ * rows next to `side` (halo) into dev_buf; *count receives the record count.           */
+int weed_slab_pack(weed_ctx* ctx, weed_side side, int what /*0=halo,1=migrate*/,
+                   void* dev_buf, size_t capacity_records, uint32_t* count);
+int weed_slab_unpack(weed_ctx* ctx, weed_side side, int what, const void* dev_buf,
+                     uint32_t count);
+#define WEED_SLAB_RECORD_BYTES 64
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEEDGPU_H */

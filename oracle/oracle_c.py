@@ -1,0 +1,136 @@
+"""ctypes wrapper around oracle/libweedoracle.so (TEST INFRASTRUCTURE ONLY)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+COLS = {  # key -> (component id, schema name, dtype)
+    "T.active": (0, "active", np.uint8), "T.x": (0, "x", np.float32), "T.y": (0, "y", np.float32),
+    "RB.active": (1, "active", np.uint8), "RB.static": (1, "static", np.uint8),
+    "RB.vx": (1, "vx", np.float32), "RB.vy": (1, "vy", np.float32),
+    "RB.ax": (1, "ax", np.float32), "RB.ay": (1, "ay", np.float32),
+    "RB.px": (1, "px", np.float32), "RB.py": (1, "py", np.float32),
+    "RB.maxVel": (1, "maxVel", np.float32), "RB.velocityAngle": (1, "velocityAngle", np.float32),
+    "RB.speed": (1, "speed", np.float32), "RB.collisionCount": (1, "collisionCount", np.uint8),
+    "C.active": (2, "active", np.uint8), "C.radius": (2, "radius", np.float32),
+    "C.isTrigger": (2, "isTrigger", np.uint8), "C.visualRange": (2, "visualRange", np.float32),
+}
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libweedoracle.so")
+    src = os.path.join(_HERE, "weed_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "weed_nudge.h")
+    stale = (not os.path.exists(so)) or any(
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libweedoracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.wo_create.restype = C.c_void_p
+        L.wo_create.argtypes = [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double]
+        L.wo_destroy.argtypes = [C.c_void_p]
+        L.wo_set_physics.argtypes = [C.c_void_p, C.c_int32] + [C.c_double] * 6
+        L.wo_bind.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.wo_spatial.argtypes = [C.c_void_p]
+        L.wo_physics.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.wo_step.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.wo_grid_export.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+        L.wo_grid_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.wo_column_offset.restype = C.c_int64
+        L.wo_column_offset.argtypes = [C.c_int, C.c_char_p, C.c_int64]
+        L.wo_buffer_size.restype = C.c_int64
+        L.wo_buffer_size.argtypes = [C.c_int, C.c_int64]
+        L.wo_bench_freerun.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.wo_bench_lockstep.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.wo_js_toint32.restype = C.c_int32
+        L.wo_js_toint32.argtypes = [C.c_double]
+        L.wo_seeded_random.restype = C.c_double
+        L.wo_seeded_random.argtypes = [C.c_double, C.c_int]
+        L.wo_nudge_dir.argtypes = [C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.wo_nudge_hash.restype = C.c_uint32
+        L.wo_nudge_hash.argtypes = [C.c_uint32] * 5
+        _LIB = L
+    return _LIB
+
+
+class OracleC:
+    """The C oracle over its own SAB-layout buffers; .col[...] are numpy views into them."""
+
+    def __init__(self, N, worldWidth, worldHeight, cellSize, maxNeighbors, maxPairs=10000,
+                 seed=1.0, physics=None):
+        L = lib()
+        self.N, self.M, self.maxPairs = N, maxNeighbors, maxPairs
+        self.bufs = [np.zeros(L.wo_buffer_size(k, N), dtype=np.uint8) for k in range(3)]
+        self.neighborData = np.zeros(N * (1 + maxNeighbors), dtype=np.int32)
+        self.distanceData = np.zeros(N * (1 + maxNeighbors), dtype=np.float32)
+        self.collisionData = np.zeros(1 + 2 * maxPairs, dtype=np.int32)
+        self.h = L.wo_create(N, worldWidth, worldHeight, cellSize, maxNeighbors, maxPairs, float(seed))
+        for k in range(3):
+            L.wo_bind(self.h, k, self.bufs[k].ctypes.data)
+        L.wo_bind(self.h, 3, self.neighborData.ctypes.data)
+        L.wo_bind(self.h, 4, self.distanceData.ctypes.data)
+        L.wo_bind(self.h, 5, self.collisionData.ctypes.data)
+        self.col = {}
+        for key, (comp, name, dt) in COLS.items():
+            off = L.wo_column_offset(comp, name.encode(), N)
+            self.col[key] = self.bufs[comp][off:off + N * np.dtype(dt).itemsize].view(dt)
+        cols, rows = C.c_int32(), C.c_int32()
+        L.wo_grid_dims(self.h, C.byref(cols), C.byref(rows))
+        self.gridCols, self.gridRows = cols.value, rows.value
+        if physics:
+            self.set_physics(**physics)
+
+    def set_physics(self, subStepCount=4, boundaryElasticity=0.8, collisionResponseStrength=0.5,
+                    verletDamping=0.995, minSpeedForRotation=0.1, gravityX=0.0, gravityY=0.0):
+        lib().wo_set_physics(self.h, subStepCount, boundaryElasticity, collisionResponseStrength,
+                             verletDamping, minSpeedForRotation, gravityX, gravityY)
+
+    def load(self, columns):
+        for k, v in columns.items():
+            self.col[k][:] = v
+
+    def spatial(self):
+        lib().wo_spatial(self.h)
+
+    def physics(self, dtRatio=1.0, order=0):
+        lib().wo_physics(self.h, float(dtRatio), order)
+
+    def step(self, dtRatio=1.0, order=0):
+        lib().wo_step(self.h, float(dtRatio), order)
+
+    def grid_csr(self):
+        Cn = self.gridCols * self.gridRows
+        cellOf = np.zeros(self.N, dtype=np.int32)
+        start = np.zeros(Cn + 1, dtype=np.int32)
+        idx = np.zeros(self.N, dtype=np.int32)
+        lib().wo_grid_export(self.h, cellOf.ctypes.data, start.ctypes.data, idx.ctypes.data)
+        return cellOf, start, idx[: start[Cn]]
+
+    def bench(self, frames, dtRatio=1.0, freerun=True):
+        a, b = C.c_double(), C.c_double()
+        f = lib().wo_bench_freerun if freerun else lib().wo_bench_lockstep
+        f(self.h, frames, float(dtRatio), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        if self.h:
+            lib().wo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
