@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the spatial+physics hot path (BASELINE.json metric:
+entity-substep updates/sec, grid + neighbors + Verlet + collide, at 16M entities).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" is one lockstep frame (grid rebuild, neighbor query, integration, S constraint
+substeps, write-back) over the whole scene.  Prints ONE JSON line (rank 0).
+
+  value     device-resident throughput: A * S * K / t, t = CUDA-event time of K frames, inputs
+            already in HBM (A = active entities, S = subStepCount)
+  e2e       the same frames through GameEngine.step() with HOST component buffers: every step
+            uploads the columns tick() writes (ax, ay) and downloads the columns the
+            renderer/logic read (x, y, vx, vy, velocityAngle, speed)
+  roofline  dominant kernel, algorithmic bytes / its CUDA-event time, against the
+            measured HBM copy peak of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the CPU restatement of the reference's two JS workers
+            (oracle/, "port": no JS engine exists in this image) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "entity_substep_updates_per_sec"
+UNIT = "entity-substeps/s"
+
+KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
+                "k_explicit_capped", "k_substep(xS)", "k_writeback"]
+
+
+def workload(name, n_override=None):
+    from multithreadedgameengine_b200 import scenes
+    full = {"config3": 1_000_000, "config4": 16_000_000, "config5": 128_000_000}
+    if name in full:
+        n = n_override or full[name]
+        if n == full[name]:
+            return getattr(scenes, name)()
+        return scenes.scaled(name, n)
+    if name == "config1":
+        return scenes.balls_readme()
+    if name == "config1b":
+        return scenes.balls_demo()
+    if name == "config2":
+        return scenes.boids()
+    raise SystemExit(f"unknown workload {name}")
+
+
+def describe(name, cfg):
+    return {"workload": f"{name}: synthetic balls, {cfg['entityCount'] - 1} entities + Mouse, world "
+                        f"{cfg['worldWidth']:.0f}x{cfg['worldHeight']:.0f}, cellSize {cfg['spatial']['cellSize']:g}, "
+                        f"maxNeighbors {cfg['spatial']['maxNeighbors']}, subStepCount {cfg['physics']['subStepCount']}",
+            "entities": cfg["entityCount"], "subStepCount": cfg["physics"]["subStepCount"]}
+
+
+def algorithmic_bytes(kbar, S):
+    """SURVEY §8(d) / DESIGN.md: compulsory bytes per active entity per frame."""
+    per_kernel = {
+        "k_cell_key": 13.0, "k_cell_scan+k_scatter_ids": 8.0,
+        "k_neighbors": 24.0 + 8.0 * (1.0 + kbar),
+        "k_build_slots (integrate+derived)": 64.0 + 18.0,
+        "k_substep": S * (34.0 + 4.0 * (1.0 + kbar)),
+    }
+    return 127.0 + 8.0 * (1.0 + kbar) + S * (34.0 + 4.0 * (1.0 + kbar)), per_kernel
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_for(cfg, cols):
+    from multithreadedgameengine_b200.engine import PHYSICS_DEFAULTS
+    from oracle.oracle_c import OracleC
+    p = dict(PHYSICS_DEFAULTS)
+    p.update({k: v for k, v in cfg["physics"].items() if k not in ("gravity", "maxCollisionPairs")})
+    g = cfg["physics"].get("gravity", {"x": 0, "y": 0})
+    o = OracleC(cfg["entityCount"], cfg["worldWidth"], cfg["worldHeight"], cfg["spatial"]["cellSize"],
+                cfg["spatial"]["maxNeighbors"], int(cfg["physics"].get("maxCollisionPairs") or 10000), cfg.get("seed", 1.0),
+                dict(subStepCount=p["subStepCount"], boundaryElasticity=p["boundaryElasticity"],
+                     collisionResponseStrength=p["collisionResponseStrength"], verletDamping=p["verletDamping"],
+                     minSpeedForRotation=p["minSpeedForRotation"], gravityX=g["x"], gravityY=g["y"]))
+    o.load(cols)
+    return o
+
+
+def cpu_reference(name, steps, warmup, sample_entities):
+    """The reference's CPU structure: ONE spatial worker thread + ONE physics worker thread,
+    free-running on shared buffers (gameEngine.js:978-996, AbstractWorker.js:114-146),
+    restated in C (oracle/weed_oracle.c).  Bounded sample of the same workload at the same
+    entity density."""
+    cfg, cols = workload(name, sample_entities)
+    o = oracle_for(cfg, cols)
+    S = cfg["physics"]["subStepCount"]
+    active = int(cols["T.active"].sum())
+    if warmup:
+        o.bench(warmup, 1.0, freerun=True)
+    ts, tp = o.bench(steps, 1.0, freerun=True)
+    t = max(ts, tp)
+    ls, lp = o.bench(max(1, steps // 2), 1.0, freerun=False)
+    lock = (ls + lp) / max(1, steps // 2)
+    return {
+        "value": active * S * steps / t, "unit": UNIT, "cores": 2, "kind": "port",
+        "sample": f"{name} at the same density scaled to {cfg['entityCount'] - 1} entities, {steps} frames, "
+                  f"2 free-running threads (spatial {ts / steps * 1e3:.1f} ms/frame, physics {tp / steps * 1e3:.1f} ms/frame); "
+                  f"single-thread lockstep {lock * 1e3:.1f} ms/frame = {active * S / lock:.3e} {UNIT}",
+        "host_cores_available": len(os.sched_getaffinity(0)),
+    }, cfg, t / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, args.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(args.workload, workload(args.workload, 1000)[0] if False else cfg),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    line["config"]["note"] = ("CPU restatement (C port) of the reference's JS spatial+physics workers; no JavaScript engine "
+                              "exists in this image, so the original cannot be executed")
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from multithreadedgameengine_b200 import binding as B
+    from multithreadedgameengine_b200.engine import GameEngine
+
+    name = args.workload
+    n_total = args.entities
+    # N>1: slab exchange is not built yet -> every rank runs an independent replica of the
+    # single-GPU workload (weak scaling, no data-path collective); see DESIGN.md.
+    cfg, cols = workload(name, n_total)
+    S = cfg["physics"]["subStepCount"]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng = GameEngine(cfg, device=local, stream=stream.cuda_stream, host_neighbor_rows=False)
+        eng.load_columns(cols)
+        active = int(cols["T.active"].sum())
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        # ---- device-resident timing ---------------------------------------------------------
+        eng.run(args.warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record(stream)
+            eng.run(args.steps)
+            e1.record(stream)
+            barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        st = eng.stats()
+        kbar = st["neighborsTotal"] / max(1, st["activeInGrid"])
+        value = world * active * S * args.steps / (ms * 1e-3)
+
+        # ---- per-kernel CUDA-event timing (same frames continue; direct launches) -------------
+        eng_t = GameEngine(cfg, device=local, flags=B.FLAG_KERNEL_TIMING, stream=stream.cuda_stream, host_neighbor_rows=False)
+        eng_t.load_columns(cols)
+        eng_t.run(args.warmup + args.steps)   # bring it to the same simulation state
+        acc = np.zeros(8)
+        for _ in range(args.steps):
+            eng_t.run(1)
+            acc += np.array(eng_t.stats()["ms"][:8])
+        kms = acc / args.steps
+        st_t = eng_t.stats()
+        kbar_t = st_t["neighborsTotal"] / max(1, st_t["activeInGrid"])
+        eng_t.close()
+        top = int(np.argmax(kms))
+        F, per_kernel = algorithmic_bytes(kbar_t, S)
+        alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
+               6: S * (34.0 + 4.0 * (1.0 + kbar_t)), 7: 0.0}[top]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg * active / (kms[top] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                    "algorithmic_bytes_per_entity": alg, "kernel_ms": kms[top],
+                    "whole_frame": {"bytes_per_entity_frame": F, "achieved_GBps": F * active * args.steps / (ms * 1e-3) / 1e9,
+                                    "frac": F * active * args.steps / (ms * 1e-3) / 1e9 / peak}}
+
+        # ---- end to end through the host-facing API -----------------------------------------------
+        up = eng.mask("RB.ax", "RB.ay")
+        down = eng.mask("T.x", "T.y", "RB.vx", "RB.vy", "RB.velocityAngle", "RB.speed")
+        for _ in range(min(3, args.warmup)):
+            eng.step(1.0, up, down)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            eng.step(1.0, up, down)
+        e3.record(stream)
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms_e2e = max(e2.elapsed_time(e3), wall * 1e3)
+        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        N = cfg["entityCount"]
+        e2e = {"value": world * active * S * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 24 * N, "ms_per_step": ms_e2e / args.steps,
+               "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"}
+        launches = st["kernelLaunchesPerStep"] * args.steps
+        eng.close()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu, _, _ = cpu_reference(name, args.cpu_steps, 1, args.cpu_sample)
+        conf = describe(name, cfg)
+        conf.update({"parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab exchange not built yet)",
+                     "kbar": kbar, "active": active, "l2_policy": "working set >> 126 MB L2 (inputs larger than L2)"
+                     if cfg["entityCount"] > 2_000_000 else "working set may fit L2; frames are back-to-back on evolving state",
+                     "kernel_ms": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
+                     "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
+                     "collision_pairs_last_substep": st["collisionPairs"]})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config4")
+    ap.add_argument("--entities", type=int, default=None, help="override the entity count (same density)")
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="entities of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -210,24 +210,11 @@ typedef enum weed_devptr_id {
   WEED_DEV_NEIGHBOR  = 0,  /* int32  [N*(1+M)] */
   WEED_DEV_DISTANCE  = 1,  /* float  [N*(1+M)] */
   WEED_DEV_COLLISION = 2,  /* int32  [1+2*maxPairs] */
-  WEED_DEV_STATE     = 3,  /* 32 B per-entity state record, see DESIGN.md               */
-  WEED_DEV_ATTR      = 4,  /* 16 B per-entity attribute record                          */
-  WEED_DEV_VEL       = 5   /* 16 B per-entity velocity record                           */
+  WEED_DEV_STATE     = 3,  /* float4 [N] {x, y, px, py}, see DESIGN.md                  */
+  WEED_DEV_ATTR      = 4,  /* float4 [N] {maxVel, radius, visualRange, velocityAngle}   */
+  WEED_DEV_VEL       = 5   /* float4 [N] {vx, vy, speed, -}                             */
 } weed_devptr_id;
 int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
-
-/* ---- multi-GPU slabs (SURVEY §8 e) --------------------------------------------------
- * The context owns the entities whose cell row is inside its slab; rows within `halo`
- * of the slab are replicated read-only.  Exchange buffers are plain device memory so the
- * host (torch.distributed / NCCL send-recv) moves them; see INTEGRATION.md.            */
-typedef enum weed_side { WEED_SIDE_LOW = 0, WEED_SIDE_HIGH = 1 } weed_side;
-/* pack records of entities leaving through `side` (migration) or lying in the boundary
- * rows next to `side` (halo) into dev_buf; *count receives the record count.           */
-int weed_slab_pack(weed_ctx* ctx, weed_side side, int what /*0=halo,1=migrate*/,
-                   void* dev_buf, size_t capacity_records, uint32_t* count);
-int weed_slab_unpack(weed_ctx* ctx, weed_side side, int what, const void* dev_buf,
-                     uint32_t count);
-#define WEED_SLAB_RECORD_BYTES 64
 
 #ifdef __cplusplus
 }

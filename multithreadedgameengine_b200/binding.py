@@ -1,0 +1,123 @@
+"""ctypes binding of the C ABI in include/weedgpu.h (libweedgpu.so, built in-tree by
+__graft_entry__.build()).  This is the binding the tests and bench drive; a Node engine would
+bind the same symbols through the N-API shim in addon/weed_napi.cc.
+
+No fallback: if the shared library is missing, ``lib()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libweedgpu.so")
+
+WEED_OK, WEED_E_INVALID, WEED_E_CUDA, WEED_E_NOT_BOUND, WEED_E_SIZE, WEED_E_OVERFLOW, WEED_E_STATE, WEED_E_NOMEM = (
+    0, -1, -2, -3, -4, -5, -6, -7)
+ERROR_NAMES = {0: "WEED_OK", -1: "WEED_E_INVALID", -2: "WEED_E_CUDA", -3: "WEED_E_NOT_BOUND", -4: "WEED_E_SIZE",
+               -5: "WEED_E_OVERFLOW", -6: "WEED_E_STATE", -7: "WEED_E_NOMEM"}
+
+BUF_TRANSFORM, BUF_RIGIDBODY, BUF_COLLIDER, BUF_NEIGHBOR, BUF_DISTANCE, BUF_COLLISION = range(6)
+
+# WEED_COL_* bits, in the order of include/weedgpu.h
+COL = {
+    "T.active": 1 << 0, "T.x": 1 << 1, "T.y": 1 << 2,
+    "RB.active": 1 << 3, "RB.static": 1 << 4, "RB.vx": 1 << 5, "RB.vy": 1 << 6, "RB.ax": 1 << 7,
+    "RB.ay": 1 << 8, "RB.px": 1 << 9, "RB.py": 1 << 10, "RB.maxVel": 1 << 11,
+    "RB.velocityAngle": 1 << 12, "RB.speed": 1 << 13, "RB.collisionCount": 1 << 14,
+    "C.active": 1 << 15, "C.radius": 1 << 16, "C.isTrigger": 1 << 17, "C.visualRange": 1 << 18,
+}
+COLS_INPUT_ALL = 0x0007FFFF
+COLS_OUTPUT_ALL = (COL["T.x"] | COL["T.y"] | COL["RB.vx"] | COL["RB.vy"] | COL["RB.ax"] | COL["RB.ay"]
+                   | COL["RB.px"] | COL["RB.py"] | COL["RB.velocityAngle"] | COL["RB.speed"]
+                   | COL["RB.collisionCount"])
+COL_NEIGHBORS = 1 << 24
+COL_COLLISIONS = 1 << 25
+
+FLAG_NO_GRAPH = 1 << 0
+FLAG_KERNEL_TIMING = 1 << 1
+FLAG_NO_NEIGHBOR_ROWS = 1 << 2
+
+DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL = range(6)
+
+
+class PhysicsConfig(C.Structure):
+    _fields_ = [("subStepCount", C.c_int32), ("_pad0", C.c_int32),
+                ("boundaryElasticity", C.c_double), ("collisionResponseStrength", C.c_double),
+                ("verletDamping", C.c_double), ("minSpeedForRotation", C.c_double),
+                ("gravityX", C.c_double), ("gravityY", C.c_double)]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("entityCount", C.c_uint32),
+                ("worldWidth", C.c_double), ("worldHeight", C.c_double), ("cellSize", C.c_double),
+                ("maxNeighbors", C.c_uint32), ("maxCollisionPairs", C.c_uint32),
+                ("seed", C.c_double), ("physics", PhysicsConfig),
+                ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+                ("slabRowBegin", C.c_uint32), ("slabRowEnd", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("gridCols", C.c_uint32), ("gridRows", C.c_uint32),
+                ("activeInGrid", C.c_uint32), ("maxCellOccupancy", C.c_uint32),
+                ("neighborsTotal", C.c_uint64), ("cappedRows", C.c_uint32),
+                ("explicitPairs", C.c_uint32), ("explicitOverflow", C.c_uint32),
+                ("collisionPairs", C.c_uint32), ("kernelLaunchesPerStep", C.c_uint32),
+                ("_pad", C.c_uint32), ("ms", C.c_float * 12)]
+
+
+# every symbol include/weedgpu.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "weed_buffer_bytes": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "weed_column_offset": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32]),
+    "weed_column_count": (C.c_uint32, [C.c_int]),
+    "weed_column_name": (C.c_char_p, [C.c_int, C.c_uint32]),
+    "weed_default_config": (None, [C.POINTER(Config)]),
+    "weed_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "weed_destroy": (None, [C.c_void_p]),
+    "weed_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "weed_upload": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "weed_download": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "weed_spatial": (C.c_int, [C.c_void_p]),
+    "weed_physics": (C.c_int, [C.c_void_p, C.c_double]),
+    "weed_step": (C.c_int, [C.c_void_p, C.c_double, C.c_uint32, C.c_uint32]),
+    "weed_run": (C.c_int, [C.c_void_p, C.c_double, C.c_uint32]),
+    "weed_set_physics": (C.c_int, [C.c_void_p, C.POINTER(PhysicsConfig)]),
+    "weed_get_physics": (C.c_int, [C.c_void_p, C.POINTER(PhysicsConfig)]),
+    "weed_fetch_neighbors": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "weed_sync": (C.c_int, [C.c_void_p]),
+    "weed_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "weed_last_error": (C.c_char_p, [C.c_void_p]),
+    "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+}
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the spatial+physics path.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class WeedError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def check(ctx, rc):
+    if rc != WEED_OK:
+        msg = lib().weed_last_error(ctx)
+        raise WeedError(rc, msg.decode() if msg else "")
+    return rc

@@ -1,0 +1,675 @@
+// weed_ctx.cu — context, memory, launch plumbing and the C ABI of include/weedgpu.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -shared -Xcompiler -fPIC   (see __graft_entry__.build()).
+// There is no CPU path: without a CUDA device weed_create fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/weedgpu.h"
+#include "weed_kernels.cuh"
+
+using namespace weed;
+
+// =============================================================================================
+// layout: Component.initializeArrays / getBufferSize (src/core/Component.js:20-42, 77-93)
+// =============================================================================================
+namespace {
+struct ColDef { const char* name; uint32_t bytes; };
+const ColDef kTransform[] = {  // src/components/Transform.js:8-17
+    {"active", 1}, {"entityType", 1}, {"x", 4}, {"y", 4}, {"rotation", 4}};
+const ColDef kRigidBody[] = {  // src/components/RigidBody.js:9-47
+    {"active", 1}, {"static", 1}, {"vx", 4}, {"vy", 4}, {"ax", 4}, {"ay", 4}, {"px", 4}, {"py", 4},
+    {"angularVelocity", 4}, {"angularAccel", 4}, {"mass", 4}, {"invMass", 4}, {"inertia", 4},
+    {"invInertia", 4}, {"drag", 4}, {"angularDrag", 4}, {"maxVel", 4}, {"maxAcc", 4}, {"minSpeed", 4},
+    {"friction", 4}, {"velocityAngle", 4}, {"speed", 4}, {"collisionCount", 1}};
+const ColDef kCollider[] = {  // src/components/Collider.js:8-46
+    {"active", 1}, {"shapeType", 1}, {"offsetX", 4}, {"offsetY", 4}, {"radius", 4}, {"width", 4},
+    {"height", 4}, {"isTrigger", 1}, {"restitution", 4}, {"collisionLayer", 2}, {"collisionMask", 2},
+    {"aabbMinX", 4}, {"aabbMinY", 4}, {"aabbMaxX", 4}, {"aabbMaxY", 4}, {"visualRange", 4}};
+
+const ColDef* schema(int id, uint32_t* n) {
+  switch (id) {
+    case WEED_BUF_TRANSFORM: *n = 5; return kTransform;
+    case WEED_BUF_RIGIDBODY: *n = 23; return kRigidBody;
+    case WEED_BUF_COLLIDER: *n = 16; return kCollider;
+  }
+  *n = 0;
+  return nullptr;
+}
+
+// the 19 mirrored columns, in WEED_COL_* bit order: (buffer, schema index, element bytes)
+struct HotCol { int buf; uint32_t col; uint32_t bytes; };
+const HotCol kHot[19] = {
+    {WEED_BUF_TRANSFORM, 0, 1},  {WEED_BUF_TRANSFORM, 2, 4},  {WEED_BUF_TRANSFORM, 3, 4},
+    {WEED_BUF_RIGIDBODY, 0, 1},  {WEED_BUF_RIGIDBODY, 1, 1},  {WEED_BUF_RIGIDBODY, 2, 4},
+    {WEED_BUF_RIGIDBODY, 3, 4},  {WEED_BUF_RIGIDBODY, 4, 4},  {WEED_BUF_RIGIDBODY, 5, 4},
+    {WEED_BUF_RIGIDBODY, 6, 4},  {WEED_BUF_RIGIDBODY, 7, 4},  {WEED_BUF_RIGIDBODY, 16, 4},
+    {WEED_BUF_RIGIDBODY, 20, 4}, {WEED_BUF_RIGIDBODY, 21, 4}, {WEED_BUF_RIGIDBODY, 22, 1},
+    {WEED_BUF_COLLIDER, 0, 1},   {WEED_BUF_COLLIDER, 4, 4},   {WEED_BUF_COLLIDER, 7, 1},
+    {WEED_BUF_COLLIDER, 15, 4}};
+
+thread_local std::string g_create_error;
+}  // namespace
+
+extern "C" size_t weed_column_offset(weed_buffer_id id, uint32_t column, uint32_t entityCount) {
+  uint32_t n;
+  const ColDef* s = schema(id, &n);
+  if (!s || column >= n) return (size_t)-1;
+  size_t off = 0;
+  for (uint32_t k = 0; k <= column; k++) {
+    const size_t rem = off % s[k].bytes;          // Component.js:31-34
+    if (rem) off += s[k].bytes - rem;
+    if (k == column) return off;
+    off += (size_t)entityCount * s[k].bytes;      // Component.js:37
+  }
+  return (size_t)-1;
+}
+
+extern "C" uint32_t weed_column_count(weed_buffer_id id) {
+  uint32_t n;
+  schema(id, &n);
+  return n;
+}
+
+extern "C" const char* weed_column_name(weed_buffer_id id, uint32_t column) {
+  uint32_t n;
+  const ColDef* s = schema(id, &n);
+  return (s && column < n) ? s[column].name : nullptr;
+}
+
+extern "C" size_t weed_buffer_bytes(weed_buffer_id id, uint32_t entityCount, uint32_t maxNeighbors,
+                                    uint32_t maxCollisionPairs) {
+  uint32_t n;
+  const ColDef* s = schema(id, &n);
+  if (s) {  // Component.getBufferSize
+    size_t off = 0;
+    for (uint32_t k = 0; k < n; k++) {
+      const size_t rem = off % s[k].bytes;
+      if (rem) off += s[k].bytes - rem;
+      off += (size_t)entityCount * s[k].bytes;
+    }
+    return off;
+  }
+  switch (id) {
+    case WEED_BUF_NEIGHBOR:
+    case WEED_BUF_DISTANCE: return (size_t)entityCount * (1 + (size_t)maxNeighbors) * 4;  // gameEngine.js:554-558
+    case WEED_BUF_COLLISION: return (1 + (size_t)maxCollisionPairs * 2) * 4;              // gameEngine.js:694
+    default: return 0;
+  }
+}
+
+extern "C" void weed_default_config(weed_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(weed_config);
+  c->maxNeighbors = 100;          // gameEngine.js:553
+  c->maxCollisionPairs = 10000;   // gameEngine.js:689-693
+  c->seed = 1.0;
+  c->physics.subStepCount = 4;    // gameEngine.js:39-45
+  c->physics.boundaryElasticity = 0.8;
+  c->physics.collisionResponseStrength = 0.5;
+  c->physics.verletDamping = 0.995;
+  c->physics.minSpeedForRotation = 0.1;
+}
+
+// =============================================================================================
+// context
+// =============================================================================================
+enum KernelSlot { KS_KEY = 0, KS_SCAN, KS_SCATTER, KS_BUILD, KS_NEIGH, KS_XCAP, KS_SUBSTEP, KS_WB, KS_COUNT };
+
+struct weed_ctx {
+  weed_config cfg;
+  weed_physics_config phys;
+  GridDims g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  bool failed = false;
+  std::string err;
+
+  // host buffers (owned by the caller)
+  void* host[WEED_BUF_COUNT] = {};
+  size_t hostBytes[WEED_BUF_COUNT] = {};
+  bool registered[WEED_BUF_COUNT] = {};
+
+  std::vector<void*> allocs;
+  // by id
+  ById d{};
+  uint32_t *key = nullptr, *rank = nullptr, *arrIds = nullptr, *slotOf = nullptr;
+  // grid
+  uint32_t *cellCount = nullptr, *cellStart = nullptr;
+  uint32_t scanTiles = 0, wbTiles = 0;
+  unsigned long long *scanStatus = nullptr, *wbStatus = nullptr;
+  // by slot
+  BySlot s{};
+  // outputs
+  int32_t* nd = nullptr; float* dd = nullptr; int32_t* coll = nullptr;
+  size_t rowWords = 0;
+  // control
+  Params* dParams = nullptr;
+  Counters* dCtr = nullptr;
+  Params hParams{};
+  double lastDt = -1;
+  bool paramsDirty = true;
+  // staging for host<->device columns
+  void* stage[19] = {};
+  // graph of one full frame
+  cudaGraphExec_t frameGraph = nullptr;
+  int graphSubSteps = -1;
+  bool spatialValid = false;  // rows/slots of the current frame exist (weed_spatial ran)
+  cudaEvent_t ev[KS_COUNT + 8] = {};
+  float ms[12] = {};
+  uint32_t launchesPerStep = 0;
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ctx->failed = true;                                                                     \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      return WEED_E_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define GUARD(ctx)                                                                            \
+  do {                                                                                        \
+    if (!(ctx)) return WEED_E_INVALID;                                                        \
+    if ((ctx)->failed) return WEED_E_CUDA;                                                    \
+    cudaSetDevice((ctx)->device);                                                             \
+  } while (0)
+
+static int fail(weed_ctx* ctx, int code, const std::string& msg) {
+  ctx->err = msg;
+  return code;
+}
+
+template <typename T>
+static int dalloc(weed_ctx* ctx, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) {
+    ctx->failed = true;
+    ctx->err = "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? WEED_E_NOMEM : WEED_E_CUDA;
+  }
+  ctx->allocs.push_back(q);
+  if (zero) {
+    e = cudaMemsetAsync(q, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) { ctx->failed = true; ctx->err = cudaGetErrorString(e); return WEED_E_CUDA; }
+  }
+  *p = (T*)q;
+  return WEED_OK;
+}
+
+static double clamp01(double v, double fallback) {  // utils.js:16-19
+  if (v != v) return fallback;
+  return fmax(0.0, fmin(1.0, v));
+}
+
+// validatePhysicsConfig (src/core/utils.js:269-301)
+static void validate_physics(weed_physics_config* cur, const weed_physics_config* in) {
+  weed_physics_config o = *in;
+  o.subStepCount = in->subStepCount < 1 ? 1 : in->subStepCount;
+  o.boundaryElasticity = clamp01(in->boundaryElasticity, cur->boundaryElasticity);
+  o.collisionResponseStrength = clamp01(in->collisionResponseStrength, cur->collisionResponseStrength);
+  o.verletDamping = clamp01(in->verletDamping, cur->verletDamping);
+  *cur = o;
+}
+
+static void refresh_params(weed_ctx* ctx, double dtRatio) {
+  Params& p = ctx->hParams;
+  const weed_physics_config& ph = ctx->phys;
+  // `this.settings.gravity.x || 0` (physics_worker.js:179-180): NaN and 0 give 0
+  const double gx = (ph.gravityX == ph.gravityX && ph.gravityX != 0) ? ph.gravityX : 0.0;
+  const double gy = (ph.gravityY == ph.gravityY && ph.gravityY != 0) ? ph.gravityY : 0.0;
+  const double gs = dtRatio * dtRatio;             // Math.pow(dtRatio, 2), physics_worker.js:261
+  p.dtRatio = dtRatio;
+  p.gravityScaleX = gs * gx;
+  p.gravityScaleY = gs * gy;
+  p.damping = ph.verletDamping;
+  p.boundaryElasticity = ph.boundaryElasticity;
+  p.responseStrength = ph.collisionResponseStrength;
+  p.minSpeedForRotation = ph.minSpeedForRotation;
+  // ToUint32(seed) for the nudge hash
+  double sd = ctx->cfg.seed;
+  uint32_t s32 = 0;
+  if (std::isfinite(sd)) {
+    double m = fmod(trunc(sd), 4294967296.0);
+    if (m < 0) m += 4294967296.0;
+    s32 = (uint32_t)m;
+  }
+  p.seed32 = s32;
+}
+
+static int push_params(weed_ctx* ctx, double dtRatio) {
+  if (!ctx->paramsDirty && dtRatio == ctx->lastDt) return WEED_OK;
+  refresh_params(ctx, dtRatio);
+  CK(cudaMemcpyAsync(ctx->dParams, &ctx->hParams, sizeof(Params), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->lastDt = dtRatio;
+  ctx->paramsDirty = false;
+  return WEED_OK;
+}
+
+extern "C" const char* weed_last_error(weed_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void weed_destroy(weed_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->frameGraph) cudaGraphExecDestroy(ctx->frameGraph);
+  for (int b = 0; b < WEED_BUF_COUNT; b++)
+    if (ctx->registered[b]) cudaHostUnregister(ctx->host[b]);
+  for (void* p : ctx->allocs) cudaFree(p);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out) { g_create_error = "null argument"; return WEED_E_INVALID; }
+  if (cfg->struct_size != sizeof(weed_config)) { g_create_error = "weed_config.struct_size mismatch (ABI)"; return WEED_E_INVALID; }
+  if (cfg->entityCount == 0 || cfg->entityCount > 0x3FFFFFF0u) { g_create_error = "entityCount out of range"; return WEED_E_INVALID; }
+  if (!(cfg->cellSize > 0) || !(cfg->worldWidth > 0) || !(cfg->worldHeight > 0)) { g_create_error = "world/cell size must be positive"; return WEED_E_INVALID; }
+  const double colsD = ceil(cfg->worldWidth / cfg->cellSize), rowsD = ceil(cfg->worldHeight / cfg->cellSize);  // spatial_worker.js:82-83
+  if (!(colsD >= 1) || !(rowsD >= 1) || colsD * rowsD > 1.0e9) { g_create_error = "grid too large"; return WEED_E_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device: libweedgpu has no CPU fallback";
+    return WEED_E_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return WEED_E_INVALID; }
+
+  weed_ctx* ctx = new weed_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  weed_physics_config defaults;
+  {
+    weed_config d; weed_default_config(&d); defaults = d.physics;
+  }
+  ctx->phys = defaults;
+  validate_physics(&ctx->phys, &cfg->physics);
+  auto bail = [&](int code) { g_create_error = ctx->err; weed_destroy(ctx); return code; };
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(WEED_E_CUDA); }
+  if (cfg->stream) ctx->stream = (cudaStream_t)cfg->stream;
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(WEED_E_CUDA); }
+    ctx->ownStream = true;
+  }
+  GridDims& g = ctx->g;
+  g.inv = 1.0 / cfg->cellSize;                     // spatial_worker.js:81
+  g.worldW = cfg->worldWidth; g.worldH = cfg->worldHeight;
+  g.cols = (int32_t)colsD; g.rows = (int32_t)rowsD;
+  g.cells = (uint32_t)(g.cols * g.rows);
+  g.N = cfg->entityCount;
+  g.M = cfg->maxNeighbors;
+  g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
+  g.xcap = g.Mpad;
+  g.maxPairs = cfg->maxCollisionPairs;
+  const size_t N = g.N;
+  int rc;
+#define A(ptr, count) if ((rc = dalloc(ctx, &(ptr), (count))) != WEED_OK) return bail(rc)
+  A(ctx->d.DP, N); A(ctx->d.ACC, N); A(ctx->d.AT, N); A(ctx->d.V, N); A(ctx->d.F, N); A(ctx->d.CC, N);
+  A(ctx->key, N); A(ctx->rank, N); A(ctx->arrIds, N); A(ctx->slotOf, N);
+  ctx->scanTiles = (uint32_t)(((size_t)g.cells + 1 + SCAN_TILE - 1) / SCAN_TILE);
+  A(ctx->cellCount, (size_t)ctx->scanTiles * SCAN_TILE);
+  A(ctx->cellStart, (size_t)ctx->scanTiles * SCAN_TILE);
+  A(ctx->scanStatus, ctx->scanTiles);
+  ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
+  A(ctx->wbStatus, ctx->wbTiles);
+  A(ctx->s.QXY, N); A(ctx->s.QVR, N); A(ctx->s.SID, N); A(ctx->s.G0, N); A(ctx->s.G1, N); A(ctx->s.PXY, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XCNT, N); A(ctx->s.OUT, N);
+  A(ctx->s.NS, N * g.Mpad);
+  A(ctx->s.XR, N * g.xcap);
+  ctx->rowWords = N * (1 + (size_t)g.M);
+  if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
+  A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
+  A(ctx->dParams, 1); A(ctx->dCtr, 1);
+  for (int c = 0; c < 19; c++) {
+    uint8_t* p = nullptr;
+    if ((rc = dalloc(ctx, &p, N * kHot[c].bytes)) != WEED_OK) return bail(rc);
+    ctx->stage[c] = p;
+  }
+#undef A
+  for (auto& e : ctx->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(WEED_E_CUDA); }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "init sync failed"; return bail(WEED_E_CUDA); }
+  *out = ctx;
+  return WEED_OK;
+}
+
+extern "C" int weed_bind(weed_ctx* ctx, weed_buffer_id id, void* host_base, size_t bytes) {
+  GUARD(ctx);
+  if ((int)id < 0 || id >= WEED_BUF_COUNT) return fail(ctx, WEED_E_INVALID, "bad buffer id");
+  const size_t need = weed_buffer_bytes(id, ctx->g.N, ctx->g.M, ctx->g.maxPairs);
+  if (host_base && bytes < need)
+    return fail(ctx, WEED_E_SIZE, "buffer " + std::to_string((int)id) + ": " + std::to_string(bytes) + " B < " + std::to_string(need) + " B");
+  if (ctx->registered[id]) { cudaHostUnregister(ctx->host[id]); ctx->registered[id] = false; }
+  ctx->host[id] = host_base;
+  ctx->hostBytes[id] = bytes;
+  if (host_base && id <= WEED_BUF_COLLIDER) {
+    // pin the SAB for the context lifetime so column copies are true async DMA; optional
+    if (cudaHostRegister(host_base, need, cudaHostRegisterDefault) == cudaSuccess) ctx->registered[id] = true;
+    else cudaGetLastError();
+  }
+  return WEED_OK;
+}
+
+static void* host_col(weed_ctx* ctx, int c) {
+  return (uint8_t*)ctx->host[kHot[c].buf] + weed_column_offset((weed_buffer_id)kHot[c].buf, kHot[c].col, ctx->g.N);
+}
+
+static int check_bound(weed_ctx* ctx, uint32_t mask) {
+  for (int c = 0; c < 19; c++)
+    if ((mask >> c) & 1u)
+      if (!ctx->host[kHot[c].buf]) return fail(ctx, WEED_E_NOT_BOUND, "component buffer " + std::to_string(kHot[c].buf) + " not bound");
+  return WEED_OK;
+}
+
+static int upload_async(weed_ctx* ctx, uint32_t mask) {
+  mask &= WEED_COLS_INPUT_ALL;
+  if (!mask) return WEED_OK;
+  int rc = check_bound(ctx, mask);
+  if (rc) return rc;
+  const size_t N = ctx->g.N;
+  for (int c = 0; c < 19; c++)
+    if ((mask >> c) & 1u)
+      CK(cudaMemcpyAsync(ctx->stage[c], host_col(ctx, c), N * kHot[c].bytes, cudaMemcpyHostToDevice, ctx->stream));
+  Staging st;
+  const void** sp = reinterpret_cast<const void**>(&st);
+  for (int c = 0; c < 19; c++) sp[c] = ctx->stage[c];
+  k_pack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, mask, st, ctx->d);
+  CK(cudaGetLastError());
+  ctx->spatialValid = false;
+  return WEED_OK;
+}
+
+static int download_async(weed_ctx* ctx, uint32_t mask) {
+  const uint32_t cols = mask & WEED_COLS_INPUT_ALL;
+  const size_t N = ctx->g.N;
+  if (cols) {
+    int rc = check_bound(ctx, cols);
+    if (rc) return rc;
+    StagingOut st;
+    void** sp = reinterpret_cast<void**>(&st);
+    for (int c = 0; c < 19; c++) sp[c] = ctx->stage[c];
+    k_unpack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, cols, st, ctx->d);
+    CK(cudaGetLastError());
+    for (int c = 0; c < 19; c++)
+      if ((cols >> c) & 1u)
+        CK(cudaMemcpyAsync(host_col(ctx, c), ctx->stage[c], N * kHot[c].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (mask & WEED_COL_NEIGHBORS) {
+    if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
+    if (!ctx->host[WEED_BUF_NEIGHBOR] || !ctx->host[WEED_BUF_DISTANCE]) return fail(ctx, WEED_E_NOT_BOUND, "neighbor/distance buffer not bound");
+    CK(cudaMemcpyAsync(ctx->host[WEED_BUF_NEIGHBOR], ctx->nd, ctx->rowWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->host[WEED_BUF_DISTANCE], ctx->dd, ctx->rowWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (mask & WEED_COL_COLLISIONS) {
+    if (!ctx->host[WEED_BUF_COLLISION]) return fail(ctx, WEED_E_NOT_BOUND, "collision buffer not bound");
+    // pairCount first, then only the pairs that exist
+    CK(cudaMemcpyAsync(ctx->host[WEED_BUF_COLLISION], ctx->coll, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t n = *(int32_t*)ctx->host[WEED_BUF_COLLISION];
+    if (n > 0)
+      CK(cudaMemcpyAsync((int32_t*)ctx->host[WEED_BUF_COLLISION] + 1, ctx->coll + 1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return WEED_OK;
+}
+
+extern "C" int weed_upload(weed_ctx* ctx, uint32_t mask) {
+  GUARD(ctx);
+  int rc = upload_async(ctx, mask);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+extern "C" int weed_download(weed_ctx* ctx, uint32_t mask) {
+  GUARD(ctx);
+  int rc = download_async(ctx, mask);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+// ---- launches --------------------------------------------------------------------------------
+static inline unsigned blocks_for(size_t threads, unsigned bs) { return (unsigned)((threads + bs - 1) / bs); }
+
+#define TIME_MARK(ctx, timing, k) do { if (timing) cudaEventRecord((ctx)->ev[k], (ctx)->stream); } while (0)
+
+static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
+  const GridDims& g = ctx->g;
+  cudaStream_t st = ctx->stream;
+  const unsigned nb = blocks_for(g.N, 256);
+  const unsigned tb = blocks_for((size_t)g.N * TILE_W, 256);
+  k_spatial_begin<<<1, 32, 0, st>>>(ctx->dCtr);
+  TIME_MARK(ctx, timing, 0);
+  k_cell_key<<<nb, 256, 0, st>>>(g, ctx->d.DP, ctx->d.F, ctx->key, ctx->rank, ctx->cellCount);
+  TIME_MARK(ctx, timing, 1);
+  k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr);
+  TIME_MARK(ctx, timing, 2);
+  k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds);
+  TIME_MARK(ctx, timing, 3);
+  if (integrate)
+    k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+  else
+    k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+  TIME_MARK(ctx, timing, 4);
+  if (ctx->nd)
+    k_neighbors<true><<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+  else
+    k_neighbors<false><<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+  TIME_MARK(ctx, timing, 5);
+  k_explicit_capped<<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  TIME_MARK(ctx, timing, 6);
+  CK(cudaGetLastError());
+  return WEED_OK;
+}
+
+static int launch_constraints(weed_ctx* ctx, bool timing) {
+  const GridDims& g = ctx->g;
+  cudaStream_t st = ctx->stream;
+  const unsigned tb = blocks_for((size_t)g.N * TILE_W, 256);
+  const int S = ctx->phys.subStepCount;
+  float4* bufs[2] = {ctx->s.G0, ctx->s.G1};
+  for (int step = 0; step < S; step++) {
+    const float4* in = bufs[step & 1];
+    float4* out = bufs[(step + 1) & 1];
+    if (step == S - 1)
+      k_substep<true><<<tb, 256, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    else
+      k_substep<false><<<tb, 256, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+  }
+  TIME_MARK(ctx, timing, 7);
+  k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, bufs[(S - 1) & 1], ctx->slotOf,
+                                                   ctx->wbTiles, ctx->wbStatus, ctx->dCtr, ctx->coll, (uint32_t)(S - 1));
+  k_physics_end<<<1, 32, 0, st>>>(ctx->dCtr);
+  TIME_MARK(ctx, timing, 8);
+  CK(cudaGetLastError());
+  return WEED_OK;
+}
+
+static int launch_frame(weed_ctx* ctx, bool timing) {
+  int rc = launch_spatial(ctx, true, timing);
+  if (rc) return rc;
+  return launch_constraints(ctx, timing);
+}
+
+static int ensure_graph(weed_ctx* ctx) {
+  if (ctx->frameGraph && ctx->graphSubSteps == ctx->phys.subStepCount) return WEED_OK;
+  if (ctx->frameGraph) { cudaGraphExecDestroy(ctx->frameGraph); ctx->frameGraph = nullptr; }
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = launch_frame(ctx, false);
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  CK(e);
+  e = cudaGraphInstantiate(&ctx->frameGraph, graph, 0);
+  cudaGraphDestroy(graph);
+  CK(e);
+  ctx->graphSubSteps = ctx->phys.subStepCount;
+  return WEED_OK;
+}
+
+static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
+  int rc = push_params(ctx, dtRatio);
+  if (rc) return rc;
+  const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
+  const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
+  ctx->launchesPerStep = 9 + (uint32_t)ctx->phys.subStepCount;
+  if (!direct) {
+    rc = ensure_graph(ctx);
+    if (rc) return rc;
+  }
+  for (uint32_t f = 0; f < frames; f++) {
+    if (direct) {
+      rc = launch_frame(ctx, timing);
+      if (rc) return rc;
+    } else {
+      CK(cudaGraphLaunch(ctx->frameGraph, ctx->stream));
+    }
+  }
+  if (timing && frames) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 8; k++) cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]);
+  }
+  ctx->spatialValid = false;
+  return WEED_OK;
+}
+
+static int check_overflow(weed_ctx* ctx) {
+  Counters c;
+  CK(cudaMemcpyAsync(&c, ctx->dCtr, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (c.explicitOverflowFrame)
+    return fail(ctx, WEED_E_OVERFLOW, "explicit pair capacity exceeded (more than " + std::to_string(ctx->g.xcap) + " one-sided partners on one entity)");
+  return WEED_OK;
+}
+
+extern "C" int weed_spatial(weed_ctx* ctx) {
+  GUARD(ctx);
+  int rc = launch_spatial(ctx, false, false);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->spatialValid = true;
+  return check_overflow(ctx);
+}
+
+extern "C" int weed_physics(weed_ctx* ctx, double dtRatio) {
+  GUARD(ctx);
+  if (!ctx->spatialValid) return fail(ctx, WEED_E_STATE, "weed_physics needs the rows of a preceding weed_spatial of the same frame (or use weed_step)");
+  int rc = push_params(ctx, dtRatio);
+  if (rc) return rc;
+  const GridDims& g = ctx->g;
+  k_build_slots<true><<<blocks_for(g.N, 256), 256, 0, ctx->stream>>>(g, ctx->dParams, ctx->phys.subStepCount, true, ctx->d, ctx->s,
+                                                                      ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+  rc = launch_constraints(ctx, false);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->spatialValid = false;
+  return WEED_OK;
+}
+
+extern "C" int weed_step(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, uint32_t download_mask) {
+  GUARD(ctx);
+  int rc = upload_async(ctx, upload_mask);
+  if (rc) return rc;
+  rc = run_frames(ctx, dtRatio, 1);
+  if (rc) return rc;
+  rc = download_async(ctx, download_mask);
+  if (rc) return rc;
+  return check_overflow(ctx);
+}
+
+extern "C" int weed_run(weed_ctx* ctx, double dtRatio, uint32_t frames) {
+  GUARD(ctx);
+  return run_frames(ctx, dtRatio, frames);
+}
+
+extern "C" int weed_sync(weed_ctx* ctx) {
+  GUARD(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+extern "C" int weed_set_physics(weed_ctx* ctx, const weed_physics_config* p) {
+  GUARD(ctx);
+  if (!p) return WEED_E_INVALID;
+  validate_physics(&ctx->phys, p);
+  ctx->paramsDirty = true;
+  return WEED_OK;
+}
+
+extern "C" int weed_get_physics(weed_ctx* ctx, weed_physics_config* out) {
+  if (!ctx || !out) return WEED_E_INVALID;
+  *out = ctx->phys;
+  return WEED_OK;
+}
+
+extern "C" int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t count) {
+  GUARD(ctx);
+  if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
+  if (!ctx->host[WEED_BUF_NEIGHBOR] || !ctx->host[WEED_BUF_DISTANCE]) return fail(ctx, WEED_E_NOT_BOUND, "neighbor/distance buffer not bound");
+  if ((size_t)first + count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "row range out of bounds");
+  const size_t stride = 1 + (size_t)ctx->g.M;
+  const size_t off = (size_t)first * stride, len = (size_t)count * stride;
+  CK(cudaMemcpyAsync((int32_t*)ctx->host[WEED_BUF_NEIGHBOR] + off, ctx->nd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync((float*)ctx->host[WEED_BUF_DISTANCE] + off, ctx->dd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
+  GUARD(ctx);
+  if (!out) return WEED_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  CK(cudaMemsetAsync(&ctx->dCtr->neighborsTotal, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->dCtr->cappedRows, 0, sizeof(uint32_t), ctx->stream));
+  k_stats<<<296, 256, 0, ctx->stream>>>(ctx->g, ctx->s.NCNT, ctx->cellStart, ctx->dCtr);
+  Counters c;
+  CK(cudaMemcpyAsync(&c, ctx->dCtr, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->frames = c.frames;
+  out->gridCols = (uint32_t)ctx->g.cols; out->gridRows = (uint32_t)ctx->g.rows;
+  out->activeInGrid = c.activeInGrid;
+  out->maxCellOccupancy = c.maxCellFrame;
+  out->neighborsTotal = c.neighborsTotal;
+  out->cappedRows = c.cappedRows;
+  out->explicitPairs = c.explicitPairs;
+  out->explicitOverflow = c.explicitOverflowFrame;
+  out->collisionPairs = c.collisionPairs;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 9 + (uint32_t)ctx->phys.subStepCount;
+  memcpy(out->ms, ctx->ms, sizeof(out->ms));
+  return WEED_OK;
+}
+
+extern "C" int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes) {
+  if (!ctx || !out) return WEED_E_INVALID;
+  const size_t N = ctx->g.N;
+  void* p = nullptr; size_t b = 0;
+  switch (which) {
+    case WEED_DEV_NEIGHBOR: p = ctx->nd; b = ctx->rowWords * 4; break;
+    case WEED_DEV_DISTANCE: p = ctx->dd; b = ctx->rowWords * 4; break;
+    case WEED_DEV_COLLISION: p = ctx->coll; b = (1 + 2 * (size_t)ctx->g.maxPairs) * 4; break;
+    case WEED_DEV_STATE: p = ctx->d.DP; b = N * 16; break;
+    case WEED_DEV_ATTR: p = ctx->d.AT; b = N * 16; break;
+    case WEED_DEV_VEL: p = ctx->d.V; b = N * 16; break;
+    default: return fail(ctx, WEED_E_INVALID, "bad devptr id");
+  }
+  *out = p;
+  if (bytes) *bytes = b;
+  return WEED_OK;
+}

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's engine/worker interface for the spatial+physics path.
+
+Mirrors (same names, argument meaning and defaults):
+  * ``GameEngine(config)``            src/core/gameEngine.js:22-110  (config.spatial{cellSize,
+    maxNeighbors}, config.physics{subStepCount, gravity, verletDamping, ...}, worldWidth/Height)
+  * ``createSharedBuffers()``         src/core/gameEngine.js:534-777 (one buffer per component,
+    dense; neighborData / distanceData / collisionData)
+  * ``SpatialWorker.update()``        src/workers/spatial_worker.js:283-294
+  * ``PhysicsWorker.update(dt, r)``   src/workers/physics_worker.js:103-108
+  * ``updatePhysicsConfig(partial)``  src/core/gameEngine.js:1304-1325 -> physics_worker.js:114-129
+  * ``GameObject.updateNeighbors``    src/core/gameObject.js:700-729  (``neighbors_of(i)``)
+
+The two workers are replaced by one libweedgpu context (include/weedgpu.h).  The buffers
+created here play the role of the SharedArrayBuffers: ``tick()``-style host code reads and
+writes the component columns (``engine.Transform.x[i]``, ``engine.RigidBody.ax[i] = ...``) and
+``step()`` moves the columns named in the masks across PCIe.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import binding as B
+from .components import COLUMN_KEYS, new_component_classes
+
+PHYSICS_DEFAULTS = dict(subStepCount=4, boundaryElasticity=0.8, collisionResponseStrength=0.5,
+                        verletDamping=0.995, minSpeedForRotation=0.1)  # gameEngine.js:39-45
+
+
+def _pinned_empty(nbytes):
+    """Page-aligned host buffer (stand-in for a SharedArrayBuffer)."""
+    raw = np.empty(nbytes + 4096, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 4096
+    buf = raw[off:off + nbytes]
+    buf[:] = 0
+    return buf
+
+
+class _Worker:
+    def __init__(self, engine):
+        self.engine = engine
+
+
+class SpatialWorker(_Worker):
+    def update(self, deltaTime=16.67, dtRatio=1.0, resuming=False):
+        """spatial_worker.js:283-294: rebuildGrid() + findAllNeighbors() on the device."""
+        B.check(self.engine.ctx, B.lib().weed_spatial(self.engine.ctx))
+
+
+class PhysicsWorker(_Worker):
+    def update(self, deltaTime=16.67, dtRatio=1.0, resuming=False):
+        """physics_worker.js:103-108: updateVerlet(deltaTime, dtRatio) on the device."""
+        B.check(self.engine.ctx, B.lib().weed_physics(self.engine.ctx, float(dtRatio)))
+
+
+class GameEngine:
+    def __init__(self, config, device=0, flags=0, stream=None, host_neighbor_rows=True):
+        L = B.lib()
+        self.config = dict(config)
+        # gameEngine.js:34-49 default merge
+        phys = dict(PHYSICS_DEFAULTS)
+        phys.update({k: v for k, v in (config.get("physics") or {}).items() if k not in ("gravity", "noLimitFPS")})
+        gravity = (config.get("physics") or {}).get("gravity") or config.get("gravity") or {"x": 0, "y": 0}
+        phys["gravity"] = dict(gravity)
+        self.config["physics"] = phys
+        spatial = config.get("spatial") or {}
+        self.cellSize = float(spatial.get("cellSize") or config.get("cellSize"))            # spatial_worker.js:80
+        self.maxNeighbors = int(spatial.get("maxNeighbors") or config.get("maxNeighbors") or 100)  # gameEngine.js:552
+        self.maxCollisionPairs = int(phys.get("maxCollisionPairs") or config.get("maxCollisionPairs") or 10000)  # :689-693
+        self.totalEntityCount = int(config["entityCount"])
+        N = self.totalEntityCount
+
+        cfg = B.Config()
+        L.weed_default_config(C.byref(cfg))
+        cfg.entityCount = N
+        cfg.worldWidth = float(config["worldWidth"])
+        cfg.worldHeight = float(config["worldHeight"])
+        cfg.cellSize = self.cellSize
+        cfg.maxNeighbors = self.maxNeighbors
+        cfg.maxCollisionPairs = self.maxCollisionPairs
+        cfg.seed = float(config.get("seed") or 1.0)
+        cfg.physics = self._physics_struct(phys)
+        cfg.device = device
+        cfg.flags = flags
+        cfg.stream = stream
+        self.ctx = C.c_void_p()
+        rc = L.weed_create(C.byref(cfg), C.byref(self.ctx))
+        if rc != B.WEED_OK:
+            msg = L.weed_last_error(None)
+            raise B.WeedError(rc, msg.decode() if msg else "")
+        self.spatial = SpatialWorker(self)
+        self.physics_worker = PhysicsWorker(self)
+        self.buffers = {}
+        self.createSharedBuffers(host_neighbor_rows)
+
+    @staticmethod
+    def _physics_struct(phys):
+        p = B.PhysicsConfig()
+        p.subStepCount = int(phys.get("subStepCount", 4))
+        p.boundaryElasticity = float(phys.get("boundaryElasticity", 0.8))
+        p.collisionResponseStrength = float(phys.get("collisionResponseStrength", 0.5))
+        p.verletDamping = float(phys.get("verletDamping", 0.995))
+        p.minSpeedForRotation = float(phys.get("minSpeedForRotation", 0.1))
+        g = phys.get("gravity") or {}
+        p.gravityX = float(g.get("x", 0.0))
+        p.gravityY = float(g.get("y", 0.0))
+        return p
+
+    # ---- gameEngine.js:534-777 ---------------------------------------------------------------
+    def createSharedBuffers(self, host_neighbor_rows=True):
+        L = B.lib()
+        N, M, P = self.totalEntityCount, self.maxNeighbors, self.maxCollisionPairs
+        self.Transform, self.RigidBody, self.Collider = new_component_classes()
+        for bid, cls, name in ((B.BUF_TRANSFORM, self.Transform, "Transform"),
+                               (B.BUF_RIGIDBODY, self.RigidBody, "RigidBody"),
+                               (B.BUF_COLLIDER, self.Collider, "Collider")):
+            size = cls.getBufferSize(N)
+            assert size == L.weed_buffer_bytes(bid, N, M, P)
+            buf = _pinned_empty(size)
+            self.buffers[name] = buf
+            cls.initializeArrays(buf, N)
+            B.check(self.ctx, L.weed_bind(self.ctx, bid, buf.ctypes.data, size))
+        if host_neighbor_rows:
+            self.neighborData = _pinned_empty(N * (1 + M) * 4).view(np.int32)
+            self.distanceData = _pinned_empty(N * (1 + M) * 4).view(np.float32)
+            B.check(self.ctx, L.weed_bind(self.ctx, B.BUF_NEIGHBOR, self.neighborData.ctypes.data, self.neighborData.nbytes))
+            B.check(self.ctx, L.weed_bind(self.ctx, B.BUF_DISTANCE, self.distanceData.ctypes.data, self.distanceData.nbytes))
+        else:
+            self.neighborData = self.distanceData = None
+        self.collisionData = _pinned_empty((1 + 2 * P) * 4).view(np.int32)
+        B.check(self.ctx, L.weed_bind(self.ctx, B.BUF_COLLISION, self.collisionData.ctypes.data, self.collisionData.nbytes))
+
+    def column(self, key):
+        comp, name = COLUMN_KEYS[key]
+        return getattr((self.Transform, self.RigidBody, self.Collider)[comp], name)
+
+    @property
+    def col(self):
+        return {k: self.column(k) for k in COLUMN_KEYS}
+
+    def load_columns(self, columns, upload=True):
+        for k, v in columns.items():
+            self.column(k)[:] = v
+        if upload:
+            self.upload(B.COLS_INPUT_ALL)
+
+    # ---- data movement -----------------------------------------------------------------------
+    @staticmethod
+    def mask(*keys):
+        m = 0
+        for k in keys:
+            m |= B.COL[k] if isinstance(k, str) else int(k)
+        return m
+
+    def upload(self, mask=B.COLS_INPUT_ALL):
+        B.check(self.ctx, B.lib().weed_upload(self.ctx, mask))
+
+    def download(self, mask=B.COLS_OUTPUT_ALL):
+        B.check(self.ctx, B.lib().weed_download(self.ctx, mask))
+
+    def fetch_neighbors(self, first=0, count=None):
+        count = self.totalEntityCount - first if count is None else count
+        B.check(self.ctx, B.lib().weed_fetch_neighbors(self.ctx, first, count))
+
+    def neighbors_of(self, i, fetch=True):
+        """GameObject.updateNeighbors (gameObject.js:700-729): (ids, squared distances) of row i."""
+        if fetch:
+            self.fetch_neighbors(i, 1)
+        off = i * (1 + self.maxNeighbors)
+        n = int(self.neighborData[off])
+        return self.neighborData[off + 1:off + 1 + n], self.distanceData[off + 1:off + 1 + n]
+
+    # ---- frames ------------------------------------------------------------------------------
+    def step(self, dtRatio=1.0, upload=0, download=B.COLS_OUTPUT_ALL):
+        """One lockstep frame: upload(mask); spatial; physics(dtRatio); download(mask)."""
+        B.check(self.ctx, B.lib().weed_step(self.ctx, float(dtRatio), upload, download))
+
+    def run(self, frames, dtRatio=1.0):
+        """`frames` frames back to back on the device, no host interaction (asynchronous)."""
+        B.check(self.ctx, B.lib().weed_run(self.ctx, float(dtRatio), frames))
+
+    def sync(self):
+        B.check(self.ctx, B.lib().weed_sync(self.ctx))
+
+    def updatePhysicsConfig(self, partial):
+        """gameEngine.js:1304-1325 -> applyPhysicsConfig + validatePhysicsConfig."""
+        phys = self.config["physics"]
+        for k, v in partial.items():
+            if k == "gravity":
+                phys["gravity"] = {**phys.get("gravity", {}), **v}
+            else:
+                phys[k] = v
+        p = self._physics_struct(phys)
+        B.check(self.ctx, B.lib().weed_set_physics(self.ctx, C.byref(p)))
+
+    def physics_settings(self):
+        p = B.PhysicsConfig()
+        B.check(self.ctx, B.lib().weed_get_physics(self.ctx, C.byref(p)))
+        return {n: getattr(p, n) for n, _ in p._fields_ if not n.startswith("_")}
+
+    def stats(self):
+        s = B.Stats()
+        B.check(self.ctx, B.lib().weed_get_stats(self.ctx, C.byref(s)))
+        d = {n: getattr(s, n) for n, _ in s._fields_ if n not in ("ms", "_pad")}
+        d["ms"] = list(s.ms)
+        return d
+
+    def device_ptr(self, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        B.check(self.ctx, B.lib().weed_device_ptr(self.ctx, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            B.lib().weed_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

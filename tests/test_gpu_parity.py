@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star / SURVEY Appendix A):
+  * grid assignment and neighbor rows: BIT-EXACT (ids, order, cap, float32 d² bits);
+  * physics state vs the oracle's J-order mode (the documented deterministic resolution
+    order of the GPU): bit-exact for x, y, px, py, vx, vy, ax, ay, speed, collisionCount and
+    collisionData; velocityAngle within 1 float32 ulp (device atan2 vs libm atan2);
+  * vs the reference's sequential Gauss-Seidel order: statistical (tests/test_gpu_longrun.py).
+"""
+import numpy as np
+import pytest
+
+from helpers import active_rows_equal, assert_cols_equal, bits, make_oracle, random_scene
+from multithreadedgameengine_b200 import binding as B, scenes
+from oracle.oracle_c import OracleC
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ["T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.ax", "RB.ay", "RB.speed", "RB.collisionCount"]
+ALL_DL = B.COLS_INPUT_ALL | B.COL_NEIGHBORS | B.COL_COLLISIONS
+
+
+def make_engine(cfg, cols, **kw):
+    from multithreadedgameengine_b200.engine import GameEngine
+    eng = GameEngine(cfg, **kw)
+    eng.load_columns(cols)
+    return eng
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+def compare_state(eng, ora, what=""):
+    assert_cols_equal(eng.col, ora.col, EXACT, what)
+    for k in ("T.active", "RB.active", "RB.static", "C.active", "C.isTrigger", "RB.maxVel", "C.radius", "C.visualRange"):
+        assert np.array_equal(bits(eng.col[k]), bits(ora.col[k])), k
+    a, b = eng.col["RB.velocityAngle"], ora.col["RB.velocityAngle"]
+    ok = (ulp_diff(a, b) <= 1) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), f"{what} velocityAngle beyond 1 ulp at {np.nonzero(~ok)[0][:5]}"
+    n = int(ora.collisionData[0])
+    assert int(eng.collisionData[0]) == n, f"{what} pairCount {int(eng.collisionData[0])} vs {n}"
+    assert np.array_equal(eng.collisionData[1:1 + 2 * n], ora.collisionData[1:1 + 2 * n]), f"{what} collision pairs"
+
+
+def compare_rows(eng, ora, cfg):
+    cellOf, start, idx = ora.grid_csr()
+    rows = np.nonzero(cellOf >= 0)[0]
+    N, M = cfg["entityCount"], cfg["spatial"]["maxNeighbors"]
+    active_rows_equal(eng.neighborData, eng.distanceData, ora.neighborData, ora.distanceData, N, M, rows)
+    return cellOf
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_neighbor_rows_bit_exact_adversarial(seed):
+    rng = np.random.default_rng(100 + seed)
+    cs = [50.0, 33.3, 30.0, 66.5, 128.0, 17.0, 80.0, 100.0][seed]
+    M = [16, 8, 400, 5, 32, 12, 1, 64][seed]
+    cfg, cols = random_scene(rng, N=700, cellSize=cs, M=M)
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    eng.spatial.update()
+    ora.spatial()
+    eng.download(B.COL_NEIGHBORS)
+    cellOf = compare_rows(eng, ora, cfg)
+    # rows of entities that are not in the grid are never written
+    stride = 1 + M
+    nd = eng.neighborData.reshape(-1, stride)
+    assert not nd[cellOf < 0].any()
+    # words past 1+count keep their old contents (zero here)
+    for i in np.nonzero(cellOf >= 0)[0]:
+        assert not nd[i, 1 + nd[i, 0]:].any()
+    s = eng.stats()
+    assert s["activeInGrid"] == int((cellOf >= 0).sum())
+    assert (s["gridCols"], s["gridRows"]) == (ora.gridCols, ora.gridRows)
+    cnt = np.bincount(cellOf[cellOf >= 0])
+    assert s["maxCellOccupancy"] == cnt.max()
+    assert s["neighborsTotal"] == int(nd[cellOf >= 0, 0].sum())
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_frames_bit_exact_vs_jorder_oracle(seed):
+    rng = np.random.default_rng(200 + seed)
+    cs = [50.0, 33.3, 30.0, 66.5, 128.0, 17.0][seed]
+    cfg, cols = random_scene(rng, N=900, cellSize=cs, M=[16, 8, 400, 5, 32, 12][seed], S=[2, 1, 3, 2, 4, 2][seed])
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    for frame in range(5):
+        dt = [1.0, 0.73, 1.0, 1.31, 1.0][frame]
+        eng.step(dt, 0, ALL_DL)
+        ora.step(dt, 1)
+        compare_rows(eng, ora, cfg)
+        compare_state(eng, ora, f"seed {seed} frame {frame}")
+    eng.close()
+
+
+def test_split_workers_equal_fused_step():
+    rng = np.random.default_rng(7)
+    cfg, cols = random_scene(rng, N=800, M=24)
+    a = make_engine(cfg, cols)
+    b = make_engine(cfg, cols)
+    for _ in range(3):
+        a.step(1.0, 0, ALL_DL)
+        b.spatial.update()
+        b.physics_worker.update(16.67, 1.0)
+        b.download(ALL_DL)
+        assert_cols_equal(a.col, b.col)
+        assert np.array_equal(a.neighborData, b.neighborData)
+        assert np.array_equal(bits(a.distanceData), bits(b.distanceData))
+        n = int(a.collisionData[0])
+        assert np.array_equal(a.collisionData[:1 + 2 * n], b.collisionData[:1 + 2 * n])
+    with pytest.raises(B.WeedError):
+        b.physics_worker.update(16.67, 1.0)   # needs the rows of a preceding spatial update
+    a.close(); b.close()
+
+
+def test_config1_readme_scene_30_frames():
+    cfg, cols = scenes.balls_readme()
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    for frame in range(30):
+        eng.step(1.0, 0, ALL_DL)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+    compare_rows(eng, ora, cfg)
+    assert int(ora.collisionData[0]) > 0
+    eng.close()
+
+
+def test_config2_boids_heterogeneous_ranges():
+    """Mixed visual ranges make rows asymmetric: pairs the higher-id side cannot infer go
+    through the explicit list."""
+    cfg, cols = scenes.boids(n_prey=3000, n_pred=150, seed=11)
+    cfg["worldWidth"], cfg["worldHeight"] = 1800.0, 900.0
+    for k in ("T.x", "RB.px"):
+        cols[k] = (cols[k] * np.float32(1800.0 / 5000.0)).astype(np.float32)
+    for k in ("T.y", "RB.py"):
+        cols[k] = (cols[k] * np.float32(900.0 / 2000.0)).astype(np.float32)
+    cfg["spatial"]["maxNeighbors"] = 300
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    for frame in range(6):
+        eng.step(1.0, 0, ALL_DL)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+    compare_rows(eng, ora, cfg)
+    assert eng.stats()["explicitPairs"] > 0
+    eng.close()
+
+
+def test_capped_rows_take_the_explicit_path():
+    cfg, cols = scenes.balls_synthetic(3000, (600.0, 300.0), 16.0, 4, 2, (2.0, 6.0), 16.0, seed=5)
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    for frame in range(6):
+        eng.step(1.0, 0, ALL_DL)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+        compare_rows(eng, ora, cfg)
+    s = eng.stats()
+    assert s["cappedRows"] > 0 and s["explicitPairs"] > 0 and s["explicitOverflow"] == 0
+    eng.close()
+
+
+def test_coincident_after_bounds_uses_hash_nudge():
+    """Two out-of-world balls of equal radius are clamped into the same corner by the boundary
+    pass: distance exactly 0, the documented hash nudge (include/weed_nudge.h) applies."""
+    cfg, cols = scenes.balls_readme(n_balls=6, seed=2, world=(400.0, 300.0))
+    for i, (x, y) in enumerate([(-30.0, -20.0), (-12.0, -25.0), (500.0, 400.0), (450.0, 380.0), (200.0, 100.0), (203.0, 100.0)], start=1):
+        cols["T.x"][i] = cols["RB.px"][i] = x
+        cols["T.y"][i] = cols["RB.py"][i] = y
+        cols["C.radius"][i] = 10.0
+    cols["RB.static"][4] = 1
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    for frame in range(4):
+        eng.step(1.0, 0, ALL_DL)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+    assert eng.col["T.x"][1] != eng.col["T.x"][2] or eng.col["T.y"][1] != eng.col["T.y"][2]
+    eng.close()
+
+
+def test_update_physics_config_and_validation():
+    cfg, cols = scenes.balls_readme(n_balls=500, seed=9, world=(900.0, 500.0))
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    eng.step(1.0, 0, ALL_DL); ora.step(1.0, 1)
+    new = dict(subStepCount=0, boundaryElasticity=1.7, collisionResponseStrength=-0.2, verletDamping=0.9,
+               minSpeedForRotation=0.5, gravity=dict(x=0.3, y=-0.1))
+    eng.updatePhysicsConfig(new)
+    st = eng.physics_settings()      # validatePhysicsConfig clamps (utils.js:269-301)
+    assert (st["subStepCount"], st["boundaryElasticity"], st["collisionResponseStrength"]) == (1, 1.0, 0.0)
+    ora.set_physics(0, 1.7, -0.2, 0.9, 0.5, 0.3, -0.1)
+    for frame in range(3):
+        eng.step(1.0, 0, ALL_DL); ora.step(1.0, 1)
+        compare_state(eng, ora, f"after reconfig frame {frame}")
+    eng.close()
+
+
+def test_host_written_columns_and_partial_row_fetch():
+    """tick()-style use: the host writes ax/ay (and teleports an entity), uploads just those
+    columns, and reads single neighbor rows back (gameObject.js:700-729)."""
+    cfg, cols = scenes.balls_readme(n_balls=600, seed=4, world=(1000.0, 500.0))
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    rng = np.random.default_rng(0)
+    up = eng.mask("RB.ax", "RB.ay", "T.x", "T.y", "RB.px", "RB.py")
+    for frame in range(4):
+        ax = ((rng.random(601) - 0.5) * 2).astype(np.float32)
+        ay = ((rng.random(601) - 0.5) * 2).astype(np.float32)
+        for tgt in (eng.col, ora.col):
+            tgt["RB.ax"][:] = ax
+            tgt["RB.ay"][:] = ay
+            tgt["T.x"][0] = 100.0 + 50 * frame       # the Mouse entity moves every frame
+            tgt["T.y"][0] = 120.0
+            tgt["T.x"][17] = tgt["RB.px"][17] = 333.0  # teleport: x setter also sets px (gameObject.js:230-237)
+        eng.step(1.0, up, B.COLS_OUTPUT_ALL | B.COL_COLLISIONS)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+        stride = 1 + eng.maxNeighbors
+        for i in (0, 17, 300, 600):
+            ids, d2 = eng.neighbors_of(i)
+            n = int(ora.neighborData[i * stride])
+            assert np.array_equal(ids, ora.neighborData[i * stride + 1:i * stride + 1 + n])
+            assert np.array_equal(bits(d2), bits(ora.distanceData[i * stride + 1:i * stride + 1 + n]))
+    eng.close()
+
+
+def test_graph_and_direct_launch_agree():
+    cfg, cols = scenes.balls_readme(n_balls=700, seed=6, world=(1000.0, 500.0))
+    a = make_engine(cfg, cols)
+    b = make_engine(cfg, cols, flags=B.FLAG_NO_GRAPH)
+    c = make_engine(cfg, cols, flags=B.FLAG_KERNEL_TIMING)
+    a.run(5); b.run(5); c.run(5)
+    for e in (a, b, c):
+        e.download(ALL_DL)
+    assert_cols_equal(a.col, b.col); assert_cols_equal(a.col, c.col)
+    assert np.array_equal(a.neighborData, b.neighborData) and np.array_equal(a.neighborData, c.neighborData)
+    assert sum(c.stats()["ms"]) > 0
+    for e in (a, b, c):
+        e.close()
+
+
+def test_errors_are_codes_not_crashes():
+    from multithreadedgameengine_b200.engine import GameEngine
+    cfg, cols = scenes.balls_readme(n_balls=50, seed=1, world=(400.0, 300.0))
+    eng = GameEngine(cfg)
+    L = B.lib()
+    small = np.zeros(16, dtype=np.uint8)
+    assert L.weed_bind(eng.ctx, B.BUF_TRANSFORM, small.ctypes.data, small.nbytes) == B.WEED_E_SIZE
+    assert L.weed_bind(eng.ctx, 99, small.ctypes.data, small.nbytes) == B.WEED_E_INVALID
+    assert L.weed_fetch_neighbors(eng.ctx, 40, 100) == B.WEED_E_INVALID
+    assert L.weed_physics(eng.ctx, 1.0) == B.WEED_E_STATE
+    assert L.weed_bind(eng.ctx, B.BUF_COLLISION, None, 0) == B.WEED_OK
+    assert L.weed_download(eng.ctx, B.COL_COLLISIONS) == B.WEED_E_NOT_BOUND
+    eng.close()
