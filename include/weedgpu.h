@@ -34,7 +34,7 @@ enum {
   WEED_E_CUDA        = -2,  /* CUDA runtime failure (context becomes sticky-failed)    */
   WEED_E_NOT_BOUND   = -3,  /* a required host buffer was not bound                    */
   WEED_E_SIZE        = -4,  /* bound buffer smaller than the layout requires           */
-  WEED_E_OVERFLOW    = -5,  /* internal explicit-pair capacity exceeded (see stats)    */
+  WEED_E_OVERFLOW    = -5,  /* reserved                                                */
   WEED_E_STATE       = -6,  /* call order violated (e.g. weed_physics before spatial)  */
   WEED_E_NOMEM       = -7
 };
@@ -145,10 +145,8 @@ typedef struct weed_stats {
   uint64_t neighborsTotal;       /* sum of row counts last frame  (k-bar = /active)     */
   uint32_t cappedRows;           /* rows that hit maxNeighbors last frame               */
   uint32_t explicitPairs;        /* pairs routed through the explicit (asymmetric) path */
-  uint32_t explicitOverflow;     /* !=0: explicit-pair capacity exceeded (result invalid) */
   uint32_t collisionPairs;       /* pairs found in the last substep (uncapped)          */
   uint32_t kernelLaunchesPerStep;
-  uint32_t _pad;
   float    ms[12];               /* per-kernel ms of the last step (KERNEL_TIMING only) */
 } weed_stats;
 

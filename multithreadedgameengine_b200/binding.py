@@ -61,9 +61,8 @@ class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("gridCols", C.c_uint32), ("gridRows", C.c_uint32),
                 ("activeInGrid", C.c_uint32), ("maxCellOccupancy", C.c_uint32),
                 ("neighborsTotal", C.c_uint64), ("cappedRows", C.c_uint32),
-                ("explicitPairs", C.c_uint32), ("explicitOverflow", C.c_uint32),
-                ("collisionPairs", C.c_uint32), ("kernelLaunchesPerStep", C.c_uint32),
-                ("_pad", C.c_uint32), ("ms", C.c_float * 12)]
+                ("explicitPairs", C.c_uint32), ("collisionPairs", C.c_uint32),
+                ("kernelLaunchesPerStep", C.c_uint32), ("ms", C.c_float * 12)]
 
 
 # every symbol include/weedgpu.h declares: name -> (restype, argtypes)

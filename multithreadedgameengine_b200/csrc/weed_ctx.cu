@@ -282,6 +282,10 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return WEED_E_INVALID; }
   if (cfg->struct_size != sizeof(weed_config)) { g_create_error = "weed_config.struct_size mismatch (ABI)"; return WEED_E_INVALID; }
   if (cfg->entityCount == 0 || cfg->entityCount > 0x3FFFFFF0u) { g_create_error = "entityCount out of range"; return WEED_E_INVALID; }
+  if (((double)cfg->entityCount + 32.0) * (double)(((cfg->maxNeighbors + 7) / 8) * 8) >= 4294967295.0) {
+    g_create_error = "entityCount * maxNeighbors must stay below 2^32 per context (partition the world into slabs)";
+    return WEED_E_INVALID;
+  }
   if (!(cfg->cellSize > 0) || !(cfg->worldWidth > 0) || !(cfg->worldHeight > 0)) { g_create_error = "world/cell size must be positive"; return WEED_E_INVALID; }
   const double colsD = ceil(cfg->worldWidth / cfg->cellSize), rowsD = ceil(cfg->worldHeight / cfg->cellSize);  // spatial_worker.js:82-83
   if (!(colsD >= 1) || !(rowsD >= 1) || colsD * rowsD > 1.0e9) { g_create_error = "grid too large"; return WEED_E_INVALID; }
@@ -316,7 +320,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.N = cfg->entityCount;
   g.M = cfg->maxNeighbors;
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
-  g.xcap = g.Mpad;
+  g.Npad = ((g.N + 31) / 32) * 32;
   g.maxPairs = cfg->maxCollisionPairs;
   const size_t N = g.N;
   int rc;
@@ -329,10 +333,10 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->wbStatus, ctx->wbTiles);
-  A(ctx->s.QXY, N); A(ctx->s.QVR, N); A(ctx->s.SID, N); A(ctx->s.G0, N); A(ctx->s.G1, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XCNT, N); A(ctx->s.OUT, N);
-  A(ctx->s.NS, N * g.Mpad);
-  A(ctx->s.XR, N * g.xcap);
+  A(ctx->s.QXY, N); A(ctx->s.QVI, N); A(ctx->s.G0, N); A(ctx->s.G1, N); A(ctx->s.PXY, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N);
+  A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
+  A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
   ctx->rowWords = N * (1 + (size_t)g.M);
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
   A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
@@ -454,7 +458,6 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   const GridDims& g = ctx->g;
   cudaStream_t st = ctx->stream;
   const unsigned nb = blocks_for(g.N, 256);
-  const unsigned tb = blocks_for((size_t)g.N * TILE_W, 256);
   k_spatial_begin<<<1, 32, 0, st>>>(ctx->dCtr);
   TIME_MARK(ctx, timing, 0);
   k_cell_key<<<nb, 256, 0, st>>>(g, ctx->d.DP, ctx->d.F, ctx->key, ctx->rank, ctx->cellCount);
@@ -468,12 +471,12 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   else
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   TIME_MARK(ctx, timing, 4);
+  const unsigned kb = blocks_for(g.N, K4_THREADS);
   if (ctx->nd)
-    k_neighbors<true><<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+    k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
   else
-    k_neighbors<false><<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+    k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   TIME_MARK(ctx, timing, 5);
-  k_explicit_capped<<<tb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
   return WEED_OK;
@@ -482,7 +485,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
 static int launch_constraints(weed_ctx* ctx, bool timing) {
   const GridDims& g = ctx->g;
   cudaStream_t st = ctx->stream;
-  const unsigned tb = blocks_for((size_t)g.N * TILE_W, 256);
+  const unsigned tb = blocks_for(g.N, 256);
   const int S = ctx->phys.subStepCount;
   float4* bufs[2] = {ctx->s.G0, ctx->s.G1};
   for (int step = 0; step < S; step++) {
@@ -529,7 +532,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 9 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 8 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -550,22 +553,13 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   return WEED_OK;
 }
 
-static int check_overflow(weed_ctx* ctx) {
-  Counters c;
-  CK(cudaMemcpyAsync(&c, ctx->dCtr, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (c.explicitOverflowFrame)
-    return fail(ctx, WEED_E_OVERFLOW, "explicit pair capacity exceeded (more than " + std::to_string(ctx->g.xcap) + " one-sided partners on one entity)");
-  return WEED_OK;
-}
-
 extern "C" int weed_spatial(weed_ctx* ctx) {
   GUARD(ctx);
   int rc = launch_spatial(ctx, false, false);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->spatialValid = true;
-  return check_overflow(ctx);
+  return WEED_OK;
 }
 
 extern "C" int weed_physics(weed_ctx* ctx, double dtRatio) {
@@ -591,7 +585,8 @@ extern "C" int weed_step(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, ui
   if (rc) return rc;
   rc = download_async(ctx, download_mask);
   if (rc) return rc;
-  return check_overflow(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
 }
 
 extern "C" int weed_run(weed_ctx* ctx, double dtRatio, uint32_t frames) {
@@ -649,9 +644,8 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->neighborsTotal = c.neighborsTotal;
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
-  out->explicitOverflow = c.explicitOverflowFrame;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 9 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 8 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   return WEED_OK;
 }

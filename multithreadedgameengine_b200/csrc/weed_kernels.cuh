@@ -5,9 +5,9 @@
 //   id order   k_scatter_ids   K3a ids into their cell segment (arrival order)
 //   id order   k_build_slots   K3b stable position inside the cell (ascending id), Verlet
 //                                  integration (K5) + derived speed/angle fused, slot records
-//   slot order k_neighbors     K4  capped ordered gather, 8 lanes per entity
-//   slot order k_explicit_capped K4b explicit pairs caused by capped partners (rare)
-//   slot order k_substep<LAST> K6  bounds + circle-circle correction, J-order, 8 lanes/entity
+//   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
+//                                  warp-cooperative coalesced row flush
+//   slot order k_substep<LAST> K6  bounds + circle-circle correction, J-order
 //   id order   k_writeback     WB  gather results by id, look-back scan of pair counts,
 //                                  collisionData emission (K7)
 #pragma once
@@ -18,7 +18,6 @@
 namespace weed {
 namespace cg = cooperative_groups;
 
-static constexpr int TILE_W = 8;            // lanes cooperating on one entity in K4 / K6
 static constexpr int SCAN_THREADS = 512;
 static constexpr int SCAN_ITEMS = 4;
 static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -86,7 +85,6 @@ __global__ void k_spatial_begin(Counters* ctr) {
     ctr->epoch++;
     ctr->anyCapped = 0;
     ctr->explicitPairs = 0;
-    ctr->explicitOverflowFrame = 0;
     ctr->maxCellFrame = 0;
   }
 }
@@ -197,15 +195,14 @@ struct ById {
 };
 struct BySlot {
   float2* QXY;       // position at grid-build time (query position)
-  float* QVR;        // visualRange
-  uint32_t* SID;     // entity id
+  float2* QVI;       // visualRange, entity id (bits)
   float4* G0;        // x, y, radius, flagword   (substep ping)
   float4* G1;        //                           (substep pong)
   float2* PXY;       // px, py
   uint32_t* NCNT;    // neighbor count
-  uint32_t* NS;      // internal rows [slot][Mpad]
-  uint32_t* XCNT;    // explicit incoming count
-  uint32_t* XR;      // explicit incoming rows [slot][xcap]
+  uint32_t* NST;     // internal rows, transposed: NST[k * Npad + slot]
+  uint32_t* XHEAD;   // explicit incoming pairs: list head (0 = empty, else row position + 1)
+  uint32_t* XNEXT;   // next link, indexed by the OWNER's row position (k * Npad + slot)
   OutRec* OUT;       // last-substep result
 };
 
@@ -277,142 +274,174 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   const uint32_t slot = s0 + r;
   slotOf[i] = slot;
   s.QXY[slot] = make_float2(x0, y0);
-  s.QVR[slot] = at.z;
-  s.SID[slot] = i;
+  s.QVI[slot] = make_float2(at.z, __uint_as_float(i));
   uint32_t keep = 0;
   if (afterSpatial) keep = __float_as_uint(s.G0[slot].w) & F_CAPPED;   // rows of this frame already exist
-  else s.XCNT[slot] = 0;
+  else s.XHEAD[slot] = 0;
   s.G0[slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | (cc << F_CC_SHIFT)));
   s.PXY[slot] = make_float2(dp.z, dp.w);
 }
 
 // ---- K4: capped, ordered neighbor gather (spatial_worker.js:195-277) ---------------------
-// 8 lanes per entity.  Candidates of one window row are ONE contiguous slot range because
-// slots are sorted by (cell, id) and cells of a grid row are consecutive; the reference's scan
-// order (rows, then columns, then list order) is therefore ascending slot order, and an
-// ordered ballot compaction reproduces the row content and the cap exactly.
-__device__ __forceinline__ void explicit_append(const GridDims& g, BySlot& s, Counters* ctr, uint32_t dstSlot,
-                                                uint32_t srcSlot) {
-  const uint32_t pos = atomicAdd(&s.XCNT[dstSlot], 1u);
-  if (pos < g.xcap) s.XR[(size_t)dstSlot * g.xcap + pos] = srcSlot;
-  else atomicExch(&ctr->explicitOverflowFrame, 1u);
+// One thread per entity, in slot order.  Candidates of one window row are ONE contiguous
+// slot range because slots are sorted by (cell, id) and the cells of a grid row are
+// consecutive; the reference's scan order (rows, then columns, then list order) is therefore
+// ascending slot order, so a sequential scan reproduces row content and cap exactly.
+//   * fp32 pre-filter: a candidate whose float32 d2 exceeds vr2 by more than 1e-5 relative is
+//     certainly rejected by the binary64 predicate; everything else is decided in binary64.
+//   * accepted entries are staged in shared memory (15 per thread) and flushed by the whole
+//     warp: API rows (scattered by entity id) are written 16 consecutive words at a time, the
+//     internal transposed rows NST[k][slot] 32 consecutive slots at a time.
+//
+// An explicit pair is a row entry of its owner (the lower id), so the owner's row position
+// (k * Npad + slot) is a unique pool index: incoming pairs of a target form a linked list
+// threaded through XNEXT, with no capacity limit and no allocation.
+__device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, uint32_t dstSlot, uint32_t ownerRowPos) {
+  s.XNEXT[ownerRowPos] = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
   atomicAdd(&ctr->explicitPairs, 1u);
 }
 
-template <bool WRITE_ROWS>
-__global__ void __launch_bounds__(256)
-k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
-            float* __restrict__ dd, Counters* ctr) {
-  cg::thread_block_tile<TILE_W> tile = cg::tiled_partition<TILE_W>(cg::this_thread_block());
-  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) / TILE_W;
-  const uint32_t A = cellStart[g.cells];
-  if (e >= A) return;
-  const uint32_t lane = tile.thread_rank();
-  const float2 q = s.QXY[e];
-  const float vr = s.QVR[e];
-  const uint32_t id = s.SID[e];
-  const double myX = q.x, myY = q.y;
-  const double vrSq = dmul((double)vr, (double)vr);
-  int32_t myCol, myRow;
-  cell_of(g, q.x, q.y, myCol, myRow);                 // my clamped cell (for partners' windows)
-  const size_t rowBase = (size_t)id * (1 + (size_t)g.M);
-  const size_t nsBase = (size_t)e * g.Mpad;
-  const uint32_t M = g.M;
-  uint32_t n = 0;
-  Window w;
-  if (M > 0 && query_window(g, q.x, q.y, vr, w)) {
-    for (int32_t row = w.r0; row <= w.r1 && n < M; row++) {
-      const uint32_t a = cellStart[(uint32_t)row * g.cols + w.c0];
-      const uint32_t b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
-      for (uint32_t t0 = a; t0 < b && n < M; t0 += TILE_W) {
-        const uint32_t t = t0 + lane;
-        bool acc = false;
-        double d2 = 0;
-        float2 c = make_float2(0.f, 0.f);
-        if (t < b && t != e) {
-          c = s.QXY[t];
-          const double dX = dsub((double)c.x, myX);
-          const double dY = dsub((double)c.y, myY);
-          d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-          acc = d2 < vrSq && d2 > 0;               // :257
-        }
-        const uint32_t bits = tile.ballot(acc);
-        const uint32_t pos = n + __popc(bits & ((1u << lane) - 1));
-        if (acc && pos < M) {
-          const uint32_t jid = s.SID[t];
-          if (WRITE_ROWS) {
-            nd[rowBase + 1 + pos] = (int32_t)jid;    // :259
-            dd[rowBase + 1 + pos] = fround(d2);      // :260
-          }
-          // would partner t's own scan accept me (ignoring its cap)?  Its window must contain
-          // my clamped cell and d2 < vr_t^2 (d2 is bitwise symmetric, and d2 > 0 holds).
-          const float vrt = s.QVR[t];
-          Window wt;
-          bool back = d2 < dmul((double)vrt, (double)vrt) && query_window(g, c.x, c.y, vrt, wt) &&
-                      myRow >= wt.r0 && myRow <= wt.r1 && myCol >= wt.c0 && myCol <= wt.c1;
-          const bool out = jid > id;
-          s.NS[nsBase + pos] = t | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
-          // pair (id, jid) is in P but the partner cannot infer it from its own row
-          if (out && !back) explicit_append(g, s, ctr, t, e);
-        }
-        n = min(M, n + (uint32_t)__popc(bits));
-      }
-    }
-  }
-  if (n >= M && M > 0) {
-    // capped row: partners cannot trust their NS_BACK bit for me, so every pair I own
-    // becomes explicit (the !back ones were appended above)
-    for (uint32_t k = lane; k < n; k += TILE_W) {
-      const uint32_t wd = s.NS[nsBase + k];
-      if ((wd & NS_OUT) && (wd & NS_BACK)) explicit_append(g, s, ctr, wd & NS_SLOT_MASK, e);
-    }
-    if (lane == 0) {
-      float4* gp = s.G0 + e;
-      reinterpret_cast<uint32_t*>(gp)[3] |= F_CAPPED;
-      ctr->anyCapped = 1;
-    }
-  }
-  if (lane == 0) {
-    if (WRITE_ROWS) {
-      nd[rowBase] = (int32_t)n;                      // :274
-      dd[rowBase] = (float)n;                        // :275
-    }
-    s.NCNT[e] = n;
-  }
+// does the scan of an entity at (x,y) with cell radius cr (spatial_worker.js:211-231) visit the
+// in-grid cell (col,row)?  The clamps of :228-231 cannot exclude an in-grid cell.
+__device__ __forceinline__ bool window_visits(const GridDims& g, float x, float y, double cr, int32_t col, int32_t row) {
+  const double c0 = (double)js_toint32(dmul((double)x, g.inv));
+  const double r0 = (double)js_toint32(dmul((double)y, g.inv));
+  return dsub(r0, cr) <= (double)row && (double)row <= dadd(r0, cr) &&
+         dsub(c0, cr) <= (double)col && (double)col <= dadd(c0, cr);
 }
 
-// ---- K4b: pairs owned by an uncapped row whose partner is capped ---------------------------
-// (the partner may have been truncated before reaching me, so it will not infer the pair)
-__global__ void __launch_bounds__(256)
-k_explicit_capped(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
-  if (!ctr->anyCapped) return;
-  cg::thread_block_tile<TILE_W> tile = cg::tiled_partition<TILE_W>(cg::this_thread_block());
-  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) / TILE_W;
-  if (e >= cellStart[g.cells]) return;
-  const uint32_t fw = __float_as_uint(s.G0[e].w);
-  if (fw & F_CAPPED) return;                         // its pairs are already explicit
-  const uint32_t n = s.NCNT[e];
-  const size_t nsBase = (size_t)e * g.Mpad;
-  for (uint32_t k = tile.thread_rank(); k < n; k += TILE_W) {
-    const uint32_t wd = s.NS[nsBase + k];
-    if ((wd & NS_OUT) && (wd & NS_BACK)) {
-      const uint32_t t = wd & NS_SLOT_MASK;
-      if (__float_as_uint(s.G0[t].w) & F_CAPPED) explicit_append(g, s, ctr, t, e);
-    }
+static constexpr int K4_THREADS = 128;
+static constexpr int K4_CH = 15;        // staged entries per thread and round
+static constexpr int K4_STRIDE = 17;    // odd stride: conflict-free smem both ways
+
+template <bool WRITE_ROWS>
+__global__ void __launch_bounds__(K4_THREADS)
+k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
+            float* __restrict__ dd, Counters* ctr) {
+  __shared__ uint32_t sW[K4_THREADS / 32][32 * K4_STRIDE];
+  __shared__ uint32_t sId[K4_THREADS / 32][32 * K4_STRIDE];
+  __shared__ float sD2[K4_THREADS / 32][32 * K4_STRIDE];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* myW = &sW[warp][lane * K4_STRIDE];
+  uint32_t* myId = &sId[warp][lane * K4_STRIDE];
+  float* myD2 = &sD2[warp][lane * K4_STRIDE];
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t A = cellStart[g.cells];
+  const uint32_t M = g.M;
+  bool done = true;
+  float2 q = make_float2(0.f, 0.f);
+  float vr = 0.f;
+  uint32_t id = 0;
+  Window w; w.r0 = 0; w.r1 = -1; w.c0 = 0; w.c1 = 0;
+  if (e < A) {
+    q = s.QXY[e];
+    const float2 vi = s.QVI[e];
+    vr = vi.x; id = __float_as_uint(vi.y);
+    done = !(M > 0 && query_window(g, q.x, q.y, vr, w));
   }
+  const double myX = q.x, myY = q.y;
+  const double vrSq = dmul((double)vr, (double)vr);
+  const double myCr = ceil(dmul((double)vr, g.inv));
+  const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf fall through)
+  int32_t myCol = 0, myRow = 0;
+  if (e < A) cell_of(g, q.x, q.y, myCol, myRow);     // my clamped cell (for partners' windows)
+  const size_t rowBase = (size_t)id * (1 + (size_t)M);
+  uint32_t n = 0;
+  int32_t row = w.r0;
+  uint32_t t = 0, b = 0;
+  if (!done) {
+    t = cellStart[(uint32_t)row * g.cols + w.c0];
+    b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+  }
+  bool any = false;           // pushed an explicit pair or capped -> nothing else to do here
+  do {
+    uint32_t cnt = 0;
+    while (!done && cnt < K4_CH) {
+      if (t >= b) {
+        if (++row > w.r1) { done = true; break; }
+        t = cellStart[(uint32_t)row * g.cols + w.c0];
+        b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+        continue;
+      }
+      const uint32_t tc = t++;
+      if (tc == e) continue;                          // :249
+      const float2 c = s.QXY[tc];
+      const float fx = c.x - q.x, fy = c.y - q.y;
+      const float d2f = fx * fx + fy * fy;
+      if (d2f > vrSqF && d2f < 3.0e38f) continue;     // certainly d2 >= vr2
+      const double dX = dsub((double)c.x, myX);       // :252-254
+      const double dY = dsub((double)c.y, myY);
+      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+      if (!(d2 < vrSq && d2 > 0)) continue;           // :257
+      const float2 vt = s.QVI[tc];
+      const uint32_t jid = __float_as_uint(vt.y);
+      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric.
+      const double crT = (vt.x == vr) ? myCr : ceil(dmul((double)vt.x, g.inv));
+      const bool back = d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow);
+      const bool out = jid > id;
+      myW[cnt] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
+      myId[cnt] = jid;
+      myD2[cnt] = fround(d2);
+      // pair (id, jid) is in P but the partner cannot infer it from its own row
+      if (out && !back) { explicit_push(s, ctr, tc, (n * g.Npad) + e); any = true; }
+      cnt++;
+      if (++n >= M) done = true;                      // :264
+    }
+    __syncwarp();
+    // ---- warp-cooperative flush -------------------------------------------------------------
+    const uint32_t first = n - cnt;                   // row position of my first staged entry
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
+    for (uint32_t k = 0; k < kmax; k++)
+      if (k < cnt) s.NST[(size_t)(first + k) * g.Npad + e] = myW[k];
+    if (WRITE_ROWS) {
+      const uint32_t h = lane >> 4, l = lane & 15;
+      for (uint32_t s2 = 0; s2 < 16; s2++) {
+        const uint32_t src = s2 * 2 + h;
+        const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t f = __shfl_sync(0xffffffffu, first, src);
+        const uint32_t fin = __shfl_sync(0xffffffffu, (uint32_t)(done && (e < A)), src);
+        const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
+        if (f == 0 && fin) {
+          // whole row in this round: header + entries in one contiguous store
+          if (l == 0) { nd[rb] = (int32_t)c; dd[rb] = (float)c; }       // :274-275
+          else if (l <= c) { nd[rb + l] = (int32_t)sId[warp][src * K4_STRIDE + l - 1]; dd[rb + l] = sD2[warp][src * K4_STRIDE + l - 1]; }
+        } else {
+          if (l < c) { nd[rb + 1 + f + l] = (int32_t)sId[warp][src * K4_STRIDE + l]; dd[rb + 1 + f + l] = sD2[warp][src * K4_STRIDE + l]; }  // :259-260
+          if (fin && l == 15) { nd[rb] = (int32_t)(f + c); dd[rb] = (float)(f + c); }
+        }
+      }
+    }
+    __syncwarp();
+  } while (__any_sync(0xffffffffu, !done));
+  if (e >= A) return;
+  if (n >= M && M > 0) {
+    // capped row: partners cannot trust their NS_BACK bit for me, so every pair I own becomes
+    // explicit (the !back ones were pushed above).  Incoming pairs are found by an uncapped
+    // window rescan in the substep kernel.
+    for (uint32_t k = 0; k < n; k++) {
+      const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
+      if ((wd & NS_OUT) && (wd & NS_BACK)) explicit_push(s, ctr, wd & NS_SLOT_MASK, k * g.Npad + e);
+    }
+    reinterpret_cast<uint32_t*>(s.G0 + e)[3] |= F_CAPPED;
+  }
+  (void)any;
+  s.NCNT[e] = n;
 }
 
 // ---- K6: one constraint substep (physics_worker.js:323-395, 405-568), J-order ---------------
-// Each entity (8 lanes) applies its own boundary pass, then evaluates every pair of P it
-// belongs to on the start-of-sweep positions (partners' boundary pass re-applied on the fly)
-// and accumulates its own corrections in ascending partner-slot order, rounding to float32
-// after each one exactly like the reference's `x[i] += ...` on a Float32Array.
+// Each entity applies its own boundary pass, then evaluates every pair of P it belongs to on
+// the start-of-sweep positions (partners' boundary pass re-applied on the fly) and
+// accumulates its own corrections in ascending partner-slot order, rounding to float32 after
+// each one exactly like the reference's `x[i] += ...` on a Float32Array.
 //
-// Pair membership (P = {(i,j): i<j, j in row(i), both active colliders}):
-//   - row entry with NS_OUT: I am i, the pair is mine.
-//   - row entry without NS_OUT (partner id lower): the pair exists iff I am in the partner's
-//     row.  That is inferred (NS_BACK, and neither row capped); every pair that cannot be
-//     inferred was appended to my explicit list XR by its owner in K4 / K4b.
+// Pair membership (P = {(i,j): i<j, j in row(i), both active colliders}), seen from entity e:
+//   - row entry with NS_OUT (partner id higher): the pair is mine.
+//   - partner k with lower id: the pair exists iff I am in row(k).
+//       k capped            -> k pushed all its pairs on the explicit lists (K4)
+//       k does not see back -> impossible here; if k sees me and I do not see k, k pushed it
+//       k uncapped, mutual  -> inferred: from my row entry (NS_BACK) when my row is complete,
+//                              or, when MY row is capped (k may be missing from it), from an
+//                              uncapped rescan of my window.
 struct SubstepAcc { float x, y; uint32_t hits, outHits; };
 
 __device__ __forceinline__ bool partner_pair(const GridDims& g, const Params& p, const BySlot& s,
@@ -422,57 +451,128 @@ __device__ __forceinline__ bool partner_pair(const GridDims& g, const Params& p,
   const uint32_t ft = __float_as_uint(gt.w);
   float xt = gt.x, yt = gt.y;
   if ((ft & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gt.z, xt, yt);  // partner after ITS boundary pass
+  // fp32 pre-filter of :455 (dist2 >= minDist^2): certain when beyond 1e-5 relative
+  {
+    const float fx = x - xt, fy = y - yt, md = r + gt.z;
+    const float d2f = fx * fx + fy * fy;
+    if (d2f > md * md * 1.00001f && d2f < 3.0e38f) { moves = false; mx = 0; my = 0; return false; }
+  }
   PairMove m;
-  if (iAmLower) m = pair_eval(p, frame, substep, s.SID, e, t, x, y, r, fw, xt, yt, gt.z, ft);
-  else          m = pair_eval(p, frame, substep, s.SID, t, e, xt, yt, gt.z, ft, x, y, r, fw);
+  if (iAmLower) m = pair_eval(p, frame, substep, s.QVI, e, t, x, y, r, fw, xt, yt, gt.z, ft);
+  else          m = pair_eval(p, frame, substep, s.QVI, t, e, xt, yt, gt.z, ft, x, y, r, fw);
   if (iAmLower) { moves = m.moveI; mx = m.mx; my = m.my; }
   else          { moves = m.moveJ; mx = -m.mx; my = -m.my; }
   moves = moves && m.hit;
   return m.hit;
 }
 
-// sequential slow path for entities with explicit incoming pairs: lane 0 merges the row and
-// the (sorted) explicit list in ascending slot order
-__device__ __noinline__ void substep_explicit(const GridDims& g, const Params& p, const BySlot& s,
+__device__ __forceinline__ void apply_partner(const GridDims& g, const Params& p, const BySlot& s,
                                               const float4* __restrict__ Gin, uint32_t frame, uint32_t substep,
-                                              uint32_t e, float x, float y, float r, uint32_t fw, uint32_t cnt,
-                                              uint32_t xcnt, SubstepAcc& acc) {
-  uint32_t* xr = s.XR + (size_t)e * g.xcap;
-  for (uint32_t a = 1; a < xcnt; a++) {      // insertion sort (already sorted after the first substep)
-    const uint32_t v = xr[a];
-    uint32_t b = a;
-    while (b > 0 && xr[b - 1] > v) { xr[b] = xr[b - 1]; b--; }
-    xr[b] = v;
-  }
-  const uint32_t* ns = s.NS + (size_t)e * g.Mpad;
-  const bool meCapped = (fw & F_CAPPED) != 0;
-  uint32_t a = 0, b = 0;
-  while (a < cnt || b < xcnt) {
-    const uint32_t wa = a < cnt ? ns[a] : 0xFFFFFFFFu;
-    const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
-    const uint32_t tb = b < xcnt ? xr[b] : 0xFFFFFFFFu;
-    uint32_t t; bool lower, inP;
-    if (tb <= ta) {             // explicit incoming: partner is i, I am j
-      t = tb; lower = false; inP = true; b++;
-      if (ta == tb) a++;        // the same partner also sits in my row as a non-inferable entry
-    } else {
-      t = ta; a++;
-      lower = (wa & NS_OUT) != 0;
-      const float4 gtmp = Gin[t];
-      inP = lower || ((wa & NS_BACK) && !meCapped && !(__float_as_uint(gtmp.w) & F_CAPPED));
+                                              uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
+                                              bool lower, SubstepAcc& acc) {
+  const float4 gt = Gin[t];
+  if ((__float_as_uint(gt.w) & F_COLLIDER) != F_COLLIDER) return;            // :441
+  double mx, my; bool moves;
+  if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
+    acc.hits++;
+    if (lower) acc.outHits++;
+    if (moves) {
+      acc.x = fround(dadd((double)acc.x, mx));
+      acc.y = fround(dadd((double)acc.y, my));
     }
-    const float4 gt = Gin[t];
-    const uint32_t ft = __float_as_uint(gt.w);
-    if (!inP || (ft & F_COLLIDER) != F_COLLIDER) continue;
-    double mx, my; bool moves;
-    if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
-      acc.hits++;
-      if (lower) acc.outHits++;
-      if (moves) {
-        acc.x = fround(dadd((double)acc.x, mx));
-        acc.y = fround(dadd((double)acc.y, my));
+  }
+}
+
+// next explicit source slot after `after` (lists are unordered: atomic arrival order)
+__device__ __forceinline__ uint32_t next_explicit(const BySlot& s, uint32_t Npad, uint32_t head, uint32_t after,
+                                                  bool first) {
+  uint32_t best = 0xFFFFFFFFu;
+  for (uint32_t p = head; p != 0; p = s.XNEXT[p - 1]) {
+    const uint32_t src = (p - 1) % Npad;
+    if ((first || src > after) && src < best) best = src;
+  }
+  return best;
+}
+
+// slow path: explicit incoming pairs and/or a capped own row.  Everything is merged in
+// ascending partner-slot order.
+__device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
+                                          const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
+                                          uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
+                                          uint32_t fw, uint32_t cnt, uint32_t head, SubstepAcc& acc) {
+  const bool meCapped = (fw & F_CAPPED) != 0;
+  uint32_t a = 0;
+  uint32_t tb = next_explicit(s, g.Npad, head, 0, true);
+  if (!meCapped) {
+    while (a < cnt || tb != 0xFFFFFFFFu) {
+      const uint32_t wa = a < cnt ? s.NST[(size_t)a * g.Npad + e] : 0xFFFFFFFFu;
+      const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
+      if (tb <= ta) {             // explicit incoming: partner is i, I am j
+        const uint32_t t = tb;
+        if (ta == tb) a++;        // the same partner also sits in my row as a non-inferable entry
+        tb = next_explicit(s, g.Npad, head, t, false);
+        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
+      } else {
+        a++;
+        const bool lower = (wa & NS_OUT) != 0;
+        if (lower || ((wa & NS_BACK) && !(__float_as_uint(Gin[ta].w) & F_CAPPED)))
+          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, ta, lower, acc);
       }
     }
+    return;
+  }
+  // capped: rescan my window without the cap (same order as K4)
+  const float2 q = s.QXY[e];
+  const float2 vi = s.QVI[e];
+  const float vr = vi.x;
+  const uint32_t id = __float_as_uint(vi.y);
+  const double vrSq = dmul((double)vr, (double)vr);
+  int32_t myCol, myRow;
+  cell_of(g, q.x, q.y, myCol, myRow);
+  Window w;
+  if (query_window(g, q.x, q.y, vr, w)) {
+    for (int32_t row = w.r0; row <= w.r1; row++) {
+      const uint32_t t0 = cellStart[(uint32_t)row * g.cols + w.c0];
+      const uint32_t t1 = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+      for (uint32_t t = t0; t < t1; t++) {
+        while (tb < t) {          // explicit partners that sort before this candidate
+          const uint32_t tx = tb;
+          tb = next_explicit(s, g.Npad, head, tx, false);
+          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tx, false, acc);
+        }
+        bool inRow = false; uint32_t wa = 0;
+        if (a < cnt) {
+          wa = s.NST[(size_t)a * g.Npad + e];
+          if ((wa & NS_SLOT_MASK) == t) { inRow = true; a++; }
+        }
+        if (t == e) continue;
+        if (tb == t) {            // explicit pair from this partner (it is capped or does not see... )
+          tb = next_explicit(s, g.Npad, head, t, false);
+          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
+          continue;
+        }
+        const float2 vt = s.QVI[t];
+        const uint32_t jid = __float_as_uint(vt.y);
+        if (jid > id) {           // my own pair: only if it made it into my (truncated) row
+          if (inRow) apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, true, acc);
+          continue;
+        }
+        // lower-id partner: inferred iff mutual visibility and its row is complete
+        if (__float_as_uint(Gin[t].w) & F_CAPPED) continue;
+        const float2 c = s.QXY[t];
+        const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
+        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+        if (!(d2 < vrSq && d2 > 0)) continue;                       // I do not see it: it pushed explicitly
+        const double crT = ceil(dmul((double)vt.x, g.inv));
+        if (!(d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow))) continue;
+        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
+      }
+    }
+  }
+  while (tb != 0xFFFFFFFFu) {
+    const uint32_t tx = tb;
+    tb = next_explicit(s, g.Npad, head, tx, false);
+    apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tx, false, acc);
   }
 }
 
@@ -481,10 +581,8 @@ __global__ void __launch_bounds__(256)
 k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
           float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
           uint32_t substep) {
-  cg::thread_block_tile<TILE_W> tile = cg::tiled_partition<TILE_W>(cg::this_thread_block());
-  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) / TILE_W;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
-  const uint32_t lane = tile.thread_rank();
   const Params p = *pp;
   const uint32_t frame = ctr->frame;
   const float4 gme = Gin[e];
@@ -496,54 +594,38 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e];
-    const uint32_t xcnt = min(s.XCNT[e], g.xcap);
-    if (xcnt == 0) {
-      const bool meCapped = (fw & F_CAPPED) != 0;
-      const uint32_t* ns = s.NS + (size_t)e * g.Mpad;
-      for (uint32_t n0 = 0; n0 < cnt; n0 += TILE_W) {
-        const uint32_t k = n0 + lane;
-        bool hit = false, moves = false, lower = false;
-        double mx = 0, my = 0;
-        if (k < cnt) {
-          const uint32_t wd = ns[k];
-          const uint32_t t = wd & NS_SLOT_MASK;
-          const float4 gt = Gin[t];
-          const uint32_t ft = __float_as_uint(gt.w);
-          lower = (wd & NS_OUT) != 0;
-          const bool inP = lower || ((wd & NS_BACK) && !meCapped && !(ft & F_CAPPED));
-          if (inP && (ft & F_COLLIDER) == F_COLLIDER)             // :441
-            hit = partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves);
-        }
-        const uint32_t hb = tile.ballot(hit);
-        acc.hits += __popc(hb);
-        acc.outHits += __popc(tile.ballot(hit && lower));
-        uint32_t mb = tile.ballot(hit && moves);
-        while (mb) {                                              // ascending slot order
-          const int src = __ffs(mb) - 1;
-          mb &= mb - 1;
-          const double ax = tile.shfl(mx, src), ay = tile.shfl(my, src);
-          acc.x = fround(dadd((double)acc.x, ax));
-          acc.y = fround(dadd((double)acc.y, ay));
+    const uint32_t xhead = s.XHEAD[e];
+    if (xhead == 0 && !(fw & F_CAPPED)) {
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
+        const uint32_t t = wd & NS_SLOT_MASK;
+        const float4 gt = Gin[t];
+        const uint32_t ft = __float_as_uint(gt.w);
+        const bool lower = (wd & NS_OUT) != 0;
+        if (!(lower || ((wd & NS_BACK) && !(ft & F_CAPPED)))) continue;
+        if ((ft & F_COLLIDER) != F_COLLIDER) continue;            // :441
+        double mx, my; bool moves;
+        if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
+          acc.hits++;
+          if (lower) acc.outHits++;
+          if (moves) {
+            acc.x = fround(dadd((double)acc.x, mx));
+            acc.y = fround(dadd((double)acc.y, my));
+          }
         }
       }
     } else {
-      if (lane == 0) substep_explicit(g, p, s, Gin, frame, substep, e, x, y, r, fw, cnt, xcnt, acc);
-      acc.x = tile.shfl(acc.x, 0); acc.y = tile.shfl(acc.y, 0);
-      acc.hits = tile.shfl(acc.hits, 0); acc.outHits = tile.shfl(acc.outHits, 0);
+      substep_slow(g, p, s, Gin, cellStart, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
-  if (lane == 0) {
-    const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;  // Uint8 wrap (:551-552)
-    if (LAST) {
-      OutRec o;
-      o.x = acc.x; o.y = acc.y; o.px = pxy.x; o.py = pxy.y;
-      o.meta = cc | (acc.outHits << 8);
-      o.pad[0] = o.pad[1] = o.pad[2] = 0;
-      s.OUT[e] = o;
-    } else {
-      Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
-      s.PXY[e] = pxy;
-    }
+  const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
+  if (LAST) {
+    float4* o = reinterpret_cast<float4*>(s.OUT + e);
+    o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
+    o[1] = make_float4(__uint_as_float(cc | (acc.outHits << 8)), 0.f, 0.f, 0.f);
+  } else {
+    Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
+    s.PXY[e] = pxy;
   }
 }
 
@@ -565,10 +647,12 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   if (i < g.N) {
     slot = slotOf[i];
     if (slot != SLOT_NONE) {
-      const OutRec o = s.OUT[slot];
-      d.DP[i] = make_float4(o.x, o.y, o.px, o.py);
-      d.CC[i] = (uint8_t)(o.meta & 0xFFu);
-      outCnt = o.meta >> 8;
+      const float4* o = reinterpret_cast<const float4*>(s.OUT + slot);
+      const float4 o0 = o[0];
+      const uint32_t meta = __float_as_uint(o[1].x);
+      d.DP[i] = o0;
+      d.CC[i] = (uint8_t)(meta & 0xFFu);
+      outCnt = meta >> 8;
     }
   }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -608,10 +692,9 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   const uint32_t fw = __float_as_uint(gme.w);
   if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gme.z, x, y);
   const uint32_t cnt = s.NCNT[slot];
-  const uint32_t* ns = s.NS + (size_t)slot * g.Mpad;
   const uint32_t frame = ctr->frame;
   for (uint32_t k = 0; k < cnt && base < g.maxPairs; k++) {
-    const uint32_t wd = ns[k];
+    const uint32_t wd = s.NST[(size_t)k * g.Npad + slot];
     if (!(wd & NS_OUT)) continue;
     const uint32_t t = wd & NS_SLOT_MASK;
     const float4 gt = Glast[t];
@@ -619,7 +702,7 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
     double mx, my; bool moves;
     if (partner_pair(g, p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, gt, true, mx, my, moves)) {
       coll[1 + 2 * (size_t)base] = (int32_t)i;                       // :556-557
-      coll[2 + 2 * (size_t)base] = (int32_t)s.SID[t];
+      coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.QVI[t].y);
       base++;
     }
   }
