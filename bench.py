@@ -36,7 +36,7 @@ METRIC = "entity_substep_updates_per_sec"
 UNIT = "entity-substeps/s"
 
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
-                "k_explicit_capped", "k_substep(xS)", "k_writeback"]
+                "k_capped_rescan+k_sort_lists", "k_substep(xS)", "k_writeback"]
 
 
 def workload(name, n_override=None):

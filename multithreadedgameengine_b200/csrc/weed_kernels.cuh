@@ -353,7 +353,6 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     t = cellStart[(uint32_t)row * g.cols + w.c0];
     b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
   }
-  bool any = false;           // pushed an explicit pair or capped -> nothing else to do here
   do {
     uint32_t cnt = 0;
     while (!done && cnt < K4_CH) {
@@ -383,7 +382,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
       myId[cnt] = jid;
       myD2[cnt] = fround(d2);
       // pair (id, jid) is in P but the partner cannot infer it from its own row
-      if (out && !back) { explicit_push(s, ctr, tc, (n * g.Npad) + e); any = true; }
+      if (out && !back) explicit_push(s, ctr, tc, (n * g.Npad) + e);
       cnt++;
       if (++n >= M) done = true;                      // :264
     }
@@ -414,18 +413,94 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (e >= A) return;
-  if (n >= M && M > 0) {
-    // capped row: partners cannot trust their NS_BACK bit for me, so every pair I own becomes
-    // explicit (the !back ones were pushed above).  Incoming pairs are found by an uncapped
-    // window rescan in the substep kernel.
-    for (uint32_t k = 0; k < n; k++) {
-      const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
-      if ((wd & NS_OUT) && (wd & NS_BACK)) explicit_push(s, ctr, wd & NS_SLOT_MASK, k * g.Npad + e);
-    }
-    reinterpret_cast<uint32_t*>(s.G0 + e)[3] |= F_CAPPED;
-  }
-  (void)any;
+  // capped row: my row may be missing partners; K4b finds the lower-id ones (SURVEY A.3 cap)
+  if (n >= M && M > 0) reinterpret_cast<uint32_t*>(s.G0 + e)[3] |= F_CAPPED;
   s.NCNT[e] = n;
+  if (n >= M && M > 0) ctr->anyCapped = 1;
+}
+
+// is slot `key` listed in the (ascending) internal row of entity k?  returns position or -1
+__device__ __forceinline__ int row_find(const GridDims& g, const BySlot& s, uint32_t k, uint32_t key) {
+  int lo = 0, hi = (int)s.NCNT[k] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t v = s.NST[(size_t)mid * g.Npad + k] & NS_SLOT_MASK;
+    if (v == key) return mid;
+    if (v < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// ---- K4b: capped rows (rare) -----------------------------------------------------------------
+// A capped row may have lost lower-id partners that do list this entity.  Rescan the window
+// past the cap, in DESCENDING slot order, and push every lower-id partner whose own row
+// contains me onto my explicit list (LIFO push => the list comes out ascending).
+__global__ void __launch_bounds__(128)
+k_capped_rescan(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
+  if (!ctr->anyCapped) return;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cellStart[g.cells]) return;
+  if (!(__float_as_uint(s.G0[e].w) & F_CAPPED)) return;
+  const uint32_t cnt = s.NCNT[e];
+  if (cnt == 0) return;
+  const uint32_t lastSlot = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
+  const float2 q = s.QXY[e];
+  const float2 vi = s.QVI[e];
+  const float vr = vi.x;
+  const uint32_t id = __float_as_uint(vi.y);
+  const double vrSq = dmul((double)vr, (double)vr);
+  int32_t myCol, myRow;
+  cell_of(g, q.x, q.y, myCol, myRow);
+  Window w;
+  if (!query_window(g, q.x, q.y, vr, w)) return;
+  for (int32_t row = w.r1; row >= w.r0; row--) {
+    const uint32_t a = cellStart[(uint32_t)row * g.cols + w.c0];
+    const uint32_t b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+    for (uint32_t t = b; t-- > a;) {
+      if (t <= lastSlot) return;                       // everything from here on is in my row
+      if (t == e) continue;
+      const float2 vt = s.QVI[t];
+      if (__float_as_uint(vt.y) > id) continue;        // my own pair, lost to the cap: not in P
+      const float2 c = s.QXY[t];
+      const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
+      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+      if (!(d2 < vrSq && d2 > 0)) continue;            // I do not see it: it pushed the pair itself
+      const double crT = ceil(dmul((double)vt.x, g.inv));
+      if (!(d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow))) continue;
+      const int pos = row_find(g, s, t, e);
+      if (pos >= 0) explicit_push(s, ctr, e, (uint32_t)pos * g.Npad + t);
+    }
+  }
+}
+
+// ---- K4c: put every explicit list in ascending source-slot order (adaptive insertion) ---------
+__global__ void __launch_bounds__(256)
+k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr) {
+  if (!ctr->explicitPairs) return;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cellStart[g.cells]) return;
+  uint32_t p = s.XHEAD[e];
+  if (p == 0 || s.XNEXT[p - 1] == 0) return;
+  uint32_t head = 0, tail = 0, tailKey = 0;
+  while (p != 0) {
+    const uint32_t nxt = s.XNEXT[p - 1];
+    const uint32_t key = (p - 1) % g.Npad;
+    if (head == 0) { head = tail = p; tailKey = key; s.XNEXT[p - 1] = 0; }
+    else if (key >= tailKey) { s.XNEXT[tail - 1] = p; s.XNEXT[p - 1] = 0; tail = p; tailKey = key; }
+    else if (key < (head - 1) % g.Npad) { s.XNEXT[p - 1] = head; head = p; }
+    else {
+      uint32_t qn = head;
+      while (true) {
+        const uint32_t qx = s.XNEXT[qn - 1];
+        if (qx == 0 || (qx - 1) % g.Npad > key) break;
+        qn = qx;
+      }
+      s.XNEXT[p - 1] = s.XNEXT[qn - 1];
+      s.XNEXT[qn - 1] = p;
+    }
+    p = nxt;
+  }
+  s.XHEAD[e] = head;
 }
 
 // ---- K6: one constraint substep (physics_worker.js:323-395, 405-568), J-order ---------------
@@ -437,11 +512,9 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
 // Pair membership (P = {(i,j): i<j, j in row(i), both active colliders}), seen from entity e:
 //   - row entry with NS_OUT (partner id higher): the pair is mine.
 //   - partner k with lower id: the pair exists iff I am in row(k).
-//       k capped            -> k pushed all its pairs on the explicit lists (K4)
-//       k does not see back -> impossible here; if k sees me and I do not see k, k pushed it
-//       k uncapped, mutual  -> inferred: from my row entry (NS_BACK) when my row is complete,
-//                              or, when MY row is capped (k may be missing from it), from an
-//                              uncapped rescan of my window.
+//       k sees me, I do not see k      -> k pushed the pair on my explicit list in K4
+//       mutual, k in my row            -> NS_BACK; if k's row is capped, binary-search it for me
+//       mutual, k cut from my capped row -> found by K4b's uncapped rescan, on my explicit list
 struct SubstepAcc { float x, y; uint32_t hits, outHits; };
 
 __device__ __forceinline__ bool partner_pair(const GridDims& g, const Params& p, const BySlot& s,
@@ -483,96 +556,35 @@ __device__ __forceinline__ void apply_partner(const GridDims& g, const Params& p
   }
 }
 
-// next explicit source slot after `after` (lists are unordered: atomic arrival order)
-__device__ __forceinline__ uint32_t next_explicit(const BySlot& s, uint32_t Npad, uint32_t head, uint32_t after,
-                                                  bool first) {
-  uint32_t best = 0xFFFFFFFFu;
-  for (uint32_t p = head; p != 0; p = s.XNEXT[p - 1]) {
-    const uint32_t src = (p - 1) % Npad;
-    if ((first || src > after) && src < best) best = src;
-  }
-  return best;
+// incoming row entry (partner id lower): am I in the partner's row?
+__device__ __forceinline__ bool incoming_in_P(const GridDims& g, const BySlot& s, uint32_t wd, uint32_t ft,
+                                              uint32_t t, uint32_t e) {
+  if (!(wd & NS_BACK)) return false;
+  if (!(ft & F_CAPPED)) return true;
+  return row_find(g, s, t, e) >= 0;
 }
 
-// slow path: explicit incoming pairs and/or a capped own row.  Everything is merged in
-// ascending partner-slot order.
+// slow path: entities with explicit incoming pairs.  The list was sorted by k_sort_lists, so
+// this is a linear merge of two ascending streams (row entries, explicit sources).
 __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
-                                          const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
-                                          uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
-                                          uint32_t fw, uint32_t cnt, uint32_t head, SubstepAcc& acc) {
-  const bool meCapped = (fw & F_CAPPED) != 0;
-  uint32_t a = 0;
-  uint32_t tb = next_explicit(s, g.Npad, head, 0, true);
-  if (!meCapped) {
-    while (a < cnt || tb != 0xFFFFFFFFu) {
-      const uint32_t wa = a < cnt ? s.NST[(size_t)a * g.Npad + e] : 0xFFFFFFFFu;
-      const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
-      if (tb <= ta) {             // explicit incoming: partner is i, I am j
-        const uint32_t t = tb;
-        if (ta == tb) a++;        // the same partner also sits in my row as a non-inferable entry
-        tb = next_explicit(s, g.Npad, head, t, false);
-        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
-      } else {
-        a++;
-        const bool lower = (wa & NS_OUT) != 0;
-        if (lower || ((wa & NS_BACK) && !(__float_as_uint(Gin[ta].w) & F_CAPPED)))
-          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, ta, lower, acc);
-      }
+                                          const float4* __restrict__ Gin, uint32_t frame, uint32_t substep,
+                                          uint32_t e, float x, float y, float r, uint32_t fw, uint32_t cnt,
+                                          uint32_t head, SubstepAcc& acc) {
+  uint32_t a = 0, pl = head;
+  while (a < cnt || pl != 0) {
+    const uint32_t wa = a < cnt ? s.NST[(size_t)a * g.Npad + e] : 0xFFFFFFFFu;
+    const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
+    const uint32_t tb = pl != 0 ? (pl - 1) % g.Npad : 0xFFFFFFFFu;
+    if (tb <= ta) {               // explicit incoming: partner is i, I am j
+      pl = s.XNEXT[pl - 1];
+      if (ta == tb) a++;
+      apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tb, false, acc);
+    } else {
+      a++;
+      const bool lower = (wa & NS_OUT) != 0;
+      if (lower || incoming_in_P(g, s, wa, __float_as_uint(Gin[ta].w), ta, e))
+        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, ta, lower, acc);
     }
-    return;
-  }
-  // capped: rescan my window without the cap (same order as K4)
-  const float2 q = s.QXY[e];
-  const float2 vi = s.QVI[e];
-  const float vr = vi.x;
-  const uint32_t id = __float_as_uint(vi.y);
-  const double vrSq = dmul((double)vr, (double)vr);
-  int32_t myCol, myRow;
-  cell_of(g, q.x, q.y, myCol, myRow);
-  Window w;
-  if (query_window(g, q.x, q.y, vr, w)) {
-    for (int32_t row = w.r0; row <= w.r1; row++) {
-      const uint32_t t0 = cellStart[(uint32_t)row * g.cols + w.c0];
-      const uint32_t t1 = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
-      for (uint32_t t = t0; t < t1; t++) {
-        while (tb < t) {          // explicit partners that sort before this candidate
-          const uint32_t tx = tb;
-          tb = next_explicit(s, g.Npad, head, tx, false);
-          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tx, false, acc);
-        }
-        bool inRow = false; uint32_t wa = 0;
-        if (a < cnt) {
-          wa = s.NST[(size_t)a * g.Npad + e];
-          if ((wa & NS_SLOT_MASK) == t) { inRow = true; a++; }
-        }
-        if (t == e) continue;
-        if (tb == t) {            // explicit pair from this partner (it is capped or does not see... )
-          tb = next_explicit(s, g.Npad, head, t, false);
-          apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
-          continue;
-        }
-        const float2 vt = s.QVI[t];
-        const uint32_t jid = __float_as_uint(vt.y);
-        if (jid > id) {           // my own pair: only if it made it into my (truncated) row
-          if (inRow) apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, true, acc);
-          continue;
-        }
-        // lower-id partner: inferred iff mutual visibility and its row is complete
-        if (__float_as_uint(Gin[t].w) & F_CAPPED) continue;
-        const float2 c = s.QXY[t];
-        const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
-        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        if (!(d2 < vrSq && d2 > 0)) continue;                       // I do not see it: it pushed explicitly
-        const double crT = ceil(dmul((double)vt.x, g.inv));
-        if (!(d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow))) continue;
-        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, t, false, acc);
-      }
-    }
-  }
-  while (tb != 0xFFFFFFFFu) {
-    const uint32_t tx = tb;
-    tb = next_explicit(s, g.Npad, head, tx, false);
-    apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tx, false, acc);
   }
 }
 
@@ -595,14 +607,14 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e];
     const uint32_t xhead = s.XHEAD[e];
-    if (xhead == 0 && !(fw & F_CAPPED)) {
+    if (xhead == 0) {
       for (uint32_t k = 0; k < cnt; k++) {
         const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
         const uint32_t t = wd & NS_SLOT_MASK;
         const float4 gt = Gin[t];
         const uint32_t ft = __float_as_uint(gt.w);
         const bool lower = (wd & NS_OUT) != 0;
-        if (!(lower || ((wd & NS_BACK) && !(ft & F_CAPPED)))) continue;
+        if (!(lower || incoming_in_P(g, s, wd, ft, t, e))) continue;
         if ((ft & F_COLLIDER) != F_COLLIDER) continue;            // :441
         double mx, my; bool moves;
         if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
@@ -615,7 +627,7 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
         }
       }
     } else {
-      substep_slow(g, p, s, Gin, cellStart, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+      substep_slow(g, p, s, Gin, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
