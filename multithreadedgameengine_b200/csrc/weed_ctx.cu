@@ -333,7 +333,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->wbStatus, ctx->wbTiles);
-  A(ctx->s.QXY, N); A(ctx->s.QVI, N); A(ctx->s.G0, N); A(ctx->s.G1, N); A(ctx->s.PXY, N);
+  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.WIN, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N);
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
@@ -470,6 +470,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
     k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   else
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+  k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
   const unsigned kb = blocks_for(g.N, K4_THREADS);
   if (ctx->nd)
@@ -487,19 +488,23 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
 static int launch_constraints(weed_ctx* ctx, bool timing) {
   const GridDims& g = ctx->g;
   cudaStream_t st = ctx->stream;
-  const unsigned tb = blocks_for(g.N, 256);
+  const unsigned tb = blocks_for(g.N, K6_THREADS);
   const int S = ctx->phys.subStepCount;
-  float4* bufs[2] = {ctx->s.G0, ctx->s.G1};
+  // substep 0 reads the slot records (stride 2), later ones ping-pong GA/GB
+  const float4* in = ctx->s.SA;
+  uint32_t gs = 2;
+  float4* bufs[2] = {ctx->s.GA, ctx->s.GB};
   for (int step = 0; step < S; step++) {
-    const float4* in = bufs[step & 1];
-    float4* out = bufs[(step + 1) & 1];
-    if (step == S - 1)
-      k_substep<true><<<tb, 256, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    else
-      k_substep<false><<<tb, 256, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    float4* out = bufs[step & 1];
+    const bool first = step == 0, last = step == S - 1;
+    if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    else if (first)          k_substep<true, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    else if (last)           k_substep<false, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    else                     k_substep<false, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    if (!last) { in = out; gs = 1; }
   }
   TIME_MARK(ctx, timing, 7);
-  k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, bufs[(S - 1) & 1], ctx->slotOf,
+  k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, in, gs, ctx->slotOf,
                                                    ctx->wbTiles, ctx->wbStatus, ctx->dCtr, ctx->coll, (uint32_t)(S - 1));
   k_physics_end<<<1, 32, 0, st>>>(ctx->dCtr);
   TIME_MARK(ctx, timing, 8);
@@ -534,7 +539,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 10 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 11 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -647,7 +652,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 10 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 11 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   return WEED_OK;
 }

@@ -1,10 +1,12 @@
 // weed_kernels.cuh — the per-frame kernels (sm_100a).  See DESIGN.md for the data flow.
 //
-//   id order   k_cell_key      K1  cell key + arrival rank (warp-aggregated atomics)
+//   id order   k_cell_key      K1  cell key + arrival rank (one L2 atomic per entity)
 //   cells      k_cell_scan     K2  exclusive scan, single pass, decoupled look-back
 //   id order   k_scatter_ids   K3a ids into their cell segment (arrival order)
 //   id order   k_build_slots   K3b stable position inside the cell (ascending id), Verlet
-//                                  integration (K5) + derived speed/angle fused, slot records
+//                                  integration (K5) + derived speed/angle fused, one 32 B
+//                                  slot record per entity (the only scattered write)
+//   slot order k_slot_prep     K3c query positions, scan windows, list heads (coalesced)
 //   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
 //                                  warp-cooperative coalesced row flush
 //   slot order k_substep<LAST> K6  bounds + circle-circle correction, J-order
@@ -105,16 +107,9 @@ k_cell_key(GridDims g, const float4* __restrict__ DP, const uint8_t* __restrict_
   int32_t col, row;
   cell_of(g, p.x, p.y, col, row);
   const uint32_t cell = (uint32_t)row * (uint32_t)g.cols + (uint32_t)col;
-  // warp-aggregated counting: one atomic per distinct cell per warp; lanes keep id order
-  const uint32_t amask = __activemask();
-  const uint32_t peers = __match_any_sync(amask, cell);
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(&cellCount[cell], __popc(peers));
-  base = __shfl_sync(peers, base, leader);
+  // arrival rank inside the cell; the stable (ascending id) position is fixed up in K3b
   key[i] = cell;
-  rank[i] = base + __popc(peers & ((1u << lane) - 1));
+  rank[i] = atomicAdd(&cellCount[cell], 1u);
 }
 
 // ---- K2: exclusive scan of the cell histogram, also clears it for the next frame ---------
@@ -185,6 +180,9 @@ k_scatter_ids(uint32_t N, const uint32_t* __restrict__ key, const uint32_t* __re
 // updateDerivedProperties (:591-603; it only reads the vx,vy stored by the integration, so it
 // commutes with the constraint substeps).  INTEGRATE=false builds the slot records of the
 // unchanged state (weed_spatial on its own).
+//
+// The only scattered write is ONE full 32-byte sector per entity (the slot record SA); every
+// other slot-order array is produced by the coalesced k_slot_prep pass.
 struct ById {
   float4* DP;        // x, y, px, py
   float2* ACC;       // ax, ay
@@ -194,14 +192,15 @@ struct ById {
   uint8_t* CC;       // collisionCount
 };
 struct BySlot {
+  float4* SA;        // slot record: SA[2s] = (x, y, radius, flagword), SA[2s+1] = (px, py, visualRange, id bits)
   float2* QXY;       // position at grid-build time (query position)
-  float2* QVI;       // visualRange, entity id (bits)
-  float4* G0;        // x, y, radius, flagword   (substep ping)
-  float4* G1;        //                           (substep pong)
-  float2* PXY;       // px, py
+  int4* WIN;         // clamped scan window of the entity: r0, r1, c0, c1 (r0 > r1: no scan)
+  float4* GA;        // substep ping-pong: x, y, radius, flagword
+  float4* GB;
+  float2* PXY;       // px, py after the first substep
   uint32_t* NCNT;    // neighbor count
   uint32_t* NST;     // internal rows, transposed: NST[k * Npad + slot]
-  uint32_t* XHEAD;   // explicit incoming pairs: list head (0 = empty, else row position + 1)
+  uint32_t* XHEAD;   // explicit incoming pairs: list head (0 = empty, else node + 1)
   uint32_t* XNEXT;   // next link, indexed by the OWNER's row position (k * Npad + slot)
   OutRec* OUT;       // last-substep result
 };
@@ -221,6 +220,7 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   const float4 at = d.AT[i];
   const float x0 = dp.x, y0 = dp.y;
   uint32_t cc = d.CC[i];
+  uint32_t moved = 0;
   if (INTEGRATE) {
     if (f & F_RB_ACTIVE) cc = 0;                                   // :174-177
     if ((f & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) {
@@ -235,6 +235,7 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
       dp.z = dp.x; dp.w = dp.y;                                                // :305-306
       dp.x = fround(dadd((double)x0, ddx));                                    // :301-302
       dp.y = fround(dadd((double)y0, ddy));
+      moved = F_MOVED;
       float4 v;
       v.x = fround(ddiv(ddx, p.dtRatio));                                      // :309-310
       v.y = fround(ddiv(ddy, p.dtRatio));
@@ -273,13 +274,28 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < i;
   const uint32_t slot = s0 + r;
   slotOf[i] = slot;
-  s.QXY[slot] = make_float2(x0, y0);
-  s.QVI[slot] = make_float2(at.z, __uint_as_float(i));
   uint32_t keep = 0;
-  if (afterSpatial) keep = __float_as_uint(s.G0[slot].w) & F_CAPPED;   // rows of this frame already exist
-  else s.XHEAD[slot] = 0;
-  s.G0[slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | (cc << F_CC_SHIFT)));
-  s.PXY[slot] = make_float2(dp.z, dp.w);
+  if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
+    keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & F_CAPPED;   // query position stays the pre-move one
+  }
+  s.SA[2 * (size_t)slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | moved | (cc << F_CC_SHIFT)));
+  s.SA[2 * (size_t)slot + 1] = make_float4(dp.z, dp.w, at.z, __uint_as_float(i));
+}
+
+// ---- K3c: coalesced slot-order pass: query positions, scan windows, list heads ----------------
+__global__ void __launch_bounds__(256)
+k_slot_prep(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cellStart[g.cells]) return;
+  const float4 lo = s.SA[2 * (size_t)e], hi = s.SA[2 * (size_t)e + 1];
+  const bool moved = (__float_as_uint(lo.w) & F_MOVED) != 0;     // integrated: px,py hold the pre-move position
+  const float x0 = moved ? hi.x : lo.x, y0 = moved ? hi.y : lo.y;
+  s.QXY[e] = make_float2(x0, y0);
+  Window w;
+  int4 wi = make_int4(1, 0, 1, 0);
+  if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
+  s.WIN[e] = wi;
+  s.XHEAD[e] = 0;
 }
 
 // ---- K4: capped, ordered neighbor gather (spatial_worker.js:195-277) ---------------------
@@ -287,11 +303,13 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
 // slot range because slots are sorted by (cell, id) and the cells of a grid row are
 // consecutive; the reference's scan order (rows, then columns, then list order) is therefore
 // ascending slot order, so a sequential scan reproduces row content and cap exactly.
-//   * fp32 pre-filter: a candidate whose float32 d2 exceeds vr2 by more than 1e-5 relative is
-//     certainly rejected by the binary64 predicate; everything else is decided in binary64.
-//   * accepted entries are staged in shared memory (15 per thread) and flushed by the whole
-//     warp: API rows (scattered by entity id) are written 16 consecutive words at a time, the
-//     internal transposed rows NST[k][slot] 32 consecutive slots at a time.
+//   * phase 1 (scan): fp32 pre-filter — a candidate whose float32 d2 exceeds vr2 by more than
+//     1e-5 relative is certainly rejected by the binary64 predicate — then the exact binary64
+//     predicate; accepted slots are staged in shared memory (15 per thread and round).
+//   * phase 2 (per staged entry, all lanes in step): partner id, "does the partner's scan
+//     accept me" bit (its precomputed window + its visualRange), explicit pushes.
+//   * flush by the whole warp: API rows (scattered by entity id) are written 16 consecutive
+//     words at a time, the internal transposed rows NST[k][slot] 32 consecutive slots at a time.
 //
 // An explicit pair is a row entry of its owner (the lower id), so the owner's row position
 // (k * Npad + slot) is a unique pool index: incoming pairs of a target form a linked list
@@ -299,15 +317,6 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
 __device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, uint32_t dstSlot, uint32_t ownerRowPos) {
   s.XNEXT[ownerRowPos] = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
   atomicAdd(&ctr->explicitPairs, 1u);
-}
-
-// does the scan of an entity at (x,y) with cell radius cr (spatial_worker.js:211-231) visit the
-// in-grid cell (col,row)?  The clamps of :228-231 cannot exclude an in-grid cell.
-__device__ __forceinline__ bool window_visits(const GridDims& g, float x, float y, double cr, int32_t col, int32_t row) {
-  const double c0 = (double)js_toint32(dmul((double)x, g.inv));
-  const double r0 = (double)js_toint32(dmul((double)y, g.inv));
-  return dsub(r0, cr) <= (double)row && (double)row <= dadd(r0, cr) &&
-         dsub(c0, cr) <= (double)col && (double)col <= dadd(c0, cr);
 }
 
 static constexpr int K4_THREADS = 128;
@@ -328,67 +337,77 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t A = cellStart[g.cells];
   const uint32_t M = g.M;
-  bool done = true;
+  const bool live = e < A;
   float2 q = make_float2(0.f, 0.f);
   float vr = 0.f;
   uint32_t id = 0;
-  Window w; w.r0 = 0; w.r1 = -1; w.c0 = 0; w.c1 = 0;
-  if (e < A) {
+  int4 win = make_int4(1, 0, 1, 0);
+  if (live) {
     q = s.QXY[e];
-    const float2 vi = s.QVI[e];
-    vr = vi.x; id = __float_as_uint(vi.y);
-    done = !(M > 0 && query_window(g, q.x, q.y, vr, w));
+    const float4 hi = s.SA[2 * (size_t)e + 1];
+    vr = hi.z; id = __float_as_uint(hi.w);
+    win = s.WIN[e];
   }
+  bool done = !(live && M > 0 && win.x <= win.y);
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
-  const double myCr = ceil(dmul((double)vr, g.inv));
-  const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf fall through)
+  const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf compare false)
   int32_t myCol = 0, myRow = 0;
-  if (e < A) cell_of(g, q.x, q.y, myCol, myRow);     // my clamped cell (for partners' windows)
+  if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
   const size_t rowBase = (size_t)id * (1 + (size_t)M);
   uint32_t n = 0;
-  int32_t row = w.r0;
+  int32_t row = win.x;
   uint32_t t = 0, b = 0;
   if (!done) {
-    t = cellStart[(uint32_t)row * g.cols + w.c0];
-    b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+    t = cellStart[(uint32_t)row * g.cols + win.z];
+    b = cellStart[(uint32_t)row * g.cols + win.w + 1];
   }
   do {
+    // ---- phase 1: scan -----------------------------------------------------------------------
     uint32_t cnt = 0;
-    while (!done && cnt < K4_CH) {
+    while (!done) {
       if (t >= b) {
-        if (++row > w.r1) { done = true; break; }
-        t = cellStart[(uint32_t)row * g.cols + w.c0];
-        b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+        if (++row > win.y) { done = true; break; }
+        t = cellStart[(uint32_t)row * g.cols + win.z];
+        b = cellStart[(uint32_t)row * g.cols + win.w + 1];
         continue;
       }
       const uint32_t tc = t++;
-      if (tc == e) continue;                          // :249
       const float2 c = s.QXY[tc];
       const float fx = c.x - q.x, fy = c.y - q.y;
-      const float d2f = fx * fx + fy * fy;
-      if (d2f > vrSqF && d2f < 3.0e38f) continue;     // certainly d2 >= vr2
-      const double dX = dsub((double)c.x, myX);       // :252-254
+      if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;   // certainly d2 >= vr2
+      const double dX = dsub((double)c.x, myX);           // :252-254
       const double dY = dsub((double)c.y, myY);
       const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-      if (!(d2 < vrSq && d2 > 0)) continue;           // :257
-      const float2 vt = s.QVI[tc];
-      const uint32_t jid = __float_as_uint(vt.y);
-      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric.
-      const double crT = (vt.x == vr) ? myCr : ceil(dmul((double)vt.x, g.inv));
-      const bool back = d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow);
-      const bool out = jid > id;
-      myW[cnt] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
-      myId[cnt] = jid;
+      if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
+      myW[cnt] = tc;
       myD2[cnt] = fround(d2);
-      // pair (id, jid) is in P but the partner cannot infer it from its own row
-      if (out && !back) explicit_push(s, ctr, tc, (n * g.Npad) + e);
       cnt++;
-      if (++n >= M) done = true;                      // :264
+      if (++n >= M) { done = true; break; }               // :264
+      if (cnt == K4_CH) break;
+    }
+    // ---- phase 2: partner attributes of the staged entries -------------------------------------
+    const uint32_t first = n - cnt;                       // row position of my first staged entry
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint32_t tc = myW[k];
+      const float2 c = s.QXY[tc];
+      const float4 ht = s.SA[2 * (size_t)tc + 1];
+      const int4 wt = s.WIN[tc];
+      const uint32_t jid = __float_as_uint(ht.w);
+      const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric,
+      // d2 > 0 holds, its scan must visit my cell.
+      const bool back = d2 < dmul((double)ht.z, (double)ht.z) &&
+                        myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+      const bool out = jid > id;
+      myW[k] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
+      myId[k] = jid;
+      // pair (id, jid) is in P but the partner cannot infer it from its own row
+      if (out && !back) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
     }
     __syncwarp();
     // ---- warp-cooperative flush -------------------------------------------------------------
-    const uint32_t first = n - cnt;                   // row position of my first staged entry
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
     for (uint32_t k = 0; k < kmax; k++)
       if (k < cnt) s.NST[(size_t)(first + k) * g.Npad + e] = myW[k];
@@ -398,7 +417,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
         const uint32_t src = s2 * 2 + h;
         const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
         const uint32_t f = __shfl_sync(0xffffffffu, first, src);
-        const uint32_t fin = __shfl_sync(0xffffffffu, (uint32_t)(done && (e < A)), src);
+        const uint32_t fin = __shfl_sync(0xffffffffu, (uint32_t)(done && live), src);
         const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
         if (f == 0 && fin) {
           // whole row in this round: header + entries in one contiguous store
@@ -412,11 +431,13 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     }
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
-  if (e >= A) return;
-  // capped row: my row may be missing partners; K4b finds the lower-id ones (SURVEY A.3 cap)
-  if (n >= M && M > 0) reinterpret_cast<uint32_t*>(s.G0 + e)[3] |= F_CAPPED;
+  if (!live) return;
+  // capped row: my row may be missing partners; K4b finds the lower-id ones
+  if (n >= M && M > 0) {
+    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+    ctr->anyCapped = 1;
+  }
   s.NCNT[e] = n;
-  if (n >= M && M > 0) ctr->anyCapped = 1;
 }
 
 // is slot `key` listed in the (ascending) internal row of entity k?  returns position or -1
@@ -440,33 +461,31 @@ k_capped_rescan(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Co
   if (!ctr->anyCapped) return;
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
-  if (!(__float_as_uint(s.G0[e].w) & F_CAPPED)) return;
+  if (!(__float_as_uint(s.SA[2 * (size_t)e].w) & F_CAPPED)) return;
   const uint32_t cnt = s.NCNT[e];
   if (cnt == 0) return;
   const uint32_t lastSlot = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
   const float2 q = s.QXY[e];
-  const float2 vi = s.QVI[e];
-  const float vr = vi.x;
-  const uint32_t id = __float_as_uint(vi.y);
+  const float4 hi = s.SA[2 * (size_t)e + 1];
+  const float vr = hi.z;
+  const uint32_t id = __float_as_uint(hi.w);
   const double vrSq = dmul((double)vr, (double)vr);
   int32_t myCol, myRow;
   cell_of(g, q.x, q.y, myCol, myRow);
-  Window w;
-  if (!query_window(g, q.x, q.y, vr, w)) return;
-  for (int32_t row = w.r1; row >= w.r0; row--) {
-    const uint32_t a = cellStart[(uint32_t)row * g.cols + w.c0];
-    const uint32_t b = cellStart[(uint32_t)row * g.cols + w.c1 + 1];
+  const int4 win = s.WIN[e];
+  for (int32_t row = win.y; row >= win.x; row--) {
+    const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
+    const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
     for (uint32_t t = b; t-- > a;) {
       if (t <= lastSlot) return;                       // everything from here on is in my row
-      if (t == e) continue;
-      const float2 vt = s.QVI[t];
-      if (__float_as_uint(vt.y) > id) continue;        // my own pair, lost to the cap: not in P
+      const float4 ht = s.SA[2 * (size_t)t + 1];
+      if (__float_as_uint(ht.w) > id) continue;        // my own pair, lost to the cap: not in P
       const float2 c = s.QXY[t];
       const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
       const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
       if (!(d2 < vrSq && d2 > 0)) continue;            // I do not see it: it pushed the pair itself
-      const double crT = ceil(dmul((double)vt.x, g.inv));
-      if (!(d2 < dmul((double)vt.x, (double)vt.x) && window_visits(g, c.x, c.y, crT, myCol, myRow))) continue;
+      const int4 wt = s.WIN[t];
+      if (!(d2 < dmul((double)ht.z, (double)ht.z) && myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w)) continue;
       const int pos = row_find(g, s, t, e);
       if (pos >= 0) explicit_push(s, ctr, e, (uint32_t)pos * g.Npad + t);
     }
@@ -515,44 +534,36 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
 //       k sees me, I do not see k      -> k pushed the pair on my explicit list in K4
 //       mutual, k in my row            -> NS_BACK; if k's row is capped, binary-search it for me
 //       mutual, k cut from my capped row -> found by K4b's uncapped rescan, on my explicit list
+//
+// Two phases per entity: phase 1 walks the row with a float32 pre-filter of the overlap test
+// (physics_worker.js:455) and stages the few partners that may overlap; phase 2 runs the
+// exact binary64 pair code on the staged ones, in order.
 struct SubstepAcc { float x, y; uint32_t hits, outHits; };
 
-__device__ __forceinline__ bool partner_pair(const GridDims& g, const Params& p, const BySlot& s,
-                                             uint32_t frame, uint32_t substep, uint32_t e, float x, float y,
-                                             float r, uint32_t fw, uint32_t t, float4 gt, bool iAmLower,
-                                             double& mx, double& my, bool& moves) {
-  const uint32_t ft = __float_as_uint(gt.w);
-  float xt = gt.x, yt = gt.y;
-  if ((ft & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gt.z, xt, yt);  // partner after ITS boundary pass
-  // fp32 pre-filter of :455 (dist2 >= minDist^2): certain when beyond 1e-5 relative
-  {
-    const float fx = x - xt, fy = y - yt, md = r + gt.z;
-    const float d2f = fx * fx + fy * fy;
-    if (d2f > md * md * 1.00001f && d2f < 3.0e38f) { moves = false; mx = 0; my = 0; return false; }
-  }
-  PairMove m;
-  if (iAmLower) m = pair_eval(p, frame, substep, s.QVI, e, t, x, y, r, fw, xt, yt, gt.z, ft);
-  else          m = pair_eval(p, frame, substep, s.QVI, t, e, xt, yt, gt.z, ft, x, y, r, fw);
-  if (iAmLower) { moves = m.moveI; mx = m.mx; my = m.my; }
-  else          { moves = m.moveJ; mx = -m.mx; my = -m.my; }
-  moves = moves && m.hit;
-  return m.hit;
+// partner position after ITS boundary pass
+__device__ __forceinline__ void partner_pos(const GridDims& g, float4 gt, float& xt, float& yt) {
+  xt = gt.x; yt = gt.y;
+  if ((__float_as_uint(gt.w) & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gt.z, xt, yt);
 }
 
-__device__ __forceinline__ void apply_partner(const GridDims& g, const Params& p, const BySlot& s,
-                                              const float4* __restrict__ Gin, uint32_t frame, uint32_t substep,
-                                              uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
-                                              bool lower, SubstepAcc& acc) {
-  const float4 gt = Gin[t];
-  if ((__float_as_uint(gt.w) & F_COLLIDER) != F_COLLIDER) return;            // :441
-  double mx, my; bool moves;
-  if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
-    acc.hits++;
-    if (lower) acc.outHits++;
-    if (moves) {
-      acc.x = fround(dadd((double)acc.x, mx));
-      acc.y = fround(dadd((double)acc.y, my));
-    }
+// float32 pre-filter of :455 (dist2 >= minDist^2): true = certainly no overlap
+__device__ __forceinline__ bool surely_apart(float x, float y, float r, float xt, float yt, float rt) {
+  const float fx = x - xt, fy = y - yt, md = r + rt;
+  return __fmaf_rn(fx, fx, fy * fy) > md * md * 1.00001f;
+}
+
+__device__ __forceinline__ void exact_pair(const Params& p, const BySlot& s, uint32_t frame, uint32_t substep,
+                                           uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
+                                           float xt, float yt, float rt, uint32_t ft, bool lower, SubstepAcc& acc) {
+  PairMove m;
+  if (lower) m = pair_eval(p, frame, substep, s.SA, e, t, x, y, r, fw, xt, yt, rt, ft);
+  else       m = pair_eval(p, frame, substep, s.SA, t, e, xt, yt, rt, ft, x, y, r, fw);
+  if (!m.hit) return;
+  acc.hits++;
+  if (lower) acc.outHits++;
+  if (lower ? m.moveI : m.moveJ) {
+    acc.x = fround(dadd((double)acc.x, lower ? m.mx : -m.mx));
+    acc.y = fround(dadd((double)acc.y, lower ? m.my : -m.my));
   }
 }
 
@@ -567,38 +578,51 @@ __device__ __forceinline__ bool incoming_in_P(const GridDims& g, const BySlot& s
 // slow path: entities with explicit incoming pairs.  The list was sorted by k_sort_lists, so
 // this is a linear merge of two ascending streams (row entries, explicit sources).
 __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
-                                          const float4* __restrict__ Gin, uint32_t frame, uint32_t substep,
-                                          uint32_t e, float x, float y, float r, uint32_t fw, uint32_t cnt,
-                                          uint32_t head, SubstepAcc& acc) {
+                                          const float4* __restrict__ Gin, uint32_t gs, uint32_t frame,
+                                          uint32_t substep, uint32_t e, float x, float y, float r, uint32_t fw,
+                                          uint32_t cnt, uint32_t head, SubstepAcc& acc) {
   uint32_t a = 0, pl = head;
   while (a < cnt || pl != 0) {
     const uint32_t wa = a < cnt ? s.NST[(size_t)a * g.Npad + e] : 0xFFFFFFFFu;
     const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
     const uint32_t tb = pl != 0 ? (pl - 1) % g.Npad : 0xFFFFFFFFu;
+    uint32_t t; bool lower;
     if (tb <= ta) {               // explicit incoming: partner is i, I am j
       pl = s.XNEXT[pl - 1];
       if (ta == tb) a++;
-      apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, tb, false, acc);
+      t = tb; lower = false;
     } else {
       a++;
-      const bool lower = (wa & NS_OUT) != 0;
-      if (lower || incoming_in_P(g, s, wa, __float_as_uint(Gin[ta].w), ta, e))
-        apply_partner(g, p, s, Gin, frame, substep, e, x, y, r, fw, ta, lower, acc);
+      t = ta; lower = (wa & NS_OUT) != 0;
+      if (!lower && !incoming_in_P(g, s, wa, __float_as_uint(Gin[(size_t)ta * gs].w), ta, e)) continue;
     }
+    const float4 gt = Gin[(size_t)t * gs];
+    const uint32_t ft = __float_as_uint(gt.w);
+    if ((ft & F_COLLIDER) != F_COLLIDER) continue;                 // :441
+    float xt, yt;
+    partner_pos(g, gt, xt, yt);
+    if (surely_apart(x, y, r, xt, yt, gt.z)) continue;
+    exact_pair(p, s, frame, substep, e, x, y, r, fw, t, xt, yt, gt.z, ft, lower, acc);
   }
 }
 
-template <bool LAST>
-__global__ void __launch_bounds__(256)
-k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
+static constexpr int K6_THREADS = 256;
+static constexpr int K6_STAGE = 6;      // staged possible overlaps per thread
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(K6_THREADS)
+k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin, uint32_t gs,
           float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
           uint32_t substep) {
+  __shared__ uint32_t sStage[K6_STAGE][K6_THREADS];
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
   const Params p = *pp;
   const uint32_t frame = ctr->frame;
-  const float4 gme = Gin[e];
-  float2 pxy = s.PXY[e];
+  const float4 gme = Gin[(size_t)e * gs];
+  float2 pxy;
+  if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
+  else pxy = s.PXY[e];
   float x = gme.x, y = gme.y;
   const float r = gme.z;
   const uint32_t fw = __float_as_uint(gme.w);
@@ -608,26 +632,34 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
     const uint32_t cnt = s.NCNT[e];
     const uint32_t xhead = s.XHEAD[e];
     if (xhead == 0) {
-      for (uint32_t k = 0; k < cnt; k++) {
-        const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
-        const uint32_t t = wd & NS_SLOT_MASK;
-        const float4 gt = Gin[t];
-        const uint32_t ft = __float_as_uint(gt.w);
-        const bool lower = (wd & NS_OUT) != 0;
-        if (!(lower || incoming_in_P(g, s, wd, ft, t, e))) continue;
-        if ((ft & F_COLLIDER) != F_COLLIDER) continue;            // :441
-        double mx, my; bool moves;
-        if (partner_pair(g, p, s, frame, substep, e, x, y, r, fw, t, gt, lower, mx, my, moves)) {
-          acc.hits++;
-          if (lower) acc.outHits++;
-          if (moves) {
-            acc.x = fround(dadd((double)acc.x, mx));
-            acc.y = fround(dadd((double)acc.y, my));
-          }
+      uint32_t k = 0;
+      while (k < cnt) {
+        // phase 1: stage the partners that may overlap
+        uint32_t nh = 0;
+        for (; k < cnt && nh < K6_STAGE; k++) {
+          const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
+          const uint32_t t = wd & NS_SLOT_MASK;
+          const float4 gt = Gin[(size_t)t * gs];
+          const uint32_t ft = __float_as_uint(gt.w);
+          if ((ft & F_COLLIDER) != F_COLLIDER) continue;          // :441
+          if (!(wd & NS_OUT) && !incoming_in_P(g, s, wd, ft, t, e)) continue;
+          float xt, yt;
+          partner_pos(g, gt, xt, yt);
+          if (surely_apart(x, y, r, xt, yt, gt.z)) continue;
+          sStage[nh++][threadIdx.x] = wd;
+        }
+        // phase 2: exact pair code, in row order
+        for (uint32_t h = 0; h < nh; h++) {
+          const uint32_t wd = sStage[h][threadIdx.x];
+          const uint32_t t = wd & NS_SLOT_MASK;
+          const float4 gt = Gin[(size_t)t * gs];
+          float xt, yt;
+          partner_pos(g, gt, xt, yt);
+          exact_pair(p, s, frame, substep, e, x, y, r, fw, t, xt, yt, gt.z, __float_as_uint(gt.w), (wd & NS_OUT) != 0, acc);
         }
       }
     } else {
-      substep_slow(g, p, s, Gin, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+      substep_slow(g, p, s, Gin, gs, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
@@ -648,7 +680,7 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
 // reference's emission order (i ascending, then row position; physics_worker.js:555-567).
 __global__ void __launch_bounds__(WB_THREADS)
 k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const float4* __restrict__ Glast,
-            const uint32_t* __restrict__ slotOf, uint32_t numTiles, unsigned long long* status,
+            uint32_t gs, const uint32_t* __restrict__ slotOf, uint32_t numTiles, unsigned long long* status,
             Counters* ctr, int32_t* __restrict__ coll, uint32_t lastSubstep) {
   __shared__ uint32_t s_tile, s_excl, s_warp[WB_THREADS / 32];
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->wbTile, 1u);
@@ -699,7 +731,7 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   if (coll == nullptr || outCnt == 0 || base >= g.maxPairs) return;
   // re-derive my colliding outgoing pairs on the last sweep's start positions
   const Params p = *pp;
-  const float4 gme = Glast[slot];
+  const float4 gme = Glast[(size_t)slot * gs];
   float x = gme.x, y = gme.y;
   const uint32_t fw = __float_as_uint(gme.w);
   if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gme.z, x, y);
@@ -709,12 +741,17 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
     const uint32_t wd = s.NST[(size_t)k * g.Npad + slot];
     if (!(wd & NS_OUT)) continue;
     const uint32_t t = wd & NS_SLOT_MASK;
-    const float4 gt = Glast[t];
-    if ((__float_as_uint(gt.w) & F_COLLIDER) != F_COLLIDER) continue;
-    double mx, my; bool moves;
-    if (partner_pair(g, p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, gt, true, mx, my, moves)) {
+    const float4 gt = Glast[(size_t)t * gs];
+    const uint32_t ft = __float_as_uint(gt.w);
+    if ((ft & F_COLLIDER) != F_COLLIDER) continue;
+    float xt, yt;
+    partner_pos(g, gt, xt, yt);
+    if (surely_apart(x, y, gme.z, xt, yt, gt.z)) continue;
+    SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
+    exact_pair(p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, xt, yt, gt.z, ft, true, acc);
+    if (acc.hits) {
       coll[1 + 2 * (size_t)base] = (int32_t)i;                       // :556-557
-      coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.QVI[t].y);
+      coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.SA[2 * (size_t)t + 1].w);
       base++;
     }
   }
