@@ -322,6 +322,8 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
   g.Npad = ((g.N + 31) / 32) * 32;
   g.maxPairs = cfg->maxCollisionPairs;
+  g.Wsafe = nextafterf((float)(g.worldW * (1.0 - 2.4e-7)), 0.0f);
+  g.Hsafe = nextafterf((float)(g.worldH * (1.0 - 2.4e-7)), 0.0f);
   const size_t N = g.N;
   int rc;
 #define A(ptr, count) if ((rc = dalloc(ctx, &(ptr), (count))) != WEED_OK) return bail(rc)

@@ -365,26 +365,36 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   do {
     // ---- phase 1: scan -----------------------------------------------------------------------
     uint32_t cnt = 0;
-    while (!done) {
+    while (!done && cnt < K4_CH) {
       if (t >= b) {
         if (++row > win.y) { done = true; break; }
         t = cellStart[(uint32_t)row * g.cols + win.z];
         b = cellStart[(uint32_t)row * g.cols + win.w + 1];
         continue;
       }
-      const uint32_t tc = t++;
-      const float2 c = s.QXY[tc];
-      const float fx = c.x - q.x, fy = c.y - q.y;
-      if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;   // certainly d2 >= vr2
-      const double dX = dsub((double)c.x, myX);           // :252-254
-      const double dY = dsub((double)c.y, myY);
-      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-      if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
-      myW[cnt] = tc;
-      myD2[cnt] = fround(d2);
-      cnt++;
-      if (++n >= M) { done = true; break; }               // :264
-      if (cnt == K4_CH) break;
+      // four candidate positions in flight (consecutive slots), then decide one by one
+      const uint32_t m = min(4u, b - t);
+      float2 cand[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) cand[u] = s.QXY[min(t + (uint32_t)u, b - 1)];
+      uint32_t used = m;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if ((uint32_t)u >= used) break;
+        const float2 c = cand[u];
+        const float fx = c.x - q.x, fy = c.y - q.y;
+        if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;   // certainly d2 >= vr2
+        const double dX = dsub((double)c.x, myX);           // :252-254
+        const double dY = dsub((double)c.y, myY);
+        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+        if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
+        myW[cnt] = t + (uint32_t)u;
+        myD2[cnt] = fround(d2);
+        cnt++;
+        if (++n >= M) { done = true; used = (uint32_t)u + 1; }          // :264
+        else if (cnt == K4_CH) used = (uint32_t)u + 1;
+      }
+      t += used;
     }
     // ---- phase 2: partner attributes of the staged entries -------------------------------------
     const uint32_t first = n - cnt;                       // row position of my first staged entry
@@ -543,7 +553,7 @@ struct SubstepAcc { float x, y; uint32_t hits, outHits; };
 // partner position after ITS boundary pass
 __device__ __forceinline__ void partner_pos(const GridDims& g, float4 gt, float& xt, float& yt) {
   xt = gt.x; yt = gt.y;
-  if ((__float_as_uint(gt.w) & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gt.z, xt, yt);
+  if ((__float_as_uint(gt.w) & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, xt, yt, gt.z)) apply_bounds_pos(g, gt.z, xt, yt);
 }
 
 // float32 pre-filter of :455 (dist2 >= minDist^2): true = certainly no overlap
@@ -607,7 +617,7 @@ __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, co
 }
 
 static constexpr int K6_THREADS = 256;
-static constexpr int K6_STAGE = 6;      // staged possible overlaps per thread
+static constexpr int K6_STAGE = 8;      // staged possible overlaps per thread
 
 template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(K6_THREADS)
@@ -626,7 +636,7 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
   float x = gme.x, y = gme.y;
   const float r = gme.z;
   const uint32_t fw = __float_as_uint(gme.w);
-  if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds(g, p.boundaryElasticity, r, x, y, pxy.x, pxy.y);
+  if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, x, y, r)) apply_bounds(g, p.boundaryElasticity, r, x, y, pxy.x, pxy.y);
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e];
@@ -634,19 +644,26 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
     if (xhead == 0) {
       uint32_t k = 0;
       while (k < cnt) {
-        // phase 1: stage the partners that may overlap
+        // phase 1: stage the partners that may overlap (4 row words, then 4 gathers in flight)
         uint32_t nh = 0;
-        for (; k < cnt && nh < K6_STAGE; k++) {
-          const uint32_t wd = s.NST[(size_t)k * g.Npad + e];
-          const uint32_t t = wd & NS_SLOT_MASK;
-          const float4 gt = Gin[(size_t)t * gs];
-          const uint32_t ft = __float_as_uint(gt.w);
-          if ((ft & F_COLLIDER) != F_COLLIDER) continue;          // :441
-          if (!(wd & NS_OUT) && !incoming_in_P(g, s, wd, ft, t, e)) continue;
-          float xt, yt;
-          partner_pos(g, gt, xt, yt);
-          if (surely_apart(x, y, r, xt, yt, gt.z)) continue;
-          sStage[nh++][threadIdx.x] = wd;
+        for (; k < cnt && nh + 4 <= K6_STAGE; k += 4) {
+          uint32_t wd[4];
+          float4 gt[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) wd[u] = s.NST[(size_t)min(k + (uint32_t)u, cnt - 1) * g.Npad + e];
+#pragma unroll
+          for (int u = 0; u < 4; u++) gt[u] = Gin[(size_t)(wd[u] & NS_SLOT_MASK) * gs];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (k + (uint32_t)u >= cnt) break;
+            const uint32_t ft = __float_as_uint(gt[u].w);
+            if ((ft & F_COLLIDER) != F_COLLIDER) continue;        // :441
+            if (!(wd[u] & NS_OUT) && !incoming_in_P(g, s, wd[u], ft, wd[u] & NS_SLOT_MASK, e)) continue;
+            float xt, yt;
+            partner_pos(g, gt[u], xt, yt);
+            if (surely_apart(x, y, r, xt, yt, gt[u].z)) continue;
+            sStage[nh++][threadIdx.x] = wd[u];
+          }
         }
         // phase 2: exact pair code, in row order
         for (uint32_t h = 0; h < nh; h++) {
