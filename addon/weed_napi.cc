@@ -1,0 +1,166 @@
+// weed_napi.cc — thin Node N-API addon over the C ABI of include/weedgpu.h.
+//
+// NOT compiled in this image (no node, no node_api.h); kept as the reference-side binding a
+// WeedJS maintainer would build with node-gyp:  it contains no logic, only argument
+// marshalling.  The SharedArrayBuffers the engine allocates (src/core/gameEngine.js:534-777)
+// are passed by reference: napi_get_arraybuffer_info yields the base pointer that
+// weed_bind() pins and mirrors on the device.
+//
+//   const weed = require('./build/Release/weed_napi.node');
+//   const ctx = weed.create({entityCount, worldWidth, worldHeight, cellSize, maxNeighbors,
+//                            maxCollisionPairs, seed, physics: {...}});
+//   weed.bind(ctx, weed.BUF_TRANSFORM, buffers.componentData.Transform);   // SharedArrayBuffer
+//   ...
+//   weed.step(ctx, dtRatio, uploadMask, downloadMask);
+#include <node_api.h>
+
+#include <cstring>
+
+#include "../include/weedgpu.h"
+
+#define NAPI_OK(call)                                             \
+  do {                                                            \
+    if ((call) != napi_ok) {                                      \
+      napi_throw_error(env, nullptr, "weed_napi: " #call);        \
+      return nullptr;                                             \
+    }                                                             \
+  } while (0)
+
+static bool get_double(napi_env env, napi_value obj, const char* key, double* out) {
+  napi_value v;
+  bool has = false;
+  if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return false;
+  if (napi_get_named_property(env, obj, key, &v) != napi_ok) return false;
+  return napi_get_value_double(env, v, out) == napi_ok;
+}
+
+static napi_value throw_weed(napi_env env, weed_ctx* ctx, int rc) {
+  napi_throw_error(env, nullptr, weed_last_error(ctx));
+  (void)rc;
+  return nullptr;
+}
+
+static void fill_physics(napi_env env, napi_value p, weed_physics_config* out) {
+  double d;
+  if (get_double(env, p, "subStepCount", &d)) out->subStepCount = (int32_t)d;
+  if (get_double(env, p, "boundaryElasticity", &d)) out->boundaryElasticity = d;
+  if (get_double(env, p, "collisionResponseStrength", &d)) out->collisionResponseStrength = d;
+  if (get_double(env, p, "verletDamping", &d)) out->verletDamping = d;
+  if (get_double(env, p, "minSpeedForRotation", &d)) out->minSpeedForRotation = d;
+  napi_value g;
+  bool has = false;
+  if (napi_has_named_property(env, p, "gravity", &has) == napi_ok && has &&
+      napi_get_named_property(env, p, "gravity", &g) == napi_ok) {
+    if (get_double(env, g, "x", &d)) out->gravityX = d;
+    if (get_double(env, g, "y", &d)) out->gravityY = d;
+  }
+}
+
+// create(config) -> external(ctx)        replaces new Worker(spatial|physics) + "init"
+static napi_value Create(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value arg;
+  NAPI_OK(napi_get_cb_info(env, info, &argc, &arg, nullptr, nullptr));
+  weed_config cfg;
+  weed_default_config(&cfg);
+  double d;
+  if (get_double(env, arg, "entityCount", &d)) cfg.entityCount = (uint32_t)d;
+  if (get_double(env, arg, "worldWidth", &d)) cfg.worldWidth = d;
+  if (get_double(env, arg, "worldHeight", &d)) cfg.worldHeight = d;
+  if (get_double(env, arg, "cellSize", &d)) cfg.cellSize = d;
+  if (get_double(env, arg, "maxNeighbors", &d)) cfg.maxNeighbors = (uint32_t)d;
+  if (get_double(env, arg, "maxCollisionPairs", &d) && d > 0) cfg.maxCollisionPairs = (uint32_t)d;  // `|| 10000`
+  if (get_double(env, arg, "seed", &d)) cfg.seed = d;
+  if (get_double(env, arg, "device", &d)) cfg.device = (int32_t)d;
+  napi_value p;
+  bool has = false;
+  if (napi_has_named_property(env, arg, "physics", &has) == napi_ok && has &&
+      napi_get_named_property(env, arg, "physics", &p) == napi_ok)
+    fill_physics(env, p, &cfg.physics);
+  weed_ctx* ctx = nullptr;
+  const int rc = weed_create(&cfg, &ctx);
+  if (rc != WEED_OK) return throw_weed(env, nullptr, rc);
+  napi_value ext;
+  NAPI_OK(napi_create_external(env, ctx, [](napi_env, void* data, void*) { weed_destroy((weed_ctx*)data); }, nullptr, &ext));
+  return ext;
+}
+
+static weed_ctx* ctx_of(napi_env env, napi_value v) {
+  void* p = nullptr;
+  napi_get_value_external(env, v, &p);
+  return (weed_ctx*)p;
+}
+
+// bind(ctx, bufferId, SharedArrayBuffer)
+static napi_value Bind(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value a[3];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  int32_t id;
+  NAPI_OK(napi_get_value_int32(env, a[1], &id));
+  void* base = nullptr;
+  size_t bytes = 0;
+  NAPI_OK(napi_get_arraybuffer_info(env, a[2], &base, &bytes));   // also accepts SharedArrayBuffer (N-API >= 8)
+  const int rc = weed_bind(ctx, (weed_buffer_id)id, base, bytes);
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
+// step(ctx, dtRatio, uploadMask, downloadMask)     replaces both workers' update()
+static napi_value Step(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value a[4];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  double dt;
+  uint32_t up, down;
+  NAPI_OK(napi_get_value_double(env, a[1], &dt));
+  NAPI_OK(napi_get_value_uint32(env, a[2], &up));
+  NAPI_OK(napi_get_value_uint32(env, a[3], &down));
+  const int rc = weed_step(ctx, dt, up, down);
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
+// setPhysics(ctx, partialConfig)      replaces {msg:"updatePhysicsConfig"}
+static napi_value SetPhysics(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value a[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  weed_physics_config p;
+  weed_get_physics(ctx, &p);
+  fill_physics(env, a[1], &p);
+  const int rc = weed_set_physics(ctx, &p);
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
+// fetchNeighbors(ctx, first, count)   rows -> the bound neighborData / distanceData SABs
+static napi_value FetchNeighbors(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value a[3];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  uint32_t first, count;
+  NAPI_OK(napi_get_value_uint32(env, a[1], &first));
+  NAPI_OK(napi_get_value_uint32(env, a[2], &count));
+  const int rc = weed_fetch_neighbors(ctx, first, count);
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
+static napi_value Init(napi_env env, napi_value exports) {
+  napi_property_descriptor props[] = {
+      {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"bind", nullptr, Bind, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"step", nullptr, Step, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"setPhysics", nullptr, SetPhysics, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"fetchNeighbors", nullptr, FetchNeighbors, nullptr, nullptr, nullptr, napi_default, nullptr},
+  };
+  napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
+  return exports;
+}
+
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)
