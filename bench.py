@@ -35,6 +35,10 @@ import numpy as np  # noqa: E402
 METRIC = "entity_substep_updates_per_sec"
 UNIT = "entity-substeps/s"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/), config4 16M on one B200; None = not captured for this kernel.
+TRAFFIC_FROM_NCU = {}
+
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
                 "k_capped_rescan+k_sort_lists", "k_substep(xS)", "k_writeback"]
 
@@ -160,8 +164,8 @@ def run_reference(args):
     base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, args.cpu_sample)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": describe(args.workload, workload(args.workload, 1000)[0] if False else cfg),
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(args.workload, cfg),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -190,55 +194,84 @@ def run_ours(args):
         dist.barrier()
     from multithreadedgameengine_b200 import binding as B
     from multithreadedgameengine_b200.engine import GameEngine
+    from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs
 
     name = args.workload
-    n_total = args.entities
-    # N>1: slab exchange is not built yet -> every rank runs an independent replica of the
-    # single-GPU workload (weak scaling, no data-path collective); see DESIGN.md.
-    cfg, cols = workload(name, n_total)
+    cfg, cols = workload(name, args.entities)      # every rank builds the same seeded scene
     S = cfg["physics"]["subStepCount"]
+    N = cfg["entityCount"]
+    active = int(cols["T.active"].sum())
+    plan = plan_slabs(cfg, cols, world) if world > 1 else None
     stream = torch.cuda.Stream()
-    with torch.cuda.stream(stream):
-        eng = GameEngine(cfg, device=local, stream=stream.cuda_stream, host_neighbor_rows=False)
-        eng.load_columns(cols)
-        active = int(cols["T.active"].sum())
 
-        def barrier():
+    def make(flags=0):
+        if world == 1:
+            e = GameEngine(cfg, device=local, flags=flags, stream=stream.cuda_stream, host_neighbor_rows=False)
+            e.load_columns(cols)
+            return e, e
+        sl = SlabEngine(cfg, cols, rank, world, device=local, flags=flags, stream=stream.cuda_stream, plan=plan)
+        return sl, sl.eng
+
+    def frames(obj, k):
+        if world == 1:
+            obj.run(k)
+        else:
+            for _ in range(k):
+                obj.step_dist()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
             torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-                torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    with torch.cuda.stream(stream):
+        obj, eng = make()
         # ---- device-resident timing ---------------------------------------------------------
-        eng.run(args.warmup)
+        frames(obj, args.warmup)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
+            t_wall = time.perf_counter()
             e0.record(stream)
-            eng.run(args.steps)
+            frames(obj, args.steps)
             e1.record(stream)
             barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+            wall = time.perf_counter() - t_wall
+        # one rank alone is pure device work (events); with slabs the exchange has host-side
+        # phases, so the wall clock of the same region is the honest figure
+        ms = max_over_ranks(e0.elapsed_time(e1) if world == 1 else max(e0.elapsed_time(e1), wall * 1e3))
         st = eng.stats()
-        kbar = st["neighborsTotal"] / max(1, st["activeInGrid"])
-        value = world * active * S * args.steps / (ms * 1e-3)
+        owned_total = active if world == 1 else int(round(sum_over_ranks(obj.owned)))
+        kbar = sum_over_ranks(st["neighborsTotal"]) / max(1.0, sum_over_ranks(st["activeInGrid"]))
+        value = owned_total * S * args.steps / (ms * 1e-3)
+        halo_frac = 0.0 if world == 1 else sum_over_ranks(st["activeInGrid"]) / max(1, owned_total) - 1.0
+        xbytes = 0 if world == 1 else int(sum_over_ranks(obj.sent_bytes))
 
-        # ---- per-kernel CUDA-event timing (same frames continue; direct launches) -------------
-        eng_t = GameEngine(cfg, device=local, flags=B.FLAG_KERNEL_TIMING, stream=stream.cuda_stream, host_neighbor_rows=False)
-        eng_t.load_columns(cols)
-        eng_t.run(args.warmup + args.steps)   # bring it to the same simulation state
+        # ---- per-kernel CUDA-event timing (direct launches; same frames, same state) ----------
+        obj_t, eng_t = make(B.FLAG_KERNEL_TIMING)
+        frames(obj_t, args.warmup + args.steps)
         acc = np.zeros(8)
         for _ in range(args.steps):
-            eng_t.run(1)
+            frames(obj_t, 1)
             acc += np.array(eng_t.stats()["ms"][:8])
         kms = acc / args.steps
         st_t = eng_t.stats()
-        kbar_t = st_t["neighborsTotal"] / max(1, st_t["activeInGrid"])
-        eng_t.close()
+        local_active = st_t["activeInGrid"]
+        kbar_t = st_t["neighborsTotal"] / max(1, local_active)
+        (obj_t.close if world > 1 else eng_t.close)()
         top = int(np.argmax(kms))
         F, per_kernel = algorithmic_bytes(kbar_t, S)
         alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
@@ -249,54 +282,57 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg * active / (kms[top] * 1e-3) / 1e9
+        achieved = alg * local_active / (kms[top] * 1e-3) / 1e9     # this rank's kernel over the entities it processes
+        frame_gbps = F * owned_total * args.steps / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": TRAFFIC_FROM_NCU.get(KERNEL_NAMES[top]),
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                    "algorithmic_bytes_per_entity": alg, "kernel_ms": kms[top],
-                    "whole_frame": {"bytes_per_entity_frame": F, "achieved_GBps": F * active * args.steps / (ms * 1e-3) / 1e9,
-                                    "frac": F * active * args.steps / (ms * 1e-3) / 1e9 / peak}}
+                    "algorithmic_bytes_per_entity": alg, "kernel_ms": float(kms[top]), "entities_per_launch": int(local_active),
+                    "whole_frame": {"bytes_per_entity_frame": F, "achieved_GBps_all_gpus": frame_gbps,
+                                    "frac_of_n_gpus_peak": frame_gbps / (peak * world)}}
 
         # ---- end to end through the host-facing API -----------------------------------------------
         up = eng.mask("RB.ax", "RB.ay")
         down = eng.mask("T.x", "T.y", "RB.vx", "RB.vy", "RB.velocityAngle", "RB.speed")
-        for _ in range(min(3, args.warmup)):
+
+        def e2e_frame():
             eng.step(1.0, up, down)
+            if world > 1:
+                obj.exchange_dist()
+
+        for _ in range(min(3, args.warmup)):
+            e2e_frame()
         barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
         t_wall = time.perf_counter()
         for _ in range(args.steps):
-            eng.step(1.0, up, down)
-        e3.record(stream)
+            e2e_frame()
         barrier()
-        wall = time.perf_counter() - t_wall
-        ms_e2e = max(e2.elapsed_time(e3), wall * 1e3)
-        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-        N = cfg["entityCount"]
-        e2e = {"value": world * active * S * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 24 * N, "ms_per_step": ms_e2e / args.steps,
-               "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"}
-        launches = st["kernelLaunchesPerStep"] * args.steps
-        eng.close()
+        ms_e2e = max_over_ranks((time.perf_counter() - t_wall) * 1e3)
+        n_host = eng.totalEntityCount
+        e2e = {"value": owned_total * S * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum_over_ranks(8 * n_host)), "d2h_bytes_per_step": int(sum_over_ranks(24 * n_host)),
+               "ms_per_step": ms_e2e / args.steps,
+               "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"
+                      + ("; + SlabEngine.exchange_dist per frame" if world > 1 else "")}
+        launches = st["kernelLaunchesPerStep"] * args.steps + (3 * args.steps if world > 1 else 0)
+        (obj.close if world > 1 else eng.close)()
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu, _, _ = cpu_reference(name, args.cpu_steps, 1, args.cpu_sample)
         conf = describe(name, cfg)
-        conf.update({"parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab exchange not built yet)",
+        conf.update({"parallelism": "1 GPU" if world == 1 else
+                     f"{world} row slabs (1 per GPU), halo {plan[1]} rows recomputed redundantly, 1 NCCL neighbour exchange per frame",
                      "kbar": kbar, "active": active, "l2_policy": "working set >> 126 MB L2 (inputs larger than L2)"
-                     if cfg["entityCount"] > 2_000_000 else "working set may fit L2; frames are back-to-back on evolving state",
-                     "kernel_ms": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
+                     if N / world > 2_000_000 else "per-GPU working set comparable to L2; frames run back-to-back on evolving state",
+                     "kernel_ms_rank0": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
-                     "collision_pairs_last_substep": st["collisionPairs"]})
+                     "collision_pairs_last_substep": st["collisionPairs"],
+                     "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk.summary()}
         print(json.dumps(line))

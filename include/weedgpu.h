@@ -135,6 +135,8 @@ typedef struct weed_config {
    * clamped cell row lies in [slabRowBegin, slabRowEnd) are owned; 0,0 = whole world. */
   uint32_t slabRowBegin;
   uint32_t slabRowEnd;
+  uint32_t slabHaloRows;         /* replicated rows beyond each cut: (S+1)*ceil(max visualRange/cellSize) */
+  uint32_t _pad1;
 } weed_config;
 
 typedef struct weed_stats {
@@ -213,6 +215,28 @@ typedef enum weed_devptr_id {
   WEED_DEV_VEL       = 5   /* float4 [N] {vx, vy, speed, -}                             */
 } weed_devptr_id;
 int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
+
+/* ---- multi-GPU slabs (SURVEY §8 e) ----------------------------------------
+ * A slab context (slabRowEnd > 0) holds a LOCAL entity table of `entityCount` slots; every
+ * slot carries a global entity id.  Component buffers, neighbor rows and column masks are
+ * then indexed by local slot.  Ownership follows position: the context owns the entities
+ * whose cell row lies in [slabRowBegin, slabRowEnd); slabHaloRows rows beyond each cut are
+ * replicas that are recomputed redundantly during the frame and dropped at its end, so ONE
+ * exchange per frame carries both the halo refresh and entity migration.  Exchange buffers
+ * are plain device memory of 64-byte records; the host moves them between adjacent slabs
+ * (torch.distributed / NCCL send-recv, or a device-to-device copy in one process).          */
+#define WEED_SLAB_RECORD_BYTES 64
+/* global ids of local slots [0,count); slots >= count are free.  Call after weed_upload.   */
+int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t count);
+/* gids_out[capacity] (0xFFFFFFFF for free slots), *top_out = slots in use                  */
+int weed_slab_get_gids(weed_ctx* ctx, uint32_t* gids_out, uint32_t* top_out);
+/* after a frame: records for the low / high neighbour into device buffers of `capacity`
+ * records each; returns the record counts and the number of entities owned this frame.      */
+int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t capacity,
+                   uint32_t* n_low, uint32_t* n_high, uint32_t* n_owned);
+/* drop this frame's replicas, then insert the neighbours' records                           */
+int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, uint32_t n_low,
+                    const void* dev_from_high, uint32_t n_high, uint32_t* new_top);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,8 @@ class Config(C.Structure):
                 ("maxNeighbors", C.c_uint32), ("maxCollisionPairs", C.c_uint32),
                 ("seed", C.c_double), ("physics", PhysicsConfig),
                 ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
-                ("slabRowBegin", C.c_uint32), ("slabRowEnd", C.c_uint32)]
+                ("slabRowBegin", C.c_uint32), ("slabRowEnd", C.c_uint32),
+                ("slabHaloRows", C.c_uint32), ("_pad1", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -88,7 +89,13 @@ SYMBOLS = {
     "weed_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "weed_last_error": (C.c_char_p, [C.c_void_p]),
     "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "weed_slab_set_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "weed_slab_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
 }
+SLAB_RECORD_BYTES = 64
 
 _LIB = None
 

@@ -167,6 +167,11 @@ struct weed_ctx {
   cudaEvent_t ev[KS_COUNT + 8] = {};
   float ms[12] = {};
   uint32_t launchesPerStep = 0;
+  // slabs
+  bool slab = false;
+  uint32_t slabTop = 0;
+  uint32_t* holes = nullptr;
+  SlabCounters* dSlab = nullptr;
 };
 
 #define CK(call)                                                                              \
@@ -322,6 +327,12 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
   g.Npad = ((g.N + 31) / 32) * 32;
   g.maxPairs = cfg->maxCollisionPairs;
+  g.slabBegin = 0; g.slabEnd = g.rows; g.slabHalo = 0;
+  if (cfg->slabRowEnd > 0) {
+    if (cfg->slabRowBegin >= cfg->slabRowEnd || (int32_t)cfg->slabRowEnd > g.rows) { ctx->err = "bad slab rows"; return bail(WEED_E_INVALID); }
+    ctx->slab = true;
+    g.slabBegin = (int32_t)cfg->slabRowBegin; g.slabEnd = (int32_t)cfg->slabRowEnd; g.slabHalo = (int32_t)cfg->slabHaloRows;
+  }
   g.Wsafe = nextafterf((float)(g.worldW * (1.0 - 2.4e-7)), 0.0f);
   g.Hsafe = nextafterf((float)(g.worldH * (1.0 - 2.4e-7)), 0.0f);
   const size_t N = g.N;
@@ -343,6 +354,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
   A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
   A(ctx->dParams, 1); A(ctx->dCtr, 1);
+  if (ctx->slab) { A(ctx->d.GID, N); A(ctx->s.SLID, N); A(ctx->holes, N); A(ctx->dSlab, 1); }
   for (int c = 0; c < 19; c++) {
     uint8_t* p = nullptr;
     if ((rc = dalloc(ctx, &p, N * kHot[c].bytes)) != WEED_OK) return bail(rc);
@@ -466,7 +478,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   TIME_MARK(ctx, timing, 1);
   k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr);
   TIME_MARK(ctx, timing, 2);
-  k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds);
+  k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds, ctx->d.GID);
   TIME_MARK(ctx, timing, 3);
   if (integrate)
     k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
@@ -674,5 +686,74 @@ extern "C" int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, 
   }
   *out = p;
   if (bytes) *bytes = b;
+  return WEED_OK;
+}
+
+// =============================================================================================
+// slabs
+// =============================================================================================
+extern "C" int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t count) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (!gids || count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "bad gid list");
+  CK(cudaMemsetAsync(ctx->d.GID, 0xFF, (size_t)ctx->g.N * 4, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d.GID, gids, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->slabTop = count;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_get_gids(weed_ctx* ctx, uint32_t* gids_out, uint32_t* top_out) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (gids_out) {
+    CK(cudaMemcpyAsync(gids_out, ctx->d.GID, (size_t)ctx->g.N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (top_out) *top_out = ctx->slabTop;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t capacity,
+                              uint32_t* n_low, uint32_t* n_high, uint32_t* n_owned) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  CK(cudaMemsetAsync(ctx->dSlab, 0, sizeof(SlabCounters), ctx->stream));
+  if (ctx->slabTop)
+    k_slab_pack<<<blocks_for(ctx->slabTop, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, ctx->slabTop, (SlabRec*)dev_low,
+                                                                        (SlabRec*)dev_high, capacity, ctx->dSlab);
+  SlabCounters sc;
+  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (sc.overflow) return fail(ctx, WEED_E_OVERFLOW, "slab exchange buffer too small: " + std::to_string(sc.nLow) + " / " + std::to_string(sc.nHigh) + " records");
+  if (n_low) *n_low = sc.nLow;
+  if (n_high) *n_high = sc.nHigh;
+  if (n_owned) *n_owned = sc.owned;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, uint32_t n_low, const void* dev_from_high,
+                               uint32_t n_high, uint32_t* new_top) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  CK(cudaMemsetAsync(ctx->dSlab, 0, sizeof(SlabCounters), ctx->stream));
+  const uint32_t top = ctx->slabTop;
+  if (top) k_slab_drop<<<blocks_for(top, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, top, ctx->holes, ctx->dSlab);
+  SlabCounters sc;
+  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_low)
+    k_slab_unpack<<<blocks_for(n_low, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_low, n_low, 0, ctx->holes, sc.nHoles, top, ctx->g.N, ctx->dSlab);
+  if (n_high)
+    k_slab_unpack<<<blocks_for(n_high, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_high, n_high, n_low, ctx->holes, sc.nHoles, top, ctx->g.N, ctx->dSlab);
+  CK(cudaGetLastError());
+  const uint64_t total = (uint64_t)n_low + n_high;
+  uint64_t nt = top;
+  if (total > sc.nHoles) nt = (uint64_t)top + (total - sc.nHoles);
+  if (nt > ctx->g.N) return fail(ctx, WEED_E_OVERFLOW, "slab entity table full: need " + std::to_string(nt) + " slots, capacity " + std::to_string(ctx->g.N));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->slabTop = (uint32_t)nt;
+  ctx->spatialValid = false;
+  if (new_top) *new_top = ctx->slabTop;
   return WEED_OK;
 }

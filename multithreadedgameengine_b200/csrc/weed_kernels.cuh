@@ -167,12 +167,13 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
 // ---- K3a: ids into their cell segment, arrival order ------------------------------------
 __global__ void __launch_bounds__(256)
 k_scatter_ids(uint32_t N, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank,
-              const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ arrIds) {
+              const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ arrIds,
+              const uint32_t* __restrict__ GID) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const uint32_t k = key[i];
   if (k == KEY_INVALID) return;
-  arrIds[cellStart[k] + rank[i]] = i;
+  arrIds[cellStart[k] + rank[i]] = GID ? GID[i] : i;   // the id that orders the cell list
 }
 
 // ---- K3b + K5: slot records, Verlet integration, derived properties ----------------------
@@ -190,6 +191,7 @@ struct ById {
   float4* V;         // vx, vy, speed, -
   uint8_t* F;        // flag bits
   uint8_t* CC;       // collisionCount
+  uint32_t* GID;     // slab mode: global entity id of each local slot (nullptr: id = index)
 };
 struct BySlot {
   float4* SA;        // slot record: SA[2s] = (x, y, radius, flagword), SA[2s+1] = (px, py, visualRange, id bits)
@@ -203,6 +205,7 @@ struct BySlot {
   uint32_t* XHEAD;   // explicit incoming pairs: list head (0 = empty, else node + 1)
   uint32_t* XNEXT;   // next link, indexed by the OWNER's row position (k * Npad + slot)
   OutRec* OUT;       // last-substep result
+  uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
 };
 
 template <bool INTEGRATE>
@@ -269,17 +272,21 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   }
   // stable position: number of ids in my cell smaller than mine (cell lists are ascending
   // in the reference because it inserts i = 0..N-1 in order, spatial_worker.js:146,168)
+  const uint32_t gid = d.GID ? d.GID[i] : i;
   const uint32_t s0 = cellStart[k], s1 = cellStart[k + 1];
   uint32_t r = 0;
-  for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < i;
+  for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < gid;
   const uint32_t slot = s0 + r;
   slotOf[i] = slot;
+  const int32_t crow = (int32_t)(k / (uint32_t)g.cols);
+  const uint32_t owned = (crow >= g.slabBegin && crow < g.slabEnd) ? F_OWNED : 0u;
+  if (s.SLID) s.SLID[slot] = i;
   uint32_t keep = 0;
   if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
     keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & F_CAPPED;   // query position stays the pre-move one
   }
-  s.SA[2 * (size_t)slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | moved | (cc << F_CC_SHIFT)));
-  s.SA[2 * (size_t)slot + 1] = make_float4(dp.z, dp.w, at.z, __uint_as_float(i));
+  s.SA[2 * (size_t)slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | moved | owned | (cc << F_CC_SHIFT)));
+  s.SA[2 * (size_t)slot + 1] = make_float4(dp.z, dp.w, at.z, __uint_as_float(gid));
 }
 
 // ---- K3c: coalesced slot-order pass: query positions, scan windows, list heads ----------------
@@ -348,13 +355,14 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     vr = hi.z; id = __float_as_uint(hi.w);
     win = s.WIN[e];
   }
+  const uint32_t lid = (live && s.SLID) ? s.SLID[e] : id;    // row address: local index
   bool done = !(live && M > 0 && win.x <= win.y);
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
   const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf compare false)
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
-  const size_t rowBase = (size_t)id * (1 + (size_t)M);
+  const size_t rowBase = (size_t)lid * (1 + (size_t)M);
   uint32_t n = 0;
   int32_t row = win.x;
   uint32_t t = 0, b = 0;
@@ -683,7 +691,7 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
   if (LAST) {
     float4* o = reinterpret_cast<float4*>(s.OUT + e);
     o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
-    o[1] = make_float4(__uint_as_float(cc | (acc.outHits << 8)), 0.f, 0.f, 0.f);
+    o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
   } else {
     Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
     s.PXY[e] = pxy;
@@ -713,7 +721,8 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
       const uint32_t meta = __float_as_uint(o[1].x);
       d.DP[i] = o0;
       d.CC[i] = (uint8_t)(meta & 0xFFu);
-      outCnt = meta >> 8;
+      outCnt = (meta >> 8) & 0x7FFFFFu;
+      if (!(meta >> 31)) outCnt = 0;               // pairs are logged by the slab that owns the lower id
     }
   }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -767,11 +776,106 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
     SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
     exact_pair(p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, xt, yt, gt.z, ft, true, acc);
     if (acc.hits) {
-      coll[1 + 2 * (size_t)base] = (int32_t)i;                       // :556-557
+      coll[1 + 2 * (size_t)base] = (int32_t)(d.GID ? d.GID[i] : i);  // :556-557
       coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.SA[2 * (size_t)t + 1].w);
       base++;
     }
   }
+}
+
+// ---- slabs (multi-GPU): one exchange per frame -------------------------------------------------
+// Ownership follows position: a context owns the entities whose clamped cell row lies in
+// [slabBegin, slabEnd).  slabHalo rows beyond each cut are replicas; they are recomputed
+// redundantly during the frame and thrown away at its end.  After the frame each context
+//   1. packs its authoritative (owned at frame start) entities that now lie within slabHalo
+//      rows of a cut, or beyond it (migration), into 64-byte records for that neighbour,
+//   2. drops every entity it did not own this frame (replicas) and lists the holes,
+//   3. unpacks the neighbours' records into the holes (or past the table top).
+struct __align__(16) SlabRec {
+  uint32_t gid, meta;     // meta: flag byte | collisionCount << 8
+  float ax, ay;
+  float4 dp;              // x, y, px, py
+  float4 at;              // maxVel, radius, visualRange, velocityAngle
+  float4 v;               // vx, vy, speed, -
+};
+static_assert(sizeof(SlabRec) == 64, "slab record must be 64 bytes");
+
+struct SlabCounters { uint32_t nLow, nHigh, nHoles, top, overflow, owned; };
+
+__device__ __forceinline__ bool present_row(const GridDims& g, const ById& d, uint32_t i, int32_t& row) {
+  const uint32_t f = d.F[i];
+  const float4 p = d.DP[i];
+  if (!(f & F_T_ACTIVE) || p.x != p.x || p.y != p.y) return false;
+  int32_t col;
+  cell_of(g, p.x, p.y, col, row);
+  return true;
+}
+
+// key[] still holds the cell of the frame-START position (ownership during the frame)
+__global__ void __launch_bounds__(256)
+k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, SlabRec* __restrict__ low,
+            SlabRec* __restrict__ high, uint32_t capacity, SlabCounters* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= top) return;
+  const uint32_t k = key[i];
+  if (k == KEY_INVALID) return;
+  const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
+  if (row0 < g.slabBegin || row0 >= g.slabEnd) return;          // not authoritative here
+  atomicAdd(&sc->owned, 1u);
+  int32_t row;
+  if (!present_row(g, d, i, row)) return;
+  const bool toLow = g.slabBegin > 0 && row < g.slabBegin + g.slabHalo;
+  const bool toHigh = g.slabEnd < g.rows && row >= g.slabEnd - g.slabHalo;
+  if (!toLow && !toHigh) return;
+  SlabRec r;
+  r.gid = d.GID[i];
+  r.meta = (uint32_t)d.F[i] | ((uint32_t)d.CC[i] << 8);
+  const float2 a = d.ACC[i];
+  r.ax = a.x; r.ay = a.y;
+  r.dp = d.DP[i]; r.at = d.AT[i]; r.v = d.V[i];
+  if (toLow) {
+    const uint32_t p = atomicAdd(&sc->nLow, 1u);
+    if (p < capacity) low[p] = r; else sc->overflow = 1;
+  }
+  if (toHigh) {
+    const uint32_t p = atomicAdd(&sc->nHigh, 1u);
+    if (p < capacity) high[p] = r; else sc->overflow = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, uint32_t* __restrict__ holes,
+            SlabCounters* sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= top) return;
+  const uint32_t k = key[i];
+  bool keep = false;
+  if (k != KEY_INVALID) {
+    const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
+    keep = row0 >= g.slabBegin && row0 < g.slabEnd;
+  } else {
+    keep = (d.F[i] & F_T_ACTIVE) != 0;    // active but never in the grid (NaN position): stays where it is
+  }
+  if (!keep) {
+    d.F[i] = 0;
+    holes[atomicAdd(&sc->nHoles, 1u)] = i;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_unpack(ById d, const SlabRec* __restrict__ recs, uint32_t n, uint32_t recBase,
+              const uint32_t* __restrict__ holes, uint32_t nHoles, uint32_t top, uint32_t capacity, SlabCounters* sc) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t q = recBase + k;
+  const uint32_t i = q < nHoles ? holes[q] : top + (q - nHoles);
+  if (i >= capacity) { sc->overflow = 1; return; }
+  const SlabRec r = recs[k];
+  d.GID[i] = r.gid;
+  d.F[i] = (uint8_t)(r.meta & 0xFFu);
+  d.CC[i] = (uint8_t)((r.meta >> 8) & 0xFFu);
+  d.ACC[i] = make_float2(r.ax, r.ay);
+  d.DP[i] = r.dp; d.AT[i] = r.at; d.V[i] = r.v;
 }
 
 // ---- host <-> device column plumbing ---------------------------------------------------------

@@ -55,7 +55,7 @@ class PhysicsWorker(_Worker):
 
 
 class GameEngine:
-    def __init__(self, config, device=0, flags=0, stream=None, host_neighbor_rows=True):
+    def __init__(self, config, device=0, flags=0, stream=None, host_neighbor_rows=True, slab=None):
         L = B.lib()
         self.config = dict(config)
         # gameEngine.js:34-49 default merge
@@ -84,6 +84,9 @@ class GameEngine:
         cfg.device = device
         cfg.flags = flags
         cfg.stream = stream
+        if slab is not None:      # (rowBegin, rowEnd, haloRows): this context is one slab of the world
+            cfg.slabRowBegin, cfg.slabRowEnd, cfg.slabHaloRows = (int(v) for v in slab)
+        self.slab = slab
         self.ctx = C.c_void_p()
         rc = L.weed_create(C.byref(cfg), C.byref(self.ctx))
         if rc != B.WEED_OK:

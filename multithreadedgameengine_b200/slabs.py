@@ -1,0 +1,246 @@
+"""World-space row slabs: one libweedgpu context per GPU (SURVEY §8 e).
+
+* Partition: contiguous blocks of grid rows; cell index = row * gridCols + col
+  (spatial_worker.js:161) makes a row block a contiguous cell range, so the reference's
+  row-major scan order is preserved inside a slab.  Cuts are chosen from the row histogram of
+  the start scene so slabs hold equal entity counts.
+* Ownership follows position: a slab owns the entities whose cell row lies in its block.
+* Halo: H = (S+1) * ceil(max visualRange / cellSize) rows beyond each cut are replicated.
+  With H that deep every substep of every owned entity — including the pair-membership
+  inference that looks at a partner's row — only depends on data inside the slab + halo, so
+  the replicas are simply recomputed redundantly and ONE exchange per frame (halo refresh +
+  migration, 64-byte records to the two adjacent slabs) is enough.
+* The exchange moves plain device buffers: `torch.distributed` send/recv (NCCL over NVLink)
+  between processes (`SlabEngine.exchange_dist`), or device-to-device copies between the
+  contexts of one process (`SlabGroup`, used by the single-GPU tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import binding as B
+from .engine import GameEngine
+
+
+def cell_rows(cfg, y):
+    """Clamped grid row of each y (spatial_worker.js:158,160), float64 like the reference."""
+    cs = float(cfg["spatial"]["cellSize"])
+    rows = math.ceil(cfg["worldHeight"] / cs)
+    inv = 1.0 / cs
+    with np.errstate(invalid="ignore"):
+        r = np.trunc(y.astype(np.float64) * inv)
+    r = np.where(np.isfinite(r), r, 0.0)
+    return np.clip(r, 0, rows - 1).astype(np.int64), rows
+
+
+def halo_rows(cfg, cols):
+    """Replicated rows beyond each cut.
+
+    Entities that can move or push (non-trigger colliders) propagate position dependencies one
+    visual range per substep, and the pair-membership inference looks one more range out (a
+    partner's row must be complete): (S+1) * h_dyn.  Observers (triggers such as the Mouse,
+    src/core/Mouse.js:139-145, and non-colliders) never move anybody, so they do not extend the
+    chain; but an owned entity's collisionCount needs the observer's row to be complete when it
+    is capped: 2 * h_obs."""
+    act = cols["T.active"] != 0
+    vr = np.where(np.isfinite(cols["C.visualRange"]), cols["C.visualRange"], 0).astype(np.float64)
+    observer = (cols["C.isTrigger"] != 0) | (cols["C.active"] == 0)
+    cs = float(cfg["spatial"]["cellSize"])
+    S = int(cfg["physics"].get("subStepCount", 4))
+    h_dyn = math.ceil(float(vr[act & ~observer].max(initial=0.0)) / cs)
+    h_obs = math.ceil(float(vr[act & observer].max(initial=0.0)) / cs)
+    return max(1, (S + 1) * h_dyn, 2 * h_obs)
+
+
+def plan_slabs(cfg, cols, world):
+    """-> list of (rowBegin, rowEnd) per rank, equal entity counts, and the halo depth."""
+    act = (cols["T.active"] != 0) & np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"])
+    row, rows = cell_rows(cfg, cols["T.y"])
+    hist = np.bincount(row[act], minlength=rows)
+    cum = np.cumsum(hist)
+    total = int(cum[-1])
+    cuts = [0]
+    for k in range(1, world):
+        target = total * k / world
+        r = int(np.searchsorted(cum, target)) + 1
+        cuts.append(min(max(r, cuts[-1] + 1), rows - (world - k)))
+    cuts.append(rows)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)], halo_rows(cfg, cols)
+
+
+def exchange_records(torch, rank, world, send_low, n_low, send_high, n_high, recv_low, recv_high, capacity):
+    """Neighbour exchange of one frame: first the two record counts, then exactly that many
+    64-byte records, with the adjacent ranks only (rank-1 = low, rank+1 = high).  Works on any
+    backend/device pair torch.distributed supports (NCCL + CUDA tensors on the GPUs, gloo + CPU
+    tensors in the CPU tests).  Returns (records received from low, from high)."""
+    dist = torch.distributed
+    dev = send_low.device
+    cnt_out = torch.tensor([n_low, n_high], dtype=torch.int64, device=dev)
+    cnt_in = torch.zeros(2, dtype=torch.int64, device=dev)
+    lo, hi = rank - 1, rank + 1
+    ops = []
+    if lo >= 0:
+        ops += [dist.P2POp(dist.isend, cnt_out[0:1], lo), dist.P2POp(dist.irecv, cnt_in[0:1], lo)]
+    if hi < world:
+        ops += [dist.P2POp(dist.isend, cnt_out[1:2], hi), dist.P2POp(dist.irecv, cnt_in[1:2], hi)]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    fl, fh = (int(v) for v in cnt_in.tolist())
+    if max(fl, fh) > capacity:
+        raise RuntimeError(f"slab exchange buffer too small: {fl}/{fh} records > {capacity}")
+    R = B.SLAB_RECORD_BYTES
+    ops = []
+    if lo >= 0:
+        if n_low:
+            ops.append(dist.P2POp(dist.isend, send_low[:n_low * R], lo))
+        if fl:
+            ops.append(dist.P2POp(dist.irecv, recv_low[:fl * R], lo))
+    if hi < world:
+        if n_high:
+            ops.append(dist.P2POp(dist.isend, send_high[:n_high * R], hi))
+        if fh:
+            ops.append(dist.P2POp(dist.irecv, recv_high[:fh * R], hi))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return fl, fh
+
+
+class SlabEngine:
+    """One slab = one GameEngine over a LOCAL entity table + the exchange buffers."""
+
+    def __init__(self, cfg, cols, rank, world, device=0, flags=0, stream=None, plan=None,
+                 capacity_factor=1.35, host_neighbor_rows=False):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.blocks, self.H = plan if plan is not None else plan_slabs(cfg, cols, world)
+        self.rb, self.re = self.blocks[rank]
+        row, self.rows = cell_rows(cfg, cols["T.y"])
+        act = cols["T.active"] != 0
+        inside = act & np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"]) & (row >= self.rb - self.H) & (row < self.re + self.H)
+        if rank == 0:   # active entities that never enter the grid (NaN position) live on slab 0
+            inside |= act & ~(np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"]))
+        sel = np.nonzero(inside)[0].astype(np.uint32)
+        self.capacity = int(len(sel) * capacity_factor) + 4096
+        lcfg = dict(cfg)
+        lcfg["entityCount"] = self.capacity
+        self.cfg = cfg
+        self.S = int(cfg["physics"].get("subStepCount", 4))
+        self.eng = GameEngine(lcfg, device=device, flags=flags, stream=stream, host_neighbor_rows=host_neighbor_rows,
+                              slab=(self.rb, self.re, self.H))
+        for k, v in cols.items():
+            self.eng.column(k)[:len(sel)] = v[sel]
+        self.eng.upload(B.COLS_INPUT_ALL)
+        B.check(self.eng.ctx, B.lib().weed_slab_set_gids(self.eng.ctx, sel.ctypes.data, len(sel)))
+        self.top = len(sel)
+        # exchange buffers: the boundary band is a small fraction of a slab
+        self.rec_capacity = max(65536, int(0.25 * self.capacity))
+        dev = torch.device("cuda", device)
+        mk = lambda: torch.empty(self.rec_capacity * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
+        self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
+        self.owned = 0
+        self.sent_bytes = 0
+
+    # ---- one frame of this slab (asynchronous) ---------------------------------------------------
+    def run(self, dtRatio=1.0):
+        self.eng.run(1, dtRatio)
+
+    def pack(self):
+        nl, nh, ow = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        B.check(self.eng.ctx, B.lib().weed_slab_pack(self.eng.ctx, self.send_low.data_ptr(), self.send_high.data_ptr(),
+                                                     self.rec_capacity, C.byref(nl), C.byref(nh), C.byref(ow)))
+        self.owned = ow.value
+        self.sent_bytes = (nl.value + nh.value) * B.SLAB_RECORD_BYTES
+        return nl.value, nh.value
+
+    def apply(self, n_from_low, n_from_high):
+        top = C.c_uint32()
+        B.check(self.eng.ctx, B.lib().weed_slab_apply(self.eng.ctx, self.recv_low.data_ptr(), n_from_low,
+                                                      self.recv_high.data_ptr(), n_from_high, C.byref(top)))
+        self.top = top.value
+
+    def exchange_dist(self):
+        """pack -> counts and records to the two adjacent ranks (NCCL send/recv) -> apply."""
+        nl, nh = self.pack()
+        fl, fh = exchange_records(self.torch, self.rank, self.world, self.send_low, nl, self.send_high, nh,
+                                  self.recv_low, self.recv_high, self.rec_capacity)
+        if self.send_low.is_cuda:
+            self.torch.cuda.current_stream().synchronize()
+        self.apply(fl, fh)
+
+    def step_dist(self, dtRatio=1.0):
+        self.run(dtRatio)
+        self.exchange_dist()
+
+    # ---- results -----------------------------------------------------------------------------------
+    def gids(self):
+        g = np.empty(self.capacity, dtype=np.uint32)
+        top = C.c_uint32()
+        B.check(self.eng.ctx, B.lib().weed_slab_get_gids(self.eng.ctx, g.ctypes.data, C.byref(top)))
+        return g, top.value
+
+    def owned_state(self, keys=("T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.speed", "RB.velocityAngle",
+                                "RB.collisionCount", "RB.ax", "RB.ay")):
+        """(gids, {column: values}) of the entities this slab owns NOW (by current position)."""
+        self.eng.download(B.COLS_INPUT_ALL)
+        g, top = self.gids()
+        c = self.eng.col
+        act = (c["T.active"][:top] != 0)
+        row, _ = cell_rows(self.cfg, c["T.y"][:top])
+        fin = np.isfinite(c["T.x"][:top]) & np.isfinite(c["T.y"][:top])
+        own = act & ((fin & (row >= self.rb) & (row < self.re)) | (~fin & (self.rank == 0)))
+        idx = np.nonzero(own)[0]
+        return g[idx], {k: c[k][idx].copy() for k in keys}, idx
+
+    def close(self):
+        self.eng.close()
+
+
+class SlabGroup:
+    """All slabs of a world inside ONE process (contexts may share a device): the exchange is a
+    device-to-device copy.  Used by the single-GPU tests; the multi-process path is
+    SlabEngine.step_dist."""
+
+    def __init__(self, cfg, cols, world, devices=None, **kw):
+        plan = plan_slabs(cfg, cols, world)
+        devices = devices or [0] * world
+        self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, **kw) for r in range(world)]
+
+    def step(self, dtRatio=1.0):
+        for s in self.slabs:
+            s.run(dtRatio)
+        counts = [s.pack() for s in self.slabs]
+        R = B.SLAB_RECORD_BYTES
+        for r, s in enumerate(self.slabs):
+            fl = fh = 0
+            if r > 0:
+                fl = counts[r - 1][1]                       # the low neighbour's "high" records
+                s.recv_low[:fl * R].copy_(self.slabs[r - 1].send_high[:fl * R])
+            if r + 1 < len(self.slabs):
+                fh = counts[r + 1][0]
+                s.recv_high[:fh * R].copy_(self.slabs[r + 1].send_low[:fh * R])
+            s._incoming = (fl, fh)
+        self.slabs[0].torch.cuda.synchronize()
+        for s in self.slabs:
+            s.apply(*s._incoming)
+
+    def gather(self, N, keys=("T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.speed", "RB.collisionCount")):
+        out = {k: None for k in keys}
+        seen = np.zeros(N, dtype=np.int32)
+        for s in self.slabs:
+            g, vals, _ = s.owned_state(keys)
+            seen[g] += 1
+            for k in keys:
+                if out[k] is None:
+                    out[k] = np.zeros(N, dtype=vals[k].dtype)
+                out[k][g] = vals[k]
+        return out, seen
+
+    def close(self):
+        for s in self.slabs:
+            s.close()

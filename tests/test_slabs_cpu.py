@@ -1,0 +1,104 @@
+"""CPU coverage of the multi-GPU (N > 1) host logic: slab planning, halo depth, and the
+neighbour exchange protocol over torch.distributed with the gloo backend (world_size 2 and 3).
+The kernels themselves are covered on the GPU by tests/test_gpu_slabs.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multithreadedgameengine_b200 import binding as B, scenes
+from multithreadedgameengine_b200.slabs import cell_rows, exchange_records, halo_rows, plan_slabs
+
+
+def test_cell_rows_follow_the_reference_key():
+    cfg = dict(worldHeight=100.0, spatial=dict(cellSize=30.0))
+    y = np.array([0.0, 29.999998, 30.0, 59.9, 99.9, 150.0, -5.0, np.nan, np.inf], dtype=np.float32)
+    rows, n = cell_rows(cfg, y)
+    assert n == 4
+    # 29.999998f * (1/30) truncates to 0 in binary64 (fp32 would say 1); clamps; NaN/Inf -> 0
+    assert rows.tolist() == [0, 0, 1, 1, 3, 3, 0, 0, 0]
+
+
+def test_halo_depth_rules():
+    cfg, cols = scenes.scaled("config4", 2000)       # S = 2, cell 16, balls vr 16, Mouse vr 150
+    assert halo_rows(cfg, cols) == 20                # 2 * ceil(150/16) beats (2+1) * 1
+    cols["T.active"][0] = 0                          # without the Mouse
+    assert halo_rows(cfg, cols) == 3
+    cfg5, cols5 = scenes.scaled("config5", 2000)     # S = 4, cell 8, vr 4
+    cols5["T.active"][0] = 0
+    assert halo_rows(cfg5, cols5) == 5
+    b, c = scenes.boids(300, 20)                     # predators (vr 250, cell 128) are dynamic: (1+1) * 2
+    c["T.active"][0] = 0
+    assert halo_rows(b, c) == 4
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_plan_is_a_balanced_partition(world):
+    cfg, cols = scenes.scaled("config4", 40000)
+    blocks, H = plan_slabs(cfg, cols, world)
+    rows, n = cell_rows(cfg, cols["T.y"])
+    assert blocks[0][0] == 0 and blocks[-1][1] == n
+    assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(blocks, blocks[1:]))
+    counts = [int(((rows >= a) & (rows < b)).sum()) for a, b in blocks]
+    assert sum(counts) == cfg["entityCount"]
+    assert max(counts) < 1.35 * cfg["entityCount"] / world + 200    # clustered scene, whole rows
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    R = B.SLAB_RECORD_BYTES
+    cap = 64
+    mk = lambda: torch.zeros(cap * R, dtype=torch.uint8)
+    ok = True
+    for frame in range(3):
+        rng = np.random.default_rng(1000 * frame + rank)
+        n_low, n_high = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+        send_low, send_high, recv_low, recv_high = mk(), mk(), mk(), mk()
+        send_low[:n_low * R] = torch.from_numpy(rng.integers(0, 255, n_low * R, dtype=np.uint8))
+        send_high[:n_high * R] = torch.from_numpy(rng.integers(0, 255, n_high * R, dtype=np.uint8))
+        fl, fh = exchange_records(torch, rank, world, send_low, n_low, send_high, n_high, recv_low, recv_high, cap)
+        # what the neighbours must have sent (same seeded generators)
+        if rank > 0:
+            g = np.random.default_rng(1000 * frame + rank - 1)
+            a, b_ = int(g.integers(0, 40)), int(g.integers(0, 40))
+            g.integers(0, 255, a * R, dtype=np.uint8)
+            want = g.integers(0, 255, b_ * R, dtype=np.uint8)          # its HIGH buffer comes to my LOW side
+            ok &= fl == b_ and np.array_equal(recv_low[:fl * R].numpy(), want)
+        else:
+            ok &= fl == 0
+        if rank + 1 < world:
+            g = np.random.default_rng(1000 * frame + rank + 1)
+            a, b_ = int(g.integers(0, 40)), int(g.integers(0, 40))
+            want = g.integers(0, 255, a * R, dtype=np.uint8)           # its LOW buffer comes to my HIGH side
+            ok &= fh == a and np.array_equal(recv_high[:fh * R].numpy(), want)
+        else:
+            ok &= fh == 0
+    # overflow is an error, not silent truncation
+    try:
+        big = torch.zeros(cap * R, dtype=torch.uint8)
+        exchange_records(torch, rank, world, big, cap, big, cap, mk(), mk(), cap // 2)
+        raised = world == 1
+    except RuntimeError:
+        raised = True
+    open(os.path.join(out_dir, f"r{rank}"), "w").write("ok" if ok and raised else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_protocol_gloo(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"r{r}").read() for r in range(world)] == ["ok"] * world
