@@ -146,7 +146,8 @@ struct weed_ctx {
   // grid
   uint32_t *cellCount = nullptr, *cellStart = nullptr;
   uint32_t scanTiles = 0, wbTiles = 0;
-  unsigned long long *scanStatus = nullptr, *wbStatus = nullptr;
+  unsigned long long *scanStatus = nullptr;
+  uint32_t *tileCount = nullptr, *tilePrefix = nullptr;
   // by slot
   BySlot s{};
   // outputs
@@ -345,7 +346,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->cellStart, (size_t)ctx->scanTiles * SCAN_TILE);
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
-  A(ctx->wbStatus, ctx->wbTiles);
+  A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.WIN, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N);
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
@@ -518,8 +519,10 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
     if (!last) { in = out; gs = 1; }
   }
   TIME_MARK(ctx, timing, 7);
-  k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, in, gs, ctx->slotOf,
-                                                   ctx->wbTiles, ctx->wbStatus, ctx->dCtr, ctx->coll, (uint32_t)(S - 1));
+  k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->d, ctx->s, ctx->slotOf, ctx->tileCount);
+  k_pair_scan<<<1, 1024, 0, st>>>(ctx->tileCount, ctx->tilePrefix, ctx->wbTiles, g.maxPairs, ctx->dCtr, ctx->coll);
+  k_pair_emit<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, in, gs, ctx->slotOf, ctx->tilePrefix,
+                                                   ctx->dCtr, ctx->coll, (uint32_t)(S - 1));
   k_physics_end<<<1, 32, 0, st>>>(ctx->dCtr);
   TIME_MARK(ctx, timing, 8);
   CK(cudaGetLastError());
@@ -553,7 +556,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 11 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -666,7 +669,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 11 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 13 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   return WEED_OK;
 }

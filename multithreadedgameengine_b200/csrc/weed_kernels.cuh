@@ -10,8 +10,9 @@
 //   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
 //                                  warp-cooperative coalesced row flush
 //   slot order k_substep<LAST> K6  bounds + circle-circle correction, J-order
-//   id order   k_writeback     WB  gather results by id, look-back scan of pair counts,
-//                                  collisionData emission (K7)
+//   id order   k_writeback     WB  gather results by id; per-tile outgoing pair counts
+//   tiles      k_pair_scan     K7a prefix of the tile counts, pair count
+//   id order   k_pair_emit     K7b collisionData emission by the tiles below the cap
 #pragma once
 #include <cooperative_groups.h>
 
@@ -408,16 +409,18 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     const uint32_t first = n - cnt;                       // row position of my first staged entry
     for (uint32_t k = 0; k < cnt; k++) {
       const uint32_t tc = myW[k];
-      const float2 c = s.QXY[tc];
       const float4 ht = s.SA[2 * (size_t)tc + 1];
       const int4 wt = s.WIN[tc];
       const uint32_t jid = __float_as_uint(ht.w);
-      const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric,
-      // d2 > 0 holds, its scan must visit my cell.
-      const bool back = d2 < dmul((double)ht.z, (double)ht.z) &&
-                        myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric and
+      // d2 > 0 holds; with equal visual ranges d2 < vr_t^2 is the predicate that just passed.
+      bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+      if (back && ht.z != vr) {
+        const float2 c = s.QXY[tc];
+        const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+        back = d2 < dmul((double)ht.z, (double)ht.z);
+      }
       const bool out = jid > id;
       myW[k] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
       myId[k] = jid;
@@ -628,7 +631,7 @@ static constexpr int K6_THREADS = 256;
 static constexpr int K6_STAGE = 8;      // staged possible overlaps per thread
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(K6_THREADS)
+__global__ void __launch_bounds__(K6_THREADS, 6)
 k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin, uint32_t gs,
           float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
           uint32_t substep) {
@@ -699,32 +702,82 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
 }
 
 // ---- WB + K7: results back to id order, collisionData -------------------------------------
-// Gathers each entity's result sector by id, writes the by-id state coalesced, scans the
-// per-entity outgoing pair counts in id order (decoupled look-back) and lets the entities
-// whose pairs fall below maxCollisionPairs re-derive them in row order — which is the
-// reference's emission order (i ascending, then row position; physics_worker.js:555-567).
+// k_writeback gathers each entity's result sector by id, writes the by-id state coalesced
+// and leaves the per-tile count of outgoing colliding pairs; k_pair_scan turns the tile counts
+// into exclusive prefixes (id order) and the pair count; k_pair_emit lets only the tiles whose
+// prefix is below maxCollisionPairs re-derive their pairs in row order — the reference's
+// emission order (i ascending, then row position; physics_worker.js:555-567).
+__device__ __forceinline__ uint32_t wb_out_count(const BySlot& s, const uint32_t* __restrict__ slotOf, uint32_t i,
+                                                 uint32_t N, uint32_t& slot) {
+  slot = SLOT_NONE;
+  if (i >= N) return 0;
+  slot = slotOf[i];
+  if (slot == SLOT_NONE) return 0;
+  const uint32_t meta = __float_as_uint(reinterpret_cast<const float4*>(s.OUT + slot)[1].x);
+  return (meta >> 31) ? ((meta >> 8) & 0x7FFFFFu) : 0u;   // pairs are logged by the slab that owns the lower id
+}
+
 __global__ void __launch_bounds__(WB_THREADS)
-k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const float4* __restrict__ Glast,
-            uint32_t gs, const uint32_t* __restrict__ slotOf, uint32_t numTiles, unsigned long long* status,
-            Counters* ctr, int32_t* __restrict__ coll, uint32_t lastSubstep) {
-  __shared__ uint32_t s_tile, s_excl, s_warp[WB_THREADS / 32];
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->wbTile, 1u);
-  __syncthreads();
-  const uint32_t tileIdx = s_tile;
-  const uint32_t i = tileIdx * WB_THREADS + threadIdx.x;
-  uint32_t slot = SLOT_NONE, outCnt = 0;
+k_writeback(GridDims g, ById d, BySlot s, const uint32_t* __restrict__ slotOf, uint32_t* __restrict__ tileCount) {
+  __shared__ uint32_t s_warp[WB_THREADS / 32];
+  const uint32_t i = blockIdx.x * WB_THREADS + threadIdx.x;
+  uint32_t outCnt = 0;
   if (i < g.N) {
-    slot = slotOf[i];
+    const uint32_t slot = slotOf[i];
     if (slot != SLOT_NONE) {
       const float4* o = reinterpret_cast<const float4*>(s.OUT + slot);
       const float4 o0 = o[0];
       const uint32_t meta = __float_as_uint(o[1].x);
       d.DP[i] = o0;
       d.CC[i] = (uint8_t)(meta & 0xFFu);
-      outCnt = (meta >> 8) & 0x7FFFFFu;
-      if (!(meta >> 31)) outCnt = 0;               // pairs are logged by the slab that owns the lower id
+      if (meta >> 31) outCnt = (meta >> 8) & 0x7FFFFFu;
     }
   }
+  for (int o = 16; o; o >>= 1) outCnt += __shfl_xor_sync(0xffffffffu, outCnt, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = outCnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < WB_THREADS / 32; w++) t += s_warp[w];
+    tileCount[blockIdx.x] = t;
+  }
+}
+
+// one block: exclusive prefix of the tile counts (a few 10^4 values)
+__global__ void __launch_bounds__(1024)
+k_pair_scan(const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tilePrefix, uint32_t numTiles,
+            uint32_t maxPairs, Counters* ctr, int32_t* __restrict__ coll) {
+  __shared__ uint32_t s_part[1024];
+  const uint32_t per = (numTiles + 1023) / 1024;
+  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, numTiles);
+  uint32_t sum = 0;
+  for (uint32_t t = lo; t < hi; t++) sum += tileCount[t];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan
+    const uint32_t v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_part[threadIdx.x] - sum;
+  for (uint32_t t = lo; t < hi; t++) { tilePrefix[t] = run; run += tileCount[t]; }
+  if (threadIdx.x == 1023) {
+    ctr->collisionPairs = s_part[1023];
+    if (coll) coll[0] = (int32_t)min(s_part[1023], maxPairs);      // :565-567
+  }
+}
+
+__global__ void __launch_bounds__(WB_THREADS)
+k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const float4* __restrict__ Glast,
+            uint32_t gs, const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ tilePrefix,
+            const Counters* __restrict__ ctr, int32_t* __restrict__ coll, uint32_t lastSubstep) {
+  __shared__ uint32_t s_warp[WB_THREADS / 32];
+  const uint32_t tileBase = tilePrefix[blockIdx.x];
+  if (tileBase >= g.maxPairs) return;                              // whole tile past the cap
+  const uint32_t i = blockIdx.x * WB_THREADS + threadIdx.x;
+  uint32_t slot;
+  const uint32_t outCnt = wb_out_count(s, slotOf, i, g.N, slot);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = outCnt;
   for (int o = 1; o < 32; o <<= 1) {
@@ -733,28 +786,9 @@ k_writeback(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  if (warp == 0) {
-    const uint32_t w = lane < WB_THREADS / 32 ? s_warp[lane] : 0;
-    uint32_t winc = w;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= (uint32_t)o) winc += v;
-    }
-    if (lane < WB_THREADS / 32) s_warp[lane] = winc - w;
-    const uint32_t agg = __shfl_sync(0xffffffffu, winc, 31);
-    const uint32_t excl = lb_exclusive(status, tileIdx, agg, ctr->epoch);
-    if (lane == 0) {
-      s_excl = excl;
-      if (tileIdx == numTiles - 1) {
-        ctr->wbTile = 0;
-        ctr->collisionPairs = excl + agg;
-        if (coll) coll[0] = (int32_t)min(excl + agg, g.maxPairs);   // :565-567
-      }
-    }
-  }
-  __syncthreads();
-  uint32_t base = s_excl + s_warp[warp] + (inc - outCnt);
-  if (coll == nullptr || outCnt == 0 || base >= g.maxPairs) return;
+  uint32_t base = tileBase + (inc - outCnt);
+  for (uint32_t w = 0; w < warp; w++) base += s_warp[w];
+  if (outCnt == 0 || base >= g.maxPairs) return;
   // re-derive my colliding outgoing pairs on the last sweep's start positions
   const Params p = *pp;
   const float4 gme = Glast[(size_t)slot * gs];
