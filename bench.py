@@ -51,6 +51,8 @@ def workload(name, n_override=None):
         if n == full[name]:
             return getattr(scenes, name)()
         return scenes.scaled(name, n)
+    if name == "config4_reflect":      # diagnostic: same scene, clusters reflected at the walls instead of clipped
+        return scenes.config4(cluster_edge="reflect")
     if name == "config1":
         return scenes.balls_readme()
     if name == "config1b":

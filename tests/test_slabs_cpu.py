@@ -39,13 +39,26 @@ def test_halo_depth_rules():
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_plan_is_a_balanced_partition(world):
     cfg, cols = scenes.scaled("config4", 40000)
-    blocks, H = plan_slabs(cfg, cols, world)
+    blocks, H = plan_slabs(cfg, cols, world, balance="count")
     rows, n = cell_rows(cfg, cols["T.y"])
     assert blocks[0][0] == 0 and blocks[-1][1] == n
     assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(blocks, blocks[1:]))
     counts = [int(((rows >= a) & (rows < b)).sum()) for a, b in blocks]
     assert sum(counts) == cfg["entityCount"]
     assert max(counts) < 1.35 * cfg["entityCount"] / world + 200    # clustered scene, whole rows
+
+
+def test_cost_balanced_plan_equalises_estimated_work():
+    from multithreadedgameengine_b200.slabs import row_costs
+    cfg, cols = scenes.scaled("config4", 60000)
+    cost, count = row_costs(cfg, cols)
+    assert int(count.sum()) == cfg["entityCount"]
+    blocks, _ = plan_slabs(cfg, cols, 4)
+    per = [cost[a:b].sum() for a, b in blocks]
+    assert max(per) < 1.25 * sum(per) / 4
+    by_count, _ = plan_slabs(cfg, cols, 4, balance="count")
+    per_c = [cost[a:b].sum() for a, b in by_count]
+    assert max(per) <= max(per_c) + 1e-6      # never worse than count balancing on its own objective
 
 
 def _free_port():
