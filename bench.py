@@ -196,7 +196,7 @@ def run_ours(args):
         dist.barrier()
     from multithreadedgameengine_b200 import binding as B
     from multithreadedgameengine_b200.engine import GameEngine
-    from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs
+    from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs, replan_from_times
 
     name = args.workload
     cfg, cols = workload(name, args.entities)      # every rank builds the same seeded scene
@@ -205,6 +205,32 @@ def run_ours(args):
     active = int(cols["T.active"].sum())
     plan = plan_slabs(cfg, cols, world) if world > 1 else None
     stream = torch.cuda.Stream()
+    balance_note = "cost model of the start scene"
+    if world > 1 and args.autobalance:
+        # measured-feedback balancing (outside the timed region, like an autotuning pass): run a
+        # few frames from the start scene, gather every slab's kernel time, move the cuts, restart
+        for it in range(args.autobalance):
+            with torch.cuda.stream(stream):
+                sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan)
+                for _ in range(2):
+                    sl.step_dist()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                tsum = 0.0
+                for _ in range(4):
+                    torch.cuda.synchronize()
+                    a0.record(stream)
+                    sl.run()
+                    a1.record(stream)
+                    torch.cuda.synchronize()
+                    tsum += a0.elapsed_time(a1)
+                    sl.exchange_dist()
+                sl.close()
+            tt = torch.tensor([tsum / 4], device="cuda", dtype=torch.float64)
+            allt = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allt, tt)
+            times = [float(t.item()) for t in allt]
+            plan = (replan_from_times(plan[0], times), plan[1])
+        balance_note = f"cost model + {args.autobalance} measured-feedback re-plans before the timed run"
 
     def make(flags=0):
         if world == 1:
@@ -331,7 +357,8 @@ def run_ours(args):
                      "kernel_ms_rank0": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
                      "collision_pairs_last_substep": st["collisionPairs"],
-                     "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes})
+                     "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes,
+                     "slab_balance": balance_note if world > 1 else None})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
@@ -353,6 +380,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="entities of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--autobalance", type=int, default=2, help="measured-feedback slab re-plans before timing (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,25 @@ def plan_slabs(cfg, cols, world, balance="cost"):
     return [(cuts[k], cuts[k + 1]) for k in range(world)], halo_rows(cfg, cols)
 
 
+def replan_from_times(blocks, times_ms):
+    """Measured-feedback balancing: given the frame time of every slab under the current cuts,
+    spread each slab's time uniformly over its rows and cut the cumulative curve into equal
+    parts.  Returns the new (rowBegin, rowEnd) list (same halo)."""
+    rows = blocks[-1][1]
+    world = len(blocks)
+    per_row = np.zeros(rows, dtype=np.float64)
+    for (a, b), t in zip(blocks, times_ms):
+        per_row[a:b] = float(t) / max(1, b - a)
+    cum = np.cumsum(per_row)
+    total = float(cum[-1])
+    cuts = [0]
+    for k in range(1, world):
+        r = int(np.searchsorted(cum, total * k / world)) + 1
+        cuts.append(min(max(r, cuts[-1] + 1), rows - (world - k)))
+    cuts.append(rows)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
 def exchange_records(torch, rank, world, send_low, n_low, send_high, n_high, recv_low, recv_high, capacity):
     """Neighbour exchange of one frame: first the two record counts, then exactly that many
     64-byte records, with the adjacent ranks only (rank-1 = low, rank+1 = high).  Works on any

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from multithreadedgameengine_b200 import binding as B, scenes
-from multithreadedgameengine_b200.slabs import cell_rows, exchange_records, halo_rows, plan_slabs
+from multithreadedgameengine_b200.slabs import cell_rows, exchange_records, halo_rows, plan_slabs, replan_from_times
 
 
 def test_cell_rows_follow_the_reference_key():
@@ -59,6 +59,16 @@ def test_cost_balanced_plan_equalises_estimated_work():
     by_count, _ = plan_slabs(cfg, cols, 4, balance="count")
     per_c = [cost[a:b].sum() for a, b in by_count]
     assert max(per) <= max(per_c) + 1e-6      # never worse than count balancing on its own objective
+
+
+def test_replan_from_times_moves_cuts_toward_the_slow_slab():
+    blocks = [(0, 100), (100, 200), (200, 300), (300, 400)]
+    new = replan_from_times(blocks, [1.0, 1.0, 1.0, 3.0])       # the last slab is 3x slower per row
+    assert new[0][0] == 0 and new[-1][1] == 400 and all(a[1] == b[0] for a, b in zip(new, new[1:]))
+    assert new[-1][1] - new[-1][0] < 100 and new[0][1] - new[0][0] > 100
+    # equal times are a fixed point (up to one row of rounding)
+    same = replan_from_times(blocks, [2.0] * 4)
+    assert all(abs(a[0] - b[0]) <= 1 and abs(a[1] - b[1]) <= 1 for a, b in zip(same, blocks))
 
 
 def _free_port():
