@@ -37,10 +37,12 @@ UNIT = "entity-substeps/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/), config4 16M on one B200; None = not captured for this kernel.
-TRAFFIC_FROM_NCU = {}
+TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r1_ncu_config4_16M_final_summary.md
+    "k_neighbors": 7.388e9, "k_substep": 3.605e9, "k_build_slots": 3.383e9, "k_writeback": 1.952e9,
+}
 
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
-                "k_capped_rescan+k_sort_lists", "k_substep(xS)", "k_writeback"]
+                "k_capped_rescan+k_sort_lists", "k_substep", "k_writeback+k_pair_scan+k_pair_emit"]
 
 
 def workload(name, n_override=None):
@@ -60,6 +62,18 @@ def workload(name, n_override=None):
     if name == "config2":
         return scenes.boids()
     raise SystemExit(f"unknown workload {name}")
+
+
+def full_config(name, n_override=None):
+    """The config block of the FULL workload (what the GPU arm runs), without building the scene."""
+    from multithreadedgameengine_b200 import scenes
+    if name not in scenes._FULL:
+        return None
+    n, (W, H), cs, M, S, _, _, _ = scenes._FULL[name]
+    if n_override and n_override != n:
+        return None
+    return dict(entityCount=n + 1, worldWidth=W, worldHeight=H, spatial=dict(cellSize=cs, maxNeighbors=M),
+                physics=dict(subStepCount=S))
 
 
 def describe(name, cfg):
@@ -167,7 +181,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": describe(args.workload, cfg),
+            "config": describe(args.workload, full_config(args.workload, args.entities) or cfg),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -296,6 +310,7 @@ def run_ours(args):
             frames(obj_t, 1)
             acc += np.array(eng_t.stats()["ms"][:8])
         kms = acc / args.steps
+        kms[6] /= S                    # per LAUNCH of k_substep (the frame runs it S times)
         st_t = eng_t.stats()
         local_active = st_t["activeInGrid"]
         kbar_t = st_t["neighborsTotal"] / max(1, local_active)
@@ -303,7 +318,7 @@ def run_ours(args):
         top = int(np.argmax(kms))
         F, per_kernel = algorithmic_bytes(kbar_t, S)
         alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
-               6: S * (34.0 + 4.0 * (1.0 + kbar_t)), 7: 0.0}[top]
+               6: 34.0 + 4.0 * (1.0 + kbar_t), 7: 0.0}[top]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -313,7 +328,8 @@ def run_ours(args):
         achieved = alg * local_active / (kms[top] * 1e-3) / 1e9     # this rank's kernel over the entities it processes
         frame_gbps = F * owned_total * args.steps / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": TRAFFIC_FROM_NCU.get(KERNEL_NAMES[top]),
+                    "frac": achieved / peak,
+                    "traffic": TRAFFIC_FROM_NCU.get(KERNEL_NAMES[top]) if (world == 1 and name == "config4" and not args.entities) else None,
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                     "algorithmic_bytes_per_entity": alg, "kernel_ms": float(kms[top]), "entities_per_launch": int(local_active),
                     "whole_frame": {"bytes_per_entity_frame": F, "achieved_GBps_all_gpus": frame_gbps,
@@ -354,7 +370,7 @@ def run_ours(args):
                      f"{world} row slabs (1 per GPU), halo {plan[1]} rows recomputed redundantly, 1 NCCL neighbour exchange per frame",
                      "kbar": kbar, "active": active, "l2_policy": "working set >> 126 MB L2 (inputs larger than L2)"
                      if N / world > 2_000_000 else "per-GPU working set comparable to L2; frames run back-to-back on evolving state",
-                     "kernel_ms_rank0": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
+                     "kernel_ms_rank0_per_launch": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
                      "collision_pairs_last_substep": st["collisionPairs"],
                      "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes,
