@@ -348,7 +348,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.WIN, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
   ctx->rowWords = N * (1 + (size_t)g.M);
@@ -493,7 +493,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   else
     k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   TIME_MARK(ctx, timing, 5);
-  k_capped_rescan<<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  k_capped_rescan<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());

@@ -87,6 +87,7 @@ __global__ void k_spatial_begin(Counters* ctr) {
   if (threadIdx.x == 0) {
     ctr->epoch++;
     ctr->anyCapped = 0;
+    ctr->nCapped = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
   }
@@ -207,6 +208,7 @@ struct BySlot {
   uint32_t* XNEXT;   // next link, indexed by the OWNER's row position (k * Npad + slot)
   OutRec* OUT;       // last-substep result
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
+  uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
 };
 
 template <bool INTEGRATE>
@@ -457,6 +459,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   if (n >= M && M > 0) {
     reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
     ctr->anyCapped = 1;
+    s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
   }
   s.NCNT[e] = n;
 }
@@ -474,41 +477,72 @@ __device__ __forceinline__ int row_find(const GridDims& g, const BySlot& s, uint
 }
 
 // ---- K4b: capped rows (rare) -----------------------------------------------------------------
-// A capped row may have lost lower-id partners that do list this entity.  Rescan the window
-// past the cap, in DESCENDING slot order, and push every lower-id partner whose own row
-// contains me onto my explicit list (LIFO push => the list comes out ascending).
-__global__ void __launch_bounds__(128)
+// A capped row may have lost lower-id partners that do list this entity.  One WARP per capped
+// entity rescans its window past the cap in DESCENDING slot order (lane 0 = highest slot) and
+// links every lower-id partner whose own row contains the entity in front of its explicit
+// list, so the list comes out ascending.  Only this warp touches this entity's list during
+// the kernel (other pushes happened in K4), so the links are plain stores.
+static constexpr int K4B_BLOCKS = 148 * 4;
+__global__ void __launch_bounds__(256)
 k_capped_rescan(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
-  if (!ctr->anyCapped) return;
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cellStart[g.cells]) return;
-  if (!(__float_as_uint(s.SA[2 * (size_t)e].w) & F_CAPPED)) return;
-  const uint32_t cnt = s.NCNT[e];
-  if (cnt == 0) return;
-  const uint32_t lastSlot = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
-  const float2 q = s.QXY[e];
-  const float4 hi = s.SA[2 * (size_t)e + 1];
-  const float vr = hi.z;
-  const uint32_t id = __float_as_uint(hi.w);
-  const double vrSq = dmul((double)vr, (double)vr);
-  int32_t myCol, myRow;
-  cell_of(g, q.x, q.y, myCol, myRow);
-  const int4 win = s.WIN[e];
-  for (int32_t row = win.y; row >= win.x; row--) {
-    const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
-    const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-    for (uint32_t t = b; t-- > a;) {
-      if (t <= lastSlot) return;                       // everything from here on is in my row
-      const float4 ht = s.SA[2 * (size_t)t + 1];
-      if (__float_as_uint(ht.w) > id) continue;        // my own pair, lost to the cap: not in P
-      const float2 c = s.QXY[t];
-      const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
-      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-      if (!(d2 < vrSq && d2 > 0)) continue;            // I do not see it: it pushed the pair itself
-      const int4 wt = s.WIN[t];
-      if (!(d2 < dmul((double)ht.z, (double)ht.z) && myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w)) continue;
-      const int pos = row_find(g, s, t, e);
-      if (pos >= 0) explicit_push(s, ctr, e, (uint32_t)pos * g.Npad + t);
+  const uint32_t nCapped = ctr->nCapped;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nCapped; w += warpsTotal) {
+    const uint32_t e = s.CAPLIST[w];
+    const uint32_t cnt = s.NCNT[e];
+    if (cnt == 0) continue;
+    const uint32_t lastSlot = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
+    const float2 q = s.QXY[e];
+    const float4 hi = s.SA[2 * (size_t)e + 1];
+    const float vr = hi.z;
+    const uint32_t id = __float_as_uint(hi.w);
+    const double vrSq = dmul((double)vr, (double)vr);
+    int32_t myCol, myRow;
+    cell_of(g, q.x, q.y, myCol, myRow);
+    const int4 win = s.WIN[e];
+    uint32_t head = s.XHEAD[e];
+    const bool wasEmpty = head == 0;
+    bool finished = false;
+    for (int32_t row = win.y; row >= win.x && !finished; row--) {
+      const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
+      const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+      for (uint32_t top = b; top > a && !finished; top = top > 32 ? top - 32 : 0) {
+        const bool inRange = top > lane && top - 1 - lane >= a;
+        const uint32_t t = inRange ? top - 1 - lane : 0;
+        const bool beyond = inRange && t > lastSlot;          // everything <= lastSlot is in my row
+        if (__ballot_sync(0xffffffffu, inRange && !beyond)) finished = true;
+        int pos = -1;
+        if (beyond) {
+          const float4 ht = s.SA[2 * (size_t)t + 1];
+          if (__float_as_uint(ht.w) < id) {                   // higher ids: my own pair, lost to the cap
+            const float2 c = s.QXY[t];
+            const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
+            const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+            if (d2 < vrSq && d2 > 0) {                        // else it does not see... I do not see it: it pushed the pair itself
+              const int4 wt = s.WIN[t];
+              if (d2 < dmul((double)ht.z, (double)ht.z) && myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w)
+                pos = row_find(g, s, t, e);
+            }
+          }
+        }
+        const uint32_t hits = __ballot_sync(0xffffffffu, pos >= 0);
+        if (hits) {
+          const uint32_t node = pos >= 0 ? (uint32_t)pos * g.Npad + t : 0;   // the partner's row position of me
+          // lane order = descending slot: the first hit links to the old head, each next one to
+          // the previous hit, the last one becomes the new head
+          const uint32_t before = hits & ((1u << lane) - 1);
+          const int prevLane = before ? 31 - __clz(before) : -1;
+          const uint32_t prevNode = __shfl_sync(0xffffffffu, node, prevLane < 0 ? 0 : prevLane);
+          if (pos >= 0) s.XNEXT[node] = prevLane < 0 ? head : prevNode + 1u;
+          head = __shfl_sync(0xffffffffu, node, 31 - __clz(hits)) + 1u;
+          if (lane == 0) atomicAdd(&ctr->explicitPairs, (uint32_t)__popc(hits));
+        }
+      }
+    }
+    if (lane == 0) {
+      s.XHEAD[e] = head;
+      if (wasEmpty && head != 0) reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_XSORTED;
     }
   }
 }
@@ -521,6 +555,7 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
   if (e >= cellStart[g.cells]) return;
   uint32_t p = s.XHEAD[e];
   if (p == 0 || s.XNEXT[p - 1] == 0) return;
+  if (__float_as_uint(s.SA[2 * (size_t)e].w) & F_XSORTED) return;   // built in order by K4b
   uint32_t head = 0, tail = 0, tailKey = 0;
   while (p != 0) {
     const uint32_t nxt = s.XNEXT[p - 1];

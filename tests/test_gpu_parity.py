@@ -368,3 +368,37 @@ def test_full_size_spatial_is_idempotent_and_step_keeps_invariants(big):
     assert (c["RB.ax"] == 0).all() and (c["RB.ay"] == 0).all()     # :313-314
     assert (c["RB.speed"] >= 0).all()
     assert not np.array_equal(before["T.y"], c["T.y"])
+
+
+def test_config2_boids_with_host_tick_consumer():
+    """BASELINE config 2 as the reference runs it: neighbor rows are fetched to the host,
+    tick() (examples/boids_tick.py, a restatement of demos/predators/boid.js) writes ax/ay,
+    the next frame uploads exactly those two columns."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    from boids_tick import tick_all
+
+    cfg, cols = scenes.boids(n_prey=1200, n_pred=60, seed=21)
+    cfg["worldWidth"], cfg["worldHeight"] = 1400.0, 700.0
+    for k, f in (("T.x", 1400 / 5000), ("RB.px", 1400 / 5000), ("T.y", 700 / 2000), ("RB.py", 700 / 2000)):
+        cols[k] = (cols[k] * np.float32(f)).astype(np.float32)
+    cfg["spatial"]["maxNeighbors"] = 200
+    N, M = cfg["entityCount"], 200
+    etype = np.zeros(N, dtype=np.uint8)
+    etype[1:1201] = 1
+    etype[1201:] = 2
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    eng.Transform.entityType[:] = etype
+    up = eng.mask("RB.ax", "RB.ay")
+    for frame in range(5):
+        eng.step(1.0, up if frame else 0, B.COLS_OUTPUT_ALL | B.COL_NEIGHBORS | B.COL_COLLISIONS)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"frame {frame}")
+        compare_rows(eng, ora, cfg)
+        tick_all(eng.col, etype, eng.neighborData, eng.distanceData, M, cfg["worldWidth"], cfg["worldHeight"])
+        tick_all(ora.col, etype, ora.neighborData, ora.distanceData, M, cfg["worldWidth"], cfg["worldHeight"])
+        assert np.array_equal(bits(eng.col["RB.ax"]), bits(ora.col["RB.ax"]))
+        assert np.abs(eng.col["RB.ax"]).max() > 0
+    eng.close()
