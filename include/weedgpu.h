@@ -76,11 +76,12 @@ enum {
   WEED_COL_C_RADIUS    = 1u << 16,
   WEED_COL_C_ISTRIGGER = 1u << 17,
   WEED_COL_C_VISRANGE  = 1u << 18,  /* Collider.visualRange    f32 */
+  WEED_COL_T_ENTITYTYPE = 1u << 19, /* Transform.entityType    u8 (read by device-side systems only) */
   /* pseudo-columns: whole output buffers (download only) */
   WEED_COL_NEIGHBORS   = 1u << 24,  /* all of neighborData + distanceData (large!)      */
   WEED_COL_COLLISIONS  = 1u << 25   /* collisionData                                    */
 };
-#define WEED_COLS_INPUT_ALL  0x0007FFFFu  /* every mirrored component column             */
+#define WEED_COLS_INPUT_ALL  0x000FFFFFu  /* every mirrored component column             */
 /* what the reference's two workers write every frame (physics_worker.js:301-314,596-601,
  * 176,551) */
 #define WEED_COLS_OUTPUT_ALL (WEED_COL_T_X | WEED_COL_T_Y | WEED_COL_RB_VX | WEED_COL_RB_VY | \
@@ -215,6 +216,28 @@ typedef enum weed_devptr_id {
   WEED_DEV_VEL       = 5   /* float4 [N] {vx, vy, speed, -}                             */
 } weed_devptr_id;
 int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
+
+/* ---- device-side consumers of the neighbor rows ("systems") ----------------
+ * The fixed-stride rows exist to feed GameObject.tick(); at >= 1M entities copying them to
+ * the host dominates a frame.  A system is a tick() restated as a kernel that reads the rows
+ * where they are and writes RigidBody.ax/ay, exactly like the logic worker would.
+ * weed_system_boids restates the boids demo: demos/predators/boid.js:115-124 (tick),
+ * :137-240 (applyFlockingBehaviors) and :318-341 (keepWithinBounds); avoidMouse and the
+ * Prey/Predator processNeighbor hooks are not included.  Call it between frames, where the
+ * logic workers run.                                                                      */
+typedef struct weed_boids_params {
+  double centeringFactor;   /* boid.js:65  0.001 */
+  double avoidFactor;       /* boid.js:66  0.3   */
+  double matchingFactor;    /* boid.js:67  0.1   */
+  double turnFactor;        /* boid.js:68  0.01  */
+  double margin;            /* boid.js:69  20    */
+  uint32_t mouseEntityType; /* Mouse.entityType (0): such neighbors are skipped, boid.js:179 */
+  uint32_t _pad;
+} weed_boids_params;
+/* protectedRange: per-entity float[entityCount] host array (Flocking.protectedRange), or
+ * NULL for 2 * Collider.radius (boid.js:64).                                              */
+int weed_system_boids(weed_ctx* ctx, const weed_boids_params* params, const float* protectedRange,
+                      double dtRatio);
 
 /* ---- multi-GPU slabs (SURVEY §8 e) ----------------------------------------
  * A slab context (slabRowEnd > 0) holds a LOCAL entity table of `entityCount` slots; every

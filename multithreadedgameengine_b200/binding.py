@@ -26,8 +26,9 @@ COL = {
     "RB.ay": 1 << 8, "RB.px": 1 << 9, "RB.py": 1 << 10, "RB.maxVel": 1 << 11,
     "RB.velocityAngle": 1 << 12, "RB.speed": 1 << 13, "RB.collisionCount": 1 << 14,
     "C.active": 1 << 15, "C.radius": 1 << 16, "C.isTrigger": 1 << 17, "C.visualRange": 1 << 18,
+    "T.entityType": 1 << 19,
 }
-COLS_INPUT_ALL = 0x0007FFFF
+COLS_INPUT_ALL = 0x000FFFFF
 COLS_OUTPUT_ALL = (COL["T.x"] | COL["T.y"] | COL["RB.vx"] | COL["RB.vy"] | COL["RB.ax"] | COL["RB.ay"]
                    | COL["RB.px"] | COL["RB.py"] | COL["RB.velocityAngle"] | COL["RB.speed"]
                    | COL["RB.collisionCount"])
@@ -56,6 +57,11 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p),
                 ("slabRowBegin", C.c_uint32), ("slabRowEnd", C.c_uint32),
                 ("slabHaloRows", C.c_uint32), ("_pad1", C.c_uint32)]
+
+
+class BoidsParams(C.Structure):
+    _fields_ = [("centeringFactor", C.c_double), ("avoidFactor", C.c_double), ("matchingFactor", C.c_double),
+                ("turnFactor", C.c_double), ("margin", C.c_double), ("mouseEntityType", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -89,6 +95,7 @@ SYMBOLS = {
     "weed_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "weed_last_error": (C.c_char_p, [C.c_void_p]),
     "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "weed_system_boids": (C.c_int, [C.c_void_p, C.POINTER(BoidsParams), C.c_void_p, C.c_double]),
     "weed_slab_set_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),

@@ -124,5 +124,5 @@ COLUMN_KEYS = {
     "RB.maxVel": (1, "maxVel"), "RB.velocityAngle": (1, "velocityAngle"), "RB.speed": (1, "speed"),
     "RB.collisionCount": (1, "collisionCount"),
     "C.active": (2, "active"), "C.radius": (2, "radius"), "C.isTrigger": (2, "isTrigger"),
-    "C.visualRange": (2, "visualRange"),
+    "C.visualRange": (2, "visualRange"), "T.entityType": (0, "entityType"),
 }

@@ -46,14 +46,14 @@ const ColDef* schema(int id, uint32_t* n) {
 
 // the 19 mirrored columns, in WEED_COL_* bit order: (buffer, schema index, element bytes)
 struct HotCol { int buf; uint32_t col; uint32_t bytes; };
-const HotCol kHot[19] = {
+const HotCol kHot[20] = {
     {WEED_BUF_TRANSFORM, 0, 1},  {WEED_BUF_TRANSFORM, 2, 4},  {WEED_BUF_TRANSFORM, 3, 4},
     {WEED_BUF_RIGIDBODY, 0, 1},  {WEED_BUF_RIGIDBODY, 1, 1},  {WEED_BUF_RIGIDBODY, 2, 4},
     {WEED_BUF_RIGIDBODY, 3, 4},  {WEED_BUF_RIGIDBODY, 4, 4},  {WEED_BUF_RIGIDBODY, 5, 4},
     {WEED_BUF_RIGIDBODY, 6, 4},  {WEED_BUF_RIGIDBODY, 7, 4},  {WEED_BUF_RIGIDBODY, 16, 4},
     {WEED_BUF_RIGIDBODY, 20, 4}, {WEED_BUF_RIGIDBODY, 21, 4}, {WEED_BUF_RIGIDBODY, 22, 1},
     {WEED_BUF_COLLIDER, 0, 1},   {WEED_BUF_COLLIDER, 4, 4},   {WEED_BUF_COLLIDER, 7, 1},
-    {WEED_BUF_COLLIDER, 15, 4}};
+    {WEED_BUF_COLLIDER, 15, 4},  {WEED_BUF_TRANSFORM, 1, 1}};
 
 thread_local std::string g_create_error;
 }  // namespace
@@ -160,7 +160,8 @@ struct weed_ctx {
   double lastDt = -1;
   bool paramsDirty = true;
   // staging for host<->device columns
-  void* stage[19] = {};
+  void* stage[20] = {};
+  float* protRange = nullptr;
   // graph of one full frame
   cudaGraphExec_t frameGraph = nullptr;
   int graphSubSteps = -1;
@@ -339,7 +340,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   const size_t N = g.N;
   int rc;
 #define A(ptr, count) if ((rc = dalloc(ctx, &(ptr), (count))) != WEED_OK) return bail(rc)
-  A(ctx->d.DP, N); A(ctx->d.ACC, N); A(ctx->d.AT, N); A(ctx->d.V, N); A(ctx->d.F, N); A(ctx->d.CC, N);
+  A(ctx->d.DP, N); A(ctx->d.ACC, N); A(ctx->d.AT, N); A(ctx->d.V, N); A(ctx->d.F, N); A(ctx->d.CC, N); A(ctx->d.ET, N);
   A(ctx->key, N); A(ctx->rank, N); A(ctx->arrIds, N); A(ctx->slotOf, N);
   ctx->scanTiles = (uint32_t)(((size_t)g.cells + 1 + SCAN_TILE - 1) / SCAN_TILE);
   A(ctx->cellCount, (size_t)ctx->scanTiles * SCAN_TILE);
@@ -356,7 +357,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
   A(ctx->dParams, 1); A(ctx->dCtr, 1);
   if (ctx->slab) { A(ctx->d.GID, N); A(ctx->s.SLID, N); A(ctx->holes, N); A(ctx->dSlab, 1); }
-  for (int c = 0; c < 19; c++) {
+  for (int c = 0; c < 20; c++) {
     uint8_t* p = nullptr;
     if ((rc = dalloc(ctx, &p, N * kHot[c].bytes)) != WEED_OK) return bail(rc);
     ctx->stage[c] = p;
@@ -391,7 +392,7 @@ static void* host_col(weed_ctx* ctx, int c) {
 }
 
 static int check_bound(weed_ctx* ctx, uint32_t mask) {
-  for (int c = 0; c < 19; c++)
+  for (int c = 0; c < 20; c++)
     if ((mask >> c) & 1u)
       if (!ctx->host[kHot[c].buf]) return fail(ctx, WEED_E_NOT_BOUND, "component buffer " + std::to_string(kHot[c].buf) + " not bound");
   return WEED_OK;
@@ -403,12 +404,12 @@ static int upload_async(weed_ctx* ctx, uint32_t mask) {
   int rc = check_bound(ctx, mask);
   if (rc) return rc;
   const size_t N = ctx->g.N;
-  for (int c = 0; c < 19; c++)
+  for (int c = 0; c < 20; c++)
     if ((mask >> c) & 1u)
       CK(cudaMemcpyAsync(ctx->stage[c], host_col(ctx, c), N * kHot[c].bytes, cudaMemcpyHostToDevice, ctx->stream));
   Staging st;
   const void** sp = reinterpret_cast<const void**>(&st);
-  for (int c = 0; c < 19; c++) sp[c] = ctx->stage[c];
+  for (int c = 0; c < 20; c++) sp[c] = ctx->stage[c];
   k_pack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, mask, st, ctx->d);
   CK(cudaGetLastError());
   ctx->spatialValid = false;
@@ -423,10 +424,10 @@ static int download_async(weed_ctx* ctx, uint32_t mask) {
     if (rc) return rc;
     StagingOut st;
     void** sp = reinterpret_cast<void**>(&st);
-    for (int c = 0; c < 19; c++) sp[c] = ctx->stage[c];
+    for (int c = 0; c < 20; c++) sp[c] = ctx->stage[c];
     k_unpack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, cols, st, ctx->d);
     CK(cudaGetLastError());
-    for (int c = 0; c < 19; c++)
+    for (int c = 0; c < 20; c++)
       if ((cols >> c) & 1u)
         CK(cudaMemcpyAsync(host_col(ctx, c), ctx->stage[c], N * kHot[c].bytes, cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -758,5 +759,28 @@ extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, uint32_t
   ctx->slabTop = (uint32_t)nt;
   ctx->spatialValid = false;
   if (new_top) *new_top = ctx->slabTop;
+  return WEED_OK;
+}
+
+// =============================================================================================
+// device-side systems
+// =============================================================================================
+extern "C" int weed_system_boids(weed_ctx* ctx, const weed_boids_params* p, const float* protectedRange, double dtRatio) {
+  GUARD(ctx);
+  if (!p) return WEED_E_INVALID;
+  if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "systems are not available on slab contexts yet");
+  const size_t N = ctx->g.N;
+  if (protectedRange) {
+    if (!ctx->protRange) { int rc = dalloc(ctx, &ctx->protRange, N); if (rc) return rc; }
+    CK(cudaMemcpyAsync(ctx->protRange, protectedRange, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  BoidsParams bp;
+  bp.centering = p->centeringFactor; bp.avoid = p->avoidFactor; bp.matching = p->matchingFactor;
+  bp.turn = p->turnFactor; bp.margin = p->margin; bp.dtRatio = dtRatio; bp.mouseType = p->mouseEntityType;
+  k_system_boids<<<blocks_for(N, 128), 128, 0, ctx->stream>>>(ctx->g, bp, ctx->d, ctx->nd, ctx->dd,
+                                                              protectedRange ? ctx->protRange : nullptr);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
 }

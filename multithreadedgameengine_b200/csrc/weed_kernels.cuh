@@ -194,6 +194,7 @@ struct ById {
   uint8_t* F;        // flag bits
   uint8_t* CC;       // collisionCount
   uint32_t* GID;     // slab mode: global entity id of each local slot (nullptr: id = index)
+  uint8_t* ET;       // Transform.entityType (device-side systems only)
 };
 struct BySlot {
   float4* SA;        // slot record: SA[2s] = (x, y, radius, flagword), SA[2s+1] = (px, py, visualRange, id bits)
@@ -955,6 +956,7 @@ struct Staging {
   const float* vx; const float* vy; const float* ax; const float* ay; const float* px; const float* py;
   const float* maxVel; const float* velAngle; const float* speed; const uint8_t* collCnt;
   const uint8_t* c_active; const float* radius; const uint8_t* isTrigger; const float* visRange;
+  const uint8_t* entityType;
 };
 
 __global__ void __launch_bounds__(256) k_pack(uint32_t N, uint32_t mask, Staging st, ById d) {
@@ -1004,6 +1006,7 @@ __global__ void __launch_bounds__(256) k_pack(uint32_t N, uint32_t mask, Staging
     d.V[i] = v;
   }
   if (mask & (1u << 14)) d.CC[i] = st.collCnt[i];
+  if (mask & (1u << 19)) d.ET[i] = st.entityType[i];
 }
 
 struct StagingOut {
@@ -1012,6 +1015,7 @@ struct StagingOut {
   float* vx; float* vy; float* ax; float* ay; float* px; float* py;
   float* maxVel; float* velAngle; float* speed; uint8_t* collCnt;
   uint8_t* c_active; float* radius; uint8_t* isTrigger; float* visRange;
+  uint8_t* entityType;
 };
 
 __global__ void __launch_bounds__(256) k_unpack(uint32_t N, uint32_t mask, StagingOut st, ById d) {
@@ -1052,6 +1056,69 @@ __global__ void __launch_bounds__(256) k_unpack(uint32_t N, uint32_t mask, Stagi
     if (mask & (1u << 13)) st.speed[i] = v.z;
   }
   if (mask & (1u << 14)) st.collCnt[i] = d.CC[i];
+  if (mask & (1u << 19)) st.entityType[i] = d.ET[i];
+}
+
+// ---- system: boids flocking tick ------------------------------------------------
+// demos/predators/boid.js:137-240 + :318-341, one thread per entity, evaluation order and
+// rounding of the JavaScript: accumulators are binary64, every `rbAX[i] += ...` rounds to
+// float32.  Reads the API rows where the spatial pass left them.
+struct BoidsParams { double centering, avoid, matching, turn, margin, dtRatio; uint32_t mouseType; };
+
+__global__ void __launch_bounds__(128)
+k_system_boids(GridDims g, BoidsParams bp, ById d, const int32_t* __restrict__ nd, const float* __restrict__ dd,
+               const float* __restrict__ protectedRange) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.N || i == 0) return;                   // index 0 is the Mouse: its tick() is empty
+  if (!(d.F[i] & F_T_ACTIVE)) return;
+  const size_t off = (size_t)i * (1 + (size_t)g.M);
+  const int32_t cnt = nd[off];
+  const float4 me = d.DP[i];
+  const double myX = me.x, myY = me.y;
+  float2 acc = d.ACC[i];
+  if (cnt > 0) {
+    const float pr = protectedRange ? protectedRange[i] : d.AT[i].y * 2.0f;   // boid.js:64
+    const double pr2 = dmul((double)pr, (double)pr);
+    double cx = 0, cy = 0, avx = 0, avy = 0, sx = 0, sy = 0;
+    uint32_t same = 0;
+    const uint32_t myType = d.ET[i];
+    for (int32_t n = 0; n < cnt; n++) {
+      const int32_t j = nd[off + 1 + n];
+      const uint32_t nt = d.ET[j];
+      if (nt == bp.mouseType) continue;                                        // :179
+      const double d2 = (double)dd[off + 1 + n];
+      const float4 pj = d.DP[j];
+      const double dx = dsub((double)pj.x, myX), dy = dsub((double)pj.y, myY);
+      if (d2 < pr2 && d2 > 0) {                                                // :192-196
+        sx = dsub(sx, ddiv(dx, d2));
+        sy = dsub(sy, ddiv(dy, d2));
+        continue;
+      }
+      if (nt == myType) {                                                      // :199-206
+        const float4 vj = d.V[j];
+        cx = dadd(cx, (double)pj.x); cy = dadd(cy, (double)pj.y);
+        avx = dadd(avx, (double)vj.x); avy = dadd(avy, (double)vj.y);
+        same++;
+      }
+    }
+    if (same) {                                                                // :221-232
+      const float4 vi = d.V[i];
+      cx = ddiv(cx, (double)same); cy = ddiv(cy, (double)same);
+      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(cx, myX), bp.centering), bp.dtRatio)));
+      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(cy, myY), bp.centering), bp.dtRatio)));
+      avx = ddiv(avx, (double)same); avy = ddiv(avy, (double)same);
+      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(avx, (double)vi.x), bp.matching), bp.dtRatio)));
+      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(avy, (double)vi.y), bp.matching), bp.dtRatio)));
+    }
+    acc.x = fround(dadd((double)acc.x, dmul(dmul(sx, bp.avoid), bp.dtRatio)));  // :235-236
+    acc.y = fround(dadd((double)acc.y, dmul(dmul(sy, bp.avoid), bp.dtRatio)));
+  }
+  const double turn = dmul(bp.turn, bp.dtRatio);                               // :334-340
+  if (myX < bp.margin) acc.x = fround(dadd((double)acc.x, turn));
+  if (myX > dsub(g.worldW, bp.margin)) acc.x = fround(dsub((double)acc.x, turn));
+  if (myY < bp.margin) acc.y = fround(dadd((double)acc.y, turn));
+  if (myY > dsub(g.worldH, bp.margin)) acc.y = fround(dsub((double)acc.y, turn));
+  d.ACC[i] = acc;
 }
 
 // ---- statistics (only when the host asks) -------------------------------------------------

@@ -186,6 +186,17 @@ class GameEngine:
     def sync(self):
         B.check(self.ctx, B.lib().weed_sync(self.ctx))
 
+    def system_boids(self, dtRatio=1.0, protectedRange=None, centeringFactor=0.001, avoidFactor=0.3,
+                     matchingFactor=0.1, turnFactor=0.01, margin=20.0, mouseEntityType=0):
+        """Device-side tick() of the boids demo (demos/predators/boid.js:115-240, :318-341): reads the
+        neighbor rows on the device and accumulates RigidBody.ax/ay there (weed_system_boids)."""
+        p = B.BoidsParams(centeringFactor, avoidFactor, matchingFactor, turnFactor, margin, mouseEntityType, 0)
+        ptr = None
+        if protectedRange is not None:
+            self._prot = np.ascontiguousarray(protectedRange, dtype=np.float32)
+            ptr = self._prot.ctypes.data
+        B.check(self.ctx, B.lib().weed_system_boids(self.ctx, C.byref(p), ptr, float(dtRatio)))
+
     def updatePhysicsConfig(self, partial):
         """gameEngine.js:1304-1325 -> applyPhysicsConfig + validatePhysicsConfig."""
         phys = self.config["physics"]

@@ -402,3 +402,61 @@ def test_config2_boids_with_host_tick_consumer():
         assert np.array_equal(bits(eng.col["RB.ax"]), bits(ora.col["RB.ax"]))
         assert np.abs(eng.col["RB.ax"]).max() > 0
     eng.close()
+
+
+def test_no_neighbor_rows_flag_and_device_pointers():
+    """Physics-only consumers can skip the API rows (WEED_FLAG_NO_NEIGHBOR_ROWS): the state must
+    not change, row fetches must fail with a code; device pointers are exposed for in-process
+    consumers."""
+    import ctypes as C
+    cfg, cols = scenes.scaled("config4", 20000)
+    a = make_engine(cfg, cols)
+    b = make_engine(cfg, cols, flags=B.FLAG_NO_NEIGHBOR_ROWS, host_neighbor_rows=False)
+    a.run(4); b.run(4)
+    a.download(B.COLS_INPUT_ALL | B.COL_COLLISIONS); b.download(B.COLS_INPUT_ALL | B.COL_COLLISIONS)
+    assert_cols_equal(a.col, b.col)
+    n = int(a.collisionData[0])
+    assert n == int(b.collisionData[0]) and np.array_equal(a.collisionData[:1 + 2 * n], b.collisionData[:1 + 2 * n])
+    assert B.lib().weed_fetch_neighbors(b.ctx, 0, 1) == B.WEED_E_STATE
+    ptr, nbytes = a.device_ptr(B.DEV_NEIGHBOR)
+    assert ptr and nbytes == cfg["entityCount"] * (1 + a.maxNeighbors) * 4
+    ptr, nbytes = a.device_ptr(B.DEV_STATE)
+    assert ptr and nbytes == cfg["entityCount"] * 16
+    assert b.device_ptr(B.DEV_NEIGHBOR)[0] is None
+    a.close(); b.close()
+
+
+def test_device_side_boids_system_matches_host_tick():
+    """the boids tick() as a device-side system (weed_system_boids) must write the
+    same RigidBody.ax/ay, bit for bit, as the host-side restatement of demos/predators/boid.js
+    fed with the fetched neighbor rows — and the simulation driven by either must stay identical."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    from boids_tick import tick_all
+
+    cfg, cols = scenes.boids(n_prey=1500, n_pred=80, seed=5)
+    cfg["worldWidth"], cfg["worldHeight"] = 1500.0, 750.0
+    for k, f in (("T.x", 1500 / 5000), ("RB.px", 1500 / 5000), ("T.y", 750 / 2000), ("RB.py", 750 / 2000)):
+        cols[k] = (cols[k] * np.float32(f)).astype(np.float32)
+    cfg["spatial"]["maxNeighbors"] = 160
+    N, M = cfg["entityCount"], 160
+    etype = np.zeros(N, dtype=np.uint8)
+    etype[1:1501] = 1
+    etype[1501:] = 2
+    dev = make_engine(cfg, cols)       # tick() on the device
+    host = make_engine(cfg, cols)      # tick() on the host, rows fetched
+    for e in (dev, host):
+        e.Transform.entityType[:] = etype
+        e.upload(e.mask("T.entityType"))
+    up = host.mask("RB.ax", "RB.ay")
+    for frame in range(5):
+        dev.step(1.0, 0, 0)                                      # nothing crosses PCIe
+        host.step(1.0, up if frame else 0, B.COLS_OUTPUT_ALL | B.COL_NEIGHBORS)
+        dev.system_boids(1.0)
+        tick_all(host.col, etype, host.neighborData, host.distanceData, M, cfg["worldWidth"], cfg["worldHeight"])
+        dev.download(B.COLS_OUTPUT_ALL)
+        for k in ("RB.ax", "RB.ay", "T.x", "T.y", "RB.vx", "RB.vy"):
+            assert np.array_equal(bits(dev.col[k]), bits(host.col[k])), f"frame {frame} {k}"
+    assert np.abs(dev.col["RB.ax"]).max() > 0
+    dev.close(); host.close()
