@@ -251,15 +251,23 @@ int weed_system_boids(weed_ctx* ctx, const weed_boids_params* params, const floa
 #define WEED_SLAB_RECORD_BYTES 64
 /* global ids of local slots [0,count); slots >= count are free.  Call after weed_upload.   */
 int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t count);
-/* gids_out[capacity] (0xFFFFFFFF for free slots), *top_out = slots in use                  */
+/* gids_out[capacity] (0xFFFFFFFF for free slots), *top_out = slots in use (synchronises)   */
 int weed_slab_get_gids(weed_ctx* ctx, uint32_t* gids_out, uint32_t* top_out);
-/* after a frame: records for the low / high neighbour into device buffers of `capacity`
- * records each; returns the record counts and the number of entities owned this frame.      */
-int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t capacity,
-                   uint32_t* n_low, uint32_t* n_high, uint32_t* n_owned);
-/* drop this frame's replicas, then insert the neighbours' records                           */
-int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, uint32_t n_low,
-                    const void* dev_from_high, uint32_t n_high, uint32_t* new_top);
+/* Exchange buffers hold (quota + 1) records: record 0 is a header carrying the record count, so
+ * a FIXED-size message per neighbour and frame needs no separate size negotiation and the
+ * whole exchange stays asynchronous on the context's stream (no host synchronisation).
+ * weed_slab_pack: after a frame, records for the low / high neighbour.                     */
+int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t quota);
+/* drop this frame's replicas, then insert the neighbours' records (either may be NULL)     */
+int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, const void* dev_from_high, uint32_t quota);
+typedef struct weed_slab_stats {
+  uint32_t top, capacity;          /* local slots in use / available                         */
+  uint32_t owned;                  /* entities owned during the last packed frame            */
+  uint32_t sentLow, sentHigh, receivedLow, receivedHigh;   /* records of the last exchange   */
+  uint32_t overflow;               /* sticky: 1 = quota exceeded, 2 = table full             */
+} weed_slab_stats;
+/* synchronises; returns WEED_E_OVERFLOW if a quota or the table overflowed at any time      */
+int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,11 @@ class BoidsParams(C.Structure):
                 ("turnFactor", C.c_double), ("margin", C.c_double), ("mouseEntityType", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class SlabStats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("top", "capacity", "owned", "sentLow", "sentHigh", "receivedLow",
+                                           "receivedHigh", "overflow")]
+
+
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("gridCols", C.c_uint32), ("gridRows", C.c_uint32),
                 ("activeInGrid", C.c_uint32), ("maxCellOccupancy", C.c_uint32),
@@ -98,9 +103,9 @@ SYMBOLS = {
     "weed_system_boids": (C.c_int, [C.c_void_p, C.POINTER(BoidsParams), C.c_void_p, C.c_double]),
     "weed_slab_set_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
-    "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
-                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
-    "weed_slab_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "weed_slab_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "weed_slab_status": (C.c_int, [C.c_void_p, C.POINTER(SlabStats)]),
 }
 SLAB_RECORD_BYTES = 64
 

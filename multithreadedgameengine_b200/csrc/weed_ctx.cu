@@ -171,7 +171,6 @@ struct weed_ctx {
   uint32_t launchesPerStep = 0;
   // slabs
   bool slab = false;
-  uint32_t slabTop = 0;
   uint32_t* holes = nullptr;
   SlabCounters* dSlab = nullptr;
 };
@@ -702,63 +701,60 @@ extern "C" int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t 
   if (!gids || count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "bad gid list");
   CK(cudaMemsetAsync(ctx->d.GID, 0xFF, (size_t)ctx->g.N * 4, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d.GID, gids, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SlabCounters sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.top = count;
+  CK(cudaMemcpyAsync(ctx->dSlab, &sc, sizeof(sc), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->slabTop = count;
   return WEED_OK;
 }
 
 extern "C" int weed_slab_get_gids(weed_ctx* ctx, uint32_t* gids_out, uint32_t* top_out) {
   GUARD(ctx);
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
-  if (gids_out) {
-    CK(cudaMemcpyAsync(gids_out, ctx->d.GID, (size_t)ctx->g.N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
-  if (top_out) *top_out = ctx->slabTop;
+  SlabCounters sc;
+  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gids_out) CK(cudaMemcpyAsync(gids_out, ctx->d.GID, (size_t)ctx->g.N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (top_out) *top_out = sc.top;
   return WEED_OK;
 }
 
-extern "C" int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t capacity,
-                              uint32_t* n_low, uint32_t* n_high, uint32_t* n_owned) {
+extern "C" int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t quota) {
   GUARD(ctx);
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
-  CK(cudaMemsetAsync(ctx->dSlab, 0, sizeof(SlabCounters), ctx->stream));
-  if (ctx->slabTop)
-    k_slab_pack<<<blocks_for(ctx->slabTop, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, ctx->slabTop, (SlabRec*)dev_low,
-                                                                        (SlabRec*)dev_high, capacity, ctx->dSlab);
-  SlabCounters sc;
-  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (sc.overflow) return fail(ctx, WEED_E_OVERFLOW, "slab exchange buffer too small: " + std::to_string(sc.nLow) + " / " + std::to_string(sc.nHigh) + " records");
-  if (n_low) *n_low = sc.nLow;
-  if (n_high) *n_high = sc.nHigh;
-  if (n_owned) *n_owned = sc.owned;
-  return WEED_OK;
-}
-
-extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, uint32_t n_low, const void* dev_from_high,
-                               uint32_t n_high, uint32_t* new_top) {
-  GUARD(ctx);
-  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
-  CK(cudaMemsetAsync(ctx->dSlab, 0, sizeof(SlabCounters), ctx->stream));
-  const uint32_t top = ctx->slabTop;
-  if (top) k_slab_drop<<<blocks_for(top, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, top, ctx->holes, ctx->dSlab);
-  SlabCounters sc;
-  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (n_low)
-    k_slab_unpack<<<blocks_for(n_low, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_low, n_low, 0, ctx->holes, sc.nHoles, top, ctx->g.N, ctx->dSlab);
-  if (n_high)
-    k_slab_unpack<<<blocks_for(n_high, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_high, n_high, n_low, ctx->holes, sc.nHoles, top, ctx->g.N, ctx->dSlab);
+  if (!dev_low || !dev_high || quota == 0) return fail(ctx, WEED_E_INVALID, "exchange buffers missing");
+  k_slab_pack<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, (SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab);
+  k_slab_headers<<<1, 32, 0, ctx->stream>>>((SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab);
   CK(cudaGetLastError());
-  const uint64_t total = (uint64_t)n_low + n_high;
-  uint64_t nt = top;
-  if (total > sc.nHoles) nt = (uint64_t)top + (total - sc.nHoles);
-  if (nt > ctx->g.N) return fail(ctx, WEED_E_OVERFLOW, "slab entity table full: need " + std::to_string(nt) + " slots, capacity " + std::to_string(ctx->g.N));
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->slabTop = (uint32_t)nt;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, const void* dev_from_high, uint32_t quota) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (quota == 0) return fail(ctx, WEED_E_INVALID, "quota must be positive");
+  k_slab_drop<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, ctx->holes, ctx->dSlab);
+  k_slab_unpack<<<blocks_for(2 * (size_t)quota, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_low, (const SlabRec*)dev_from_high,
+                                                                           quota, ctx->holes, ctx->g.N, ctx->dSlab);
+  k_slab_finish<<<1, 32, 0, ctx->stream>>>((const SlabRec*)dev_from_low, (const SlabRec*)dev_from_high, quota, ctx->g.N, ctx->dSlab);
+  CK(cudaGetLastError());
   ctx->spatialValid = false;
-  if (new_top) *new_top = ctx->slabTop;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (!out) return WEED_E_INVALID;
+  SlabCounters sc;
+  CK(cudaMemcpyAsync(&sc, ctx->dSlab, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->top = sc.top; out->owned = sc.lastOwned; out->sentLow = sc.lastLow; out->sentHigh = sc.lastHigh;
+  out->receivedLow = sc.lastFromLow; out->receivedHigh = sc.lastFromHigh; out->overflow = sc.overflow;
+  out->capacity = ctx->g.N;
+  if (sc.overflow & 1u) return fail(ctx, WEED_E_OVERFLOW, "slab exchange quota exceeded: " + std::to_string(sc.lastLow) + " / " + std::to_string(sc.lastHigh) + " records");
+  if (sc.overflow & 2u) return fail(ctx, WEED_E_OVERFLOW, "slab entity table full (capacity " + std::to_string(ctx->g.N) + ")");
   return WEED_OK;
 }
 

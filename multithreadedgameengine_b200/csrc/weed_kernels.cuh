@@ -870,7 +870,15 @@ struct __align__(16) SlabRec {
 };
 static_assert(sizeof(SlabRec) == 64, "slab record must be 64 bytes");
 
-struct SlabCounters { uint32_t nLow, nHigh, nHoles, top, overflow, owned; };
+// device-resident state of the exchange: the host never has to read it between frames
+struct SlabCounters {
+  uint32_t nLow, nHigh;     // records packed for the low / high neighbour this frame
+  uint32_t nHoles;          // free slots found by the drop pass
+  uint32_t top;             // slots in use (persistent)
+  uint32_t overflow;        // sticky: bit0 exchange quota exceeded, bit1 entity table full
+  uint32_t owned;           // entities owned during the frame being packed
+  uint32_t lastOwned, lastLow, lastHigh, lastFromLow, lastFromHigh;   // previous exchange, for reporting
+};
 
 __device__ __forceinline__ bool present_row(const GridDims& g, const ById& d, uint32_t i, int32_t& row) {
   const uint32_t f = d.F[i];
@@ -881,12 +889,13 @@ __device__ __forceinline__ bool present_row(const GridDims& g, const ById& d, ui
   return true;
 }
 
-// key[] still holds the cell of the frame-START position (ownership during the frame)
+// Exchange buffers hold quota + 1 records; record 0 is a header whose `gid` word is the count.
+// key[] still holds the cell of the frame-START position (ownership during the frame).
 __global__ void __launch_bounds__(256)
-k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, SlabRec* __restrict__ low,
-            SlabRec* __restrict__ high, uint32_t capacity, SlabCounters* sc) {
+k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __restrict__ low,
+            SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= top) return;
+  if (i >= sc->top) return;
   const uint32_t k = key[i];
   if (k == KEY_INVALID) return;
   const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
@@ -905,19 +914,25 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, 
   r.dp = d.DP[i]; r.at = d.AT[i]; r.v = d.V[i];
   if (toLow) {
     const uint32_t p = atomicAdd(&sc->nLow, 1u);
-    if (p < capacity) low[p] = r; else sc->overflow = 1;
+    if (p < quota) low[1 + p] = r;
   }
   if (toHigh) {
     const uint32_t p = atomicAdd(&sc->nHigh, 1u);
-    if (p < capacity) high[p] = r; else sc->overflow = 1;
+    if (p < quota) high[1 + p] = r;
   }
 }
 
+__global__ void k_slab_headers(SlabRec* __restrict__ low, SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc) {
+  if (threadIdx.x != 0) return;
+  if (sc->nLow > quota || sc->nHigh > quota) sc->overflow |= 1u;
+  low[0].gid = min(sc->nLow, quota);
+  high[0].gid = min(sc->nHigh, quota);
+}
+
 __global__ void __launch_bounds__(256)
-k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, uint32_t* __restrict__ holes,
-            SlabCounters* sc) {
+k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t* __restrict__ holes, SlabCounters* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= top) return;
+  if (i >= sc->top) return;
   const uint32_t k = key[i];
   bool keep = false;
   if (k != KEY_INVALID) {
@@ -932,20 +947,41 @@ k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t top, 
   }
 }
 
+// first `quota` threads: records from the low neighbour, next `quota`: from the high one
 __global__ void __launch_bounds__(256)
-k_slab_unpack(ById d, const SlabRec* __restrict__ recs, uint32_t n, uint32_t recBase,
-              const uint32_t* __restrict__ holes, uint32_t nHoles, uint32_t top, uint32_t capacity, SlabCounters* sc) {
+k_slab_unpack(ById d, const SlabRec* __restrict__ fromLow, const SlabRec* __restrict__ fromHigh, uint32_t quota,
+              const uint32_t* __restrict__ holes, uint32_t capacity, SlabCounters* sc) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t q = recBase + k;
+  const uint32_t nL = fromLow ? min(fromLow[0].gid, quota) : 0u;
+  const uint32_t nH = fromHigh ? min(fromHigh[0].gid, quota) : 0u;
+  const SlabRec* src;
+  uint32_t q;
+  if (k < quota) { if (k >= nL) return; src = fromLow + 1 + k; q = k; }
+  else { const uint32_t kk = k - quota; if (kk >= nH) return; src = fromHigh + 1 + kk; q = nL + kk; }
+  const uint32_t nHoles = sc->nHoles, top = sc->top;
   const uint32_t i = q < nHoles ? holes[q] : top + (q - nHoles);
-  if (i >= capacity) { sc->overflow = 1; return; }
-  const SlabRec r = recs[k];
+  if (i >= capacity) return;                                   // flagged by k_slab_finish
+  const SlabRec r = *src;
   d.GID[i] = r.gid;
   d.F[i] = (uint8_t)(r.meta & 0xFFu);
   d.CC[i] = (uint8_t)((r.meta >> 8) & 0xFFu);
   d.ACC[i] = make_float2(r.ax, r.ay);
   d.DP[i] = r.dp; d.AT[i] = r.at; d.V[i] = r.v;
+}
+
+__global__ void k_slab_finish(const SlabRec* __restrict__ fromLow, const SlabRec* __restrict__ fromHigh, uint32_t quota,
+                              uint32_t capacity, SlabCounters* sc) {
+  if (threadIdx.x != 0) return;
+  const uint32_t nL = fromLow ? min(fromLow[0].gid, quota) : 0u;
+  const uint32_t nH = fromHigh ? min(fromHigh[0].gid, quota) : 0u;
+  const unsigned long long total = (unsigned long long)nL + nH;
+  unsigned long long nt = sc->top;
+  if (total > sc->nHoles) nt += total - sc->nHoles;
+  if (nt > capacity) { sc->overflow |= 2u; nt = capacity; }
+  sc->top = (uint32_t)nt;
+  sc->lastOwned = sc->owned; sc->lastLow = sc->nLow; sc->lastHigh = sc->nHigh;
+  sc->lastFromLow = nL; sc->lastFromHigh = nH;
+  sc->nLow = 0; sc->nHigh = 0; sc->nHoles = 0; sc->owned = 0;
 }
 
 // ---- host <-> device column plumbing ---------------------------------------------------------

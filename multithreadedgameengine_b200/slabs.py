@@ -110,43 +110,27 @@ def replan_from_times(blocks, times_ms):
     return [(cuts[k], cuts[k + 1]) for k in range(world)]
 
 
-def exchange_records(torch, rank, world, send_low, n_low, send_high, n_high, recv_low, recv_high, capacity):
-    """Neighbour exchange of one frame: first the two record counts, then exactly that many
-    64-byte records, with the adjacent ranks only (rank-1 = low, rank+1 = high).  Works on any
-    backend/device pair torch.distributed supports (NCCL + CUDA tensors on the GPUs, gloo + CPU
-    tensors in the CPU tests).  Returns (records received from low, from high)."""
+def exchange_fixed(torch, rank, world, send_low, send_high, recv_low, recv_high):
+    """Neighbour exchange of one frame: ONE fixed-size message per adjacent rank and direction
+    (rank-1 = low, rank+1 = high).  Every buffer holds quota + 1 records of 64 bytes; record 0 is
+    a header carrying the number of valid records, so no size negotiation and no host
+    synchronisation are needed.  Works on any backend/device pair torch.distributed supports
+    (NCCL + CUDA tensors on the GPUs, gloo + CPU tensors in the CPU tests)."""
     dist = torch.distributed
-    dev = send_low.device
-    cnt_out = torch.tensor([n_low, n_high], dtype=torch.int64, device=dev)
-    cnt_in = torch.zeros(2, dtype=torch.int64, device=dev)
     lo, hi = rank - 1, rank + 1
     ops = []
     if lo >= 0:
-        ops += [dist.P2POp(dist.isend, cnt_out[0:1], lo), dist.P2POp(dist.irecv, cnt_in[0:1], lo)]
+        ops += [dist.P2POp(dist.isend, send_low, lo), dist.P2POp(dist.irecv, recv_low, lo)]
     if hi < world:
-        ops += [dist.P2POp(dist.isend, cnt_out[1:2], hi), dist.P2POp(dist.irecv, cnt_in[1:2], hi)]
+        ops += [dist.P2POp(dist.isend, send_high, hi), dist.P2POp(dist.irecv, recv_high, hi)]
     if ops:
         for r in dist.batch_isend_irecv(ops):
-            r.wait()
-    fl, fh = (int(v) for v in cnt_in.tolist())
-    if max(fl, fh) > capacity:
-        raise RuntimeError(f"slab exchange buffer too small: {fl}/{fh} records > {capacity}")
-    R = B.SLAB_RECORD_BYTES
-    ops = []
-    if lo >= 0:
-        if n_low:
-            ops.append(dist.P2POp(dist.isend, send_low[:n_low * R], lo))
-        if fl:
-            ops.append(dist.P2POp(dist.irecv, recv_low[:fl * R], lo))
-    if hi < world:
-        if n_high:
-            ops.append(dist.P2POp(dist.isend, send_high[:n_high * R], hi))
-        if fh:
-            ops.append(dist.P2POp(dist.irecv, recv_high[:fh * R], hi))
-    if ops:
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-    return fl, fh
+            r.wait()            # CUDA tensors: orders the current stream after the transfer, does not block the host
+
+
+def header_count(buf):
+    """Record count stored in the header (first 4 bytes) of an exchange buffer (host-side helper)."""
+    return int(buf[:4].cpu().numpy().view(np.uint32)[0])
 
 
 class SlabEngine:
@@ -161,9 +145,10 @@ class SlabEngine:
         self.rb, self.re = self.blocks[rank]
         row, self.rows = cell_rows(cfg, cols["T.y"])
         act = cols["T.active"] != 0
-        inside = act & np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"]) & (row >= self.rb - self.H) & (row < self.re + self.H)
+        fin = np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"])
+        inside = act & fin & (row >= self.rb - self.H) & (row < self.re + self.H)
         if rank == 0:   # active entities that never enter the grid (NaN position) live on slab 0
-            inside |= act & ~(np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"]))
+            inside |= act & ~fin
         sel = np.nonzero(inside)[0].astype(np.uint32)
         self.capacity = int(len(sel) * capacity_factor) + 4096
         lcfg = dict(cfg)
@@ -176,45 +161,50 @@ class SlabEngine:
             self.eng.column(k)[:len(sel)] = v[sel]
         self.eng.upload(B.COLS_INPUT_ALL)
         B.check(self.eng.ctx, B.lib().weed_slab_set_gids(self.eng.ctx, sel.ctypes.data, len(sel)))
-        self.top = len(sel)
-        # exchange buffers: the boundary band is a small fraction of a slab
-        self.rec_capacity = max(65536, int(0.25 * self.capacity))
+        # exchange quota: twice the start population of the widest boundary band of ANY cut (+ slack),
+        # the same on every rank, because the two sides of a cut must agree on the message size;
+        # every frame moves exactly (quota + 1) records per neighbour and direction
+        hist = np.bincount(row[act & fin], minlength=self.rows)
+        band = 0
+        for (_, cut) in self.blocks[:-1]:
+            band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
+        self.quota = 2 * band + 8192
         dev = torch.device("cuda", device)
-        mk = lambda: torch.empty(self.rec_capacity * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
+        mk = lambda: torch.zeros((self.quota + 1) * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
         self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
-        self.owned = 0
-        self.sent_bytes = 0
 
-    # ---- one frame of this slab (asynchronous) ---------------------------------------------------
+    # ---- one frame of this slab: everything below is asynchronous on the context's stream ---------
     def run(self, dtRatio=1.0):
         self.eng.run(1, dtRatio)
 
     def pack(self):
-        nl, nh, ow = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        B.check(self.eng.ctx, B.lib().weed_slab_pack(self.eng.ctx, self.send_low.data_ptr(), self.send_high.data_ptr(),
-                                                     self.rec_capacity, C.byref(nl), C.byref(nh), C.byref(ow)))
-        self.owned = ow.value
-        self.sent_bytes = (nl.value + nh.value) * B.SLAB_RECORD_BYTES
-        return nl.value, nh.value
+        B.check(self.eng.ctx, B.lib().weed_slab_pack(self.eng.ctx, self.send_low.data_ptr(), self.send_high.data_ptr(), self.quota))
 
-    def apply(self, n_from_low, n_from_high):
-        top = C.c_uint32()
-        B.check(self.eng.ctx, B.lib().weed_slab_apply(self.eng.ctx, self.recv_low.data_ptr(), n_from_low,
-                                                      self.recv_high.data_ptr(), n_from_high, C.byref(top)))
-        self.top = top.value
+    def apply(self):
+        lo = self.recv_low.data_ptr() if self.rank > 0 else None
+        hi = self.recv_high.data_ptr() if self.rank + 1 < self.world else None
+        B.check(self.eng.ctx, B.lib().weed_slab_apply(self.eng.ctx, lo, hi, self.quota))
 
     def exchange_dist(self):
-        """pack -> counts and records to the two adjacent ranks (NCCL send/recv) -> apply."""
-        nl, nh = self.pack()
-        fl, fh = exchange_records(self.torch, self.rank, self.world, self.send_low, nl, self.send_high, nh,
-                                  self.recv_low, self.recv_high, self.rec_capacity)
-        if self.send_low.is_cuda:
-            self.torch.cuda.current_stream().synchronize()
-        self.apply(fl, fh)
+        """pack -> one fixed-size NCCL send/recv per adjacent rank -> apply; no host synchronisation."""
+        self.pack()
+        exchange_fixed(self.torch, self.rank, self.world, self.send_low, self.send_high, self.recv_low, self.recv_high)
+        self.apply()
 
     def step_dist(self, dtRatio=1.0):
         self.run(dtRatio)
         self.exchange_dist()
+
+    def status(self):
+        """Synchronises; raises if a quota or the entity table overflowed at any time."""
+        st = B.SlabStats()
+        B.check(self.eng.ctx, B.lib().weed_slab_status(self.eng.ctx, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    @property
+    def exchange_bytes_per_frame(self):
+        n = (self.rank > 0) + (self.rank + 1 < self.world)
+        return n * (self.quota + 1) * B.SLAB_RECORD_BYTES
 
     # ---- results -----------------------------------------------------------------------------------
     def gids(self):
@@ -253,20 +243,19 @@ class SlabGroup:
     def step(self, dtRatio=1.0):
         for s in self.slabs:
             s.run(dtRatio)
-        counts = [s.pack() for s in self.slabs]
-        R = B.SLAB_RECORD_BYTES
+        for s in self.slabs:
+            s.pack()
+        self.slabs[0].torch.cuda.synchronize()
         for r, s in enumerate(self.slabs):
-            fl = fh = 0
             if r > 0:
-                fl = counts[r - 1][1]                       # the low neighbour's "high" records
-                s.recv_low[:fl * R].copy_(self.slabs[r - 1].send_high[:fl * R])
+                s.recv_low.copy_(self.slabs[r - 1].send_high)
             if r + 1 < len(self.slabs):
-                fh = counts[r + 1][0]
-                s.recv_high[:fh * R].copy_(self.slabs[r + 1].send_low[:fh * R])
-            s._incoming = (fl, fh)
+                s.recv_high.copy_(self.slabs[r + 1].send_low)
         self.slabs[0].torch.cuda.synchronize()
         for s in self.slabs:
-            s.apply(*s._incoming)
+            s.apply()
+        for s in self.slabs:
+            s.status()
 
     def gather(self, N, keys=("T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.speed", "RB.collisionCount")):
         out = {k: None for k in keys}

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from multithreadedgameengine_b200 import binding as B, scenes
-from multithreadedgameengine_b200.slabs import cell_rows, exchange_records, halo_rows, plan_slabs, replan_from_times
+from multithreadedgameengine_b200.slabs import cell_rows, exchange_fixed, halo_rows, header_count, plan_slabs, replan_from_times
 
 
 def test_cell_rows_follow_the_reference_key():
@@ -79,45 +79,42 @@ def _free_port():
     return p
 
 
+def _payload(frame, rank, side, quota, R):
+    """Deterministic (count, bytes) a rank puts in its low (0) / high (1) send buffer."""
+    g = np.random.default_rng(10007 * frame + 31 * rank + side)
+    n = int(g.integers(0, quota + 1))
+    return n, g.integers(0, 255, n * R, dtype=np.uint8)
+
+
 def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     R = B.SLAB_RECORD_BYTES
-    cap = 64
-    mk = lambda: torch.zeros(cap * R, dtype=torch.uint8)
+    quota = 48
+    mk = lambda: torch.zeros((quota + 1) * R, dtype=torch.uint8)
     ok = True
     for frame in range(3):
-        rng = np.random.default_rng(1000 * frame + rank)
-        n_low, n_high = int(rng.integers(0, 40)), int(rng.integers(0, 40))
-        send_low, send_high, recv_low, recv_high = mk(), mk(), mk(), mk()
-        send_low[:n_low * R] = torch.from_numpy(rng.integers(0, 255, n_low * R, dtype=np.uint8))
-        send_high[:n_high * R] = torch.from_numpy(rng.integers(0, 255, n_high * R, dtype=np.uint8))
-        fl, fh = exchange_records(torch, rank, world, send_low, n_low, send_high, n_high, recv_low, recv_high, cap)
-        # what the neighbours must have sent (same seeded generators)
-        if rank > 0:
-            g = np.random.default_rng(1000 * frame + rank - 1)
-            a, b_ = int(g.integers(0, 40)), int(g.integers(0, 40))
-            g.integers(0, 255, a * R, dtype=np.uint8)
-            want = g.integers(0, 255, b_ * R, dtype=np.uint8)          # its HIGH buffer comes to my LOW side
-            ok &= fl == b_ and np.array_equal(recv_low[:fl * R].numpy(), want)
+        bufs = {}
+        for side in (0, 1):
+            n, data = _payload(frame, rank, side, quota, R)
+            b_ = mk()
+            b_[:4] = torch.from_numpy(np.array([n], dtype=np.uint32).view(np.uint8))     # header: record count
+            b_[R:R + n * R] = torch.from_numpy(data)
+            bufs[side] = b_
+        recv_low, recv_high = mk(), mk()
+        exchange_fixed(torch, rank, world, bufs[0], bufs[1], recv_low, recv_high)
+        if rank > 0:      # the low neighbour's HIGH buffer arrives on my LOW side
+            n, data = _payload(frame, rank - 1, 1, quota, R)
+            ok &= header_count(recv_low) == n and np.array_equal(recv_low[R:R + n * R].numpy(), data)
         else:
-            ok &= fl == 0
+            ok &= header_count(recv_low) == 0
         if rank + 1 < world:
-            g = np.random.default_rng(1000 * frame + rank + 1)
-            a, b_ = int(g.integers(0, 40)), int(g.integers(0, 40))
-            want = g.integers(0, 255, a * R, dtype=np.uint8)           # its LOW buffer comes to my HIGH side
-            ok &= fh == a and np.array_equal(recv_high[:fh * R].numpy(), want)
+            n, data = _payload(frame, rank + 1, 0, quota, R)
+            ok &= header_count(recv_high) == n and np.array_equal(recv_high[R:R + n * R].numpy(), data)
         else:
-            ok &= fh == 0
-    # overflow is an error, not silent truncation
-    try:
-        big = torch.zeros(cap * R, dtype=torch.uint8)
-        exchange_records(torch, rank, world, big, cap, big, cap, mk(), mk(), cap // 2)
-        raised = world == 1
-    except RuntimeError:
-        raised = True
-    open(os.path.join(out_dir, f"r{rank}"), "w").write("ok" if ok and raised else "bad")
+            ok &= header_count(recv_high) == 0
+    open(os.path.join(out_dir, f"r{rank}"), "w").write("ok" if ok else "bad")
     dist.destroy_process_group()
 
 

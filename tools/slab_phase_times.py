@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 import bench
-from multithreadedgameengine_b200.slabs import SlabEngine, exchange_records, plan_slabs
+from multithreadedgameengine_b200.slabs import SlabEngine, exchange_fixed, plan_slabs
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -30,16 +30,17 @@ with torch.cuda.stream(stream):
         t0 = time.perf_counter()
         sl.run(); sl.eng.sync()
         t1 = time.perf_counter()
-        nl, nh = sl.pack()
+        sl.pack(); sl.eng.sync()
         t2 = time.perf_counter()
-        fl, fh = exchange_records(torch, rank, world, sl.send_low, nl, sl.send_high, nh, sl.recv_low, sl.recv_high, sl.rec_capacity)
+        exchange_fixed(torch, rank, world, sl.send_low, sl.send_high, sl.recv_low, sl.recv_high)
         torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
-        sl.apply(fl, fh)
+        sl.apply(); sl.eng.sync()
         t4 = time.perf_counter()
         T += [t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0]
     T *= 1e3 / frames
-    print(f"rank {rank}: frame {T[0]:.3f} ms, pack {T[1]:.3f}, exchange {T[2]:.3f}, apply {T[3]:.3f}, total {T[4]:.3f}; "
-          f"records out {nl}+{nh}, in {fl}+{fh}, top {sl.top}, owned {sl.owned}", flush=True)
+    st = sl.status()
+    print(f"rank {rank}: frame {T[0]:.3f} ms, pack {T[1]:.3f}, exchange {T[2]:.3f}, apply {T[3]:.3f}, total {T[4]:.3f} "
+          f"(each phase synchronised for the measurement); quota {sl.quota}, {st}", flush=True)
     sl.close()
 dist.destroy_process_group()
