@@ -294,7 +294,10 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   }
   if (!(cfg->cellSize > 0) || !(cfg->worldWidth > 0) || !(cfg->worldHeight > 0)) { g_create_error = "world/cell size must be positive"; return WEED_E_INVALID; }
   const double colsD = ceil(cfg->worldWidth / cfg->cellSize), rowsD = ceil(cfg->worldHeight / cfg->cellSize);  // spatial_worker.js:82-83
-  if (!(colsD >= 1) || !(rowsD >= 1) || colsD * rowsD > 1.0e9) { g_create_error = "grid too large"; return WEED_E_INVALID; }
+  if (!(colsD >= 1) || !(rowsD >= 1) || colsD * rowsD > 1.0e9 || colsD > 65535 || rowsD > 65535) {
+    g_create_error = "grid too large (at most 65535 x 65535 cells, 1e9 in total)";
+    return WEED_E_INVALID;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     g_create_error = "no CUDA device: libweedgpu has no CPU fallback";
@@ -347,7 +350,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
-  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.WIN, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
+  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);

@@ -200,6 +200,8 @@ struct BySlot {
   float4* SA;        // slot record: SA[2s] = (x, y, radius, flagword), SA[2s+1] = (px, py, visualRange, id bits)
   float2* QXY;       // position at grid-build time (query position)
   int4* WIN;         // clamped scan window of the entity: r0, r1, c0, c1 (r0 > r1: no scan)
+  uint4* PW;         // what a neighbour needs about me in one 16 B gather: visualRange bits, id,
+                     // r0 | r1 << 16, c0 | c1 << 16 (grid dimensions are limited to 65535)
   float4* GA;        // substep ping-pong: x, y, radius, flagword
   float4* GB;
   float2* PXY;       // px, py after the first substep
@@ -306,6 +308,8 @@ k_slot_prep(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart) {
   int4 wi = make_int4(1, 0, 1, 0);
   if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
   s.WIN[e] = wi;
+  s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
+                       (uint32_t)wi.z | ((uint32_t)wi.w << 16));
   s.XHEAD[e] = 0;
 }
 
@@ -412,17 +416,19 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     const uint32_t first = n - cnt;                       // row position of my first staged entry
     for (uint32_t k = 0; k < cnt; k++) {
       const uint32_t tc = myW[k];
-      const float4 ht = s.SA[2 * (size_t)tc + 1];
-      const int4 wt = s.WIN[tc];
-      const uint32_t jid = __float_as_uint(ht.w);
+      const uint4 pw = s.PW[tc];
+      const uint32_t jid = pw.y;
+      const float vrT = __uint_as_float(pw.x);
       // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric and
       // d2 > 0 holds; with equal visual ranges d2 < vr_t^2 is the predicate that just passed.
-      bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
-      if (back && ht.z != vr) {
+      // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
+      bool back = (uint32_t)myRow >= (pw.z & 0xFFFFu) && (uint32_t)myRow <= (pw.z >> 16) &&
+                  (uint32_t)myCol >= (pw.w & 0xFFFFu) && (uint32_t)myCol <= (pw.w >> 16);
+      if (back && vrT != vr) {
         const float2 c = s.QXY[tc];
         const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
         const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        back = d2 < dmul((double)ht.z, (double)ht.z);
+        back = d2 < dmul((double)vrT, (double)vrT);
       }
       const bool out = jid > id;
       myW[k] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
