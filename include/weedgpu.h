@@ -200,6 +200,9 @@ int weed_get_physics(weed_ctx* ctx, weed_physics_config* out);
 /* replaces: GameObject.updateNeighbors reading row i (src/core/gameObject.js:700-729):
  * copies rows [first, first+count) of neighborData and distanceData to the bound SABs.  */
 int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t count);
+/* same rows into caller-provided compact buffers of count*(1+maxNeighbors) words each (for
+ * worlds whose full neighborData would not fit in host memory); either pointer may be NULL */
+int weed_fetch_neighbors_to(weed_ctx* ctx, uint32_t first, uint32_t count, int32_t* neighbor_out, float* distance_out);
 
 int weed_sync(weed_ctx* ctx);
 int weed_get_stats(weed_ctx* ctx, weed_stats* out);

@@ -96,6 +96,7 @@ SYMBOLS = {
     "weed_set_physics": (C.c_int, [C.c_void_p, C.POINTER(PhysicsConfig)]),
     "weed_get_physics": (C.c_int, [C.c_void_p, C.POINTER(PhysicsConfig)]),
     "weed_fetch_neighbors": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "weed_fetch_neighbors_to": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "weed_sync": (C.c_int, [C.c_void_p]),
     "weed_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "weed_last_error": (C.c_char_p, [C.c_void_p]),

@@ -654,6 +654,18 @@ extern "C" int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t coun
   return WEED_OK;
 }
 
+extern "C" int weed_fetch_neighbors_to(weed_ctx* ctx, uint32_t first, uint32_t count, int32_t* neighbor_out, float* distance_out) {
+  GUARD(ctx);
+  if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
+  if ((size_t)first + count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "row range out of bounds");
+  const size_t stride = 1 + (size_t)ctx->g.M;
+  const size_t off = (size_t)first * stride, len = (size_t)count * stride;
+  if (neighbor_out) CK(cudaMemcpyAsync(neighbor_out, ctx->nd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (distance_out) CK(cudaMemcpyAsync(distance_out, ctx->dd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
 extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   GUARD(ctx);
   if (!out) return WEED_E_INVALID;

@@ -168,6 +168,13 @@ class GameEngine:
 
     def neighbors_of(self, i, fetch=True):
         """GameObject.updateNeighbors (gameObject.js:700-729): (ids, squared distances) of row i."""
+        if self.neighborData is None:      # no host mirror of the rows: fetch this row into a scratch pair
+            stride = 1 + self.maxNeighbors
+            nd = np.empty(stride, dtype=np.int32)
+            dd = np.empty(stride, dtype=np.float32)
+            B.check(self.ctx, B.lib().weed_fetch_neighbors_to(self.ctx, i, 1, nd.ctypes.data, dd.ctypes.data))
+            n = int(nd[0])
+            return nd[1:1 + n], dd[1:1 + n]
         if fetch:
             self.fetch_neighbors(i, 1)
         off = i * (1 + self.maxNeighbors)

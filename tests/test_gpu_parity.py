@@ -460,3 +460,52 @@ def test_device_side_boids_system_matches_host_tick():
             assert np.array_equal(bits(dev.col[k]), bits(host.col[k])), f"frame {frame} {k}"
     assert np.abs(dev.col["RB.ax"]).max() > 0
     dev.close(); host.close()
+
+
+def test_full_size_config4_16M_properties():
+    """BASELINE config 4 at its full size (16M entities, clustered, capped rows): sampled rows
+    against a brute-force float64 evaluation over ALL entities, plus frame invariants.  Rows are
+    fetched one at a time into scratch buffers (the full neighborData would be 8.3 GB)."""
+    cfg, cols = scenes.config4()
+    N, M = cfg["entityCount"], cfg["spatial"]["maxNeighbors"]
+    eng = make_engine(cfg, cols, host_neighbor_rows=False)
+    eng.spatial.update()
+    cs = cfg["spatial"]["cellSize"]
+    inv = 1.0 / cs
+    cols_n, rows_n = int(np.ceil(cfg["worldWidth"] / cs)), int(np.ceil(cfg["worldHeight"] / cs))
+    x = cols["T.x"].astype(np.float64)
+    y = cols["T.y"].astype(np.float64)
+    col = np.clip(np.trunc(x * inv).astype(np.int64), 0, cols_n - 1)
+    row = np.clip(np.trunc(y * inv).astype(np.int64), 0, rows_n - 1)
+    rng = np.random.default_rng(1)
+    dense = np.argsort(np.bincount(row * cols_n + col, minlength=rows_n * cols_n)[row * cols_n + col])[-8:]   # entities of the fullest cells
+    sample = np.concatenate([[0, N - 1], rng.integers(0, N, 30), dense])
+    capped = 0
+    for i in sample:
+        ids, d2 = eng.neighbors_of(int(i))
+        vr = float(cols["C.visualRange"][i])
+        cr = int(np.ceil(vr * inv))
+        c0, r0 = int(np.trunc(x[i] * inv)), int(np.trunc(y[i] * inv))
+        near = np.nonzero((np.abs(row - r0) <= cr) & (np.abs(col - c0) <= cr))[0]
+        dx, dy = x[near] - x[i], y[near] - y[i]
+        dist2 = dx * dx + dy * dy
+        ok = (dist2 < vr * vr) & (dist2 > 0)
+        cand, cd2 = near[ok], dist2[ok]
+        order = np.lexsort((cand, (row[cand] * cols_n + col[cand])))
+        cand, cd2 = cand[order][:M], cd2[order][:M]
+        assert np.array_equal(ids, cand.astype(np.int32)), f"row {i}"
+        assert np.array_equal(bits(d2), bits(cd2.astype(np.float32))), f"row {i} d2"
+        capped += len(ids) == M
+    assert capped > 0                                  # the fullest cells hit the cap
+    s = eng.stats()
+    assert s["activeInGrid"] == N and s["cappedRows"] > 0
+    eng.run(2)
+    eng.download(B.COLS_OUTPUT_ALL | B.COL_COLLISIONS)
+    c = eng.col
+    assert np.isfinite(c["T.x"]).all() and np.isfinite(c["T.y"]).all()
+    n = int(eng.collisionData[0])
+    assert n == eng.maxCollisionPairs                  # 2e7 pairs exist, the log is capped at 10000
+    pairs = eng.collisionData[1:1 + 2 * n].reshape(-1, 2)
+    assert (pairs[:, 0] < pairs[:, 1]).all() and (np.diff(pairs[:, 0]) >= 0).all()
+    assert (c["RB.ax"] == 0).all() and (c["RB.speed"] >= 0).all()
+    eng.close()
