@@ -48,6 +48,8 @@ KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "
 def workload(name, n_override=None):
     from multithreadedgameengine_b200 import scenes
     full = {"config3": 1_000_000, "config4": 16_000_000, "config5": 128_000_000}
+    if name == "config5":                 # 128M: build the columns frugally (float32 straight away)
+        n_override = n_override or full[name]
     if name in full:
         n = n_override or full[name]
         if n == full[name]:
@@ -304,19 +306,23 @@ def run_ours(args):
         xbytes = 0 if world == 1 else int(sum_over_ranks(obj.exchange_bytes_per_frame))
 
         # ---- per-kernel CUDA-event timing (direct launches; same frames, same state) ----------
-        obj_t, eng_t = make(B.FLAG_KERNEL_TIMING)
-        frames(obj_t, args.warmup + args.steps)
-        acc = np.zeros(8)
-        for _ in range(args.steps):
-            frames(obj_t, 1)
-            acc += np.array(eng_t.stats()["ms"][:8])
-        kms = acc / args.steps
-        kms[6] /= S                    # per LAUNCH of k_substep (the frame runs it S times)
-        st_t = eng_t.stats()
-        local_active = st_t["activeInGrid"]
-        kbar_t = st_t["neighborsTotal"] / max(1, local_active)
-        (obj_t.close if world > 1 else eng_t.close)()
-        top = int(np.argmax(kms))
+        if args.quick:
+            kms = np.full(8, np.nan)       # per-kernel split not measured in --quick runs
+            local_active, kbar_t = st["activeInGrid"], st["neighborsTotal"] / max(1, st["activeInGrid"])
+        else:
+            obj_t, eng_t = make(B.FLAG_KERNEL_TIMING)
+            frames(obj_t, args.warmup + args.steps)
+            acc = np.zeros(8)
+            for _ in range(args.steps):
+                frames(obj_t, 1)
+                acc += np.array(eng_t.stats()["ms"][:8])
+            kms = acc / args.steps
+            kms[6] /= S                    # per LAUNCH of k_substep (the frame runs it S times)
+            st_t = eng_t.stats()
+            local_active = st_t["activeInGrid"]
+            kbar_t = st_t["neighborsTotal"] / max(1, local_active)
+            (obj_t.close if world > 1 else eng_t.close)()
+        top = 4 if args.quick else int(np.argmax(kms))
         F, per_kernel = algorithmic_bytes(kbar_t, S)
         alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
                6: 34.0 + 4.0 * (1.0 + kbar_t), 7: 0.0}[top]
@@ -327,12 +333,14 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg * local_active / (kms[top] * 1e-3) / 1e9     # this rank's kernel over the entities it processes
+        if args.quick:                 # only the whole-frame figure is meaningful
+            achieved = F * owned_total * args.steps / (ms * 1e-3) / 1e9 / world
         frame_gbps = F * owned_total * args.steps / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "whole frame (per-kernel timing skipped: --quick)" if args.quick else KERNEL_NAMES[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak,
                     "traffic": TRAFFIC_FROM_NCU.get(KERNEL_NAMES[top]) if (world == 1 and name == "config4" and not args.entities) else None,
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                    "algorithmic_bytes_per_entity": alg, "kernel_ms": float(kms[top]), "entities_per_launch": int(local_active),
+                    "algorithmic_bytes_per_entity": alg, "kernel_ms": None if args.quick else float(kms[top]), "entities_per_launch": int(local_active),
                     "whole_frame": {"bytes_per_entity_frame": F, "achieved_GBps_all_gpus": frame_gbps,
                                     "frac_of_n_gpus_peak": frame_gbps / (peak * world)}}
 
@@ -345,18 +353,19 @@ def run_ours(args):
             if world > 1:
                 obj.exchange_dist()
 
-        for _ in range(min(3, args.warmup)):
+        e2e_steps = max(1, args.steps // 4) if args.quick else args.steps
+        for _ in range(1 if args.quick else min(3, args.warmup)):
             e2e_frame()
         barrier()
         t_wall = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             e2e_frame()
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t_wall) * 1e3)
         n_host = eng.totalEntityCount
-        e2e = {"value": owned_total * S * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+        e2e = {"value": owned_total * S * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(sum_over_ranks(8 * n_host)), "d2h_bytes_per_step": int(sum_over_ranks(24 * n_host)),
-               "ms_per_step": ms_e2e / args.steps,
+               "ms_per_step": ms_e2e / e2e_steps,
                "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"
                       + ("; + SlabEngine.exchange_dist per frame" if world > 1 else "")}
         launches = st["kernelLaunchesPerStep"] * args.steps + (3 * args.steps if world > 1 else 0)
@@ -371,7 +380,7 @@ def run_ours(args):
                      f"{world} row slabs (1 per GPU), halo {plan[1]} rows recomputed redundantly, 1 fixed-size NCCL neighbour exchange per frame, no host sync inside a frame",
                      "kbar": kbar, "active": active, "l2_policy": "working set >> 126 MB L2 (inputs larger than L2)"
                      if N / world > 2_000_000 else "per-GPU working set comparable to L2; frames run back-to-back on evolving state",
-                     "kernel_ms_rank0_per_launch": {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
+                     "kernel_ms_rank0_per_launch": None if args.quick else {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
                      "collision_pairs_last_substep": st["collisionPairs"],
                      "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes,
@@ -397,6 +406,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="entities of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
     ap.add_argument("--autobalance", type=int, default=2, help="measured-feedback slab re-plans before timing (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":

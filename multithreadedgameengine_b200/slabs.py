@@ -161,14 +161,14 @@ class SlabEngine:
             self.eng.column(k)[:len(sel)] = v[sel]
         self.eng.upload(B.COLS_INPUT_ALL)
         B.check(self.eng.ctx, B.lib().weed_slab_set_gids(self.eng.ctx, sel.ctypes.data, len(sel)))
-        # exchange quota: twice the start population of the widest boundary band of ANY cut (+ slack),
+        # exchange quota: 1.5x the start population of the widest boundary band of ANY cut (+ slack),
         # the same on every rank, because the two sides of a cut must agree on the message size;
         # every frame moves exactly (quota + 1) records per neighbour and direction
         hist = np.bincount(row[act & fin], minlength=self.rows)
         band = 0
         for (_, cut) in self.blocks[:-1]:
             band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
-        self.quota = 2 * band + 8192
+        self.quota = band + band // 2 + 8192
         dev = torch.device("cuda", device)
         mk = lambda: torch.zeros((self.quota + 1) * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
         self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
