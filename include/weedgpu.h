@@ -103,10 +103,7 @@ typedef struct weed_physics_config {
   double  gravityY;                   /* default 0                                     */
 } weed_physics_config;
 
-/* collision resolution order (DESIGN.md "J-order") */
-enum {
-  WEED_ORDER_JACOBI = 0   /* documented deterministic order of the GPU path            */
-};
+/* Collision resolution order: always the documented deterministic J-order. */
 
 enum {
   WEED_FLAG_NONE          = 0,
@@ -150,7 +147,10 @@ typedef struct weed_stats {
   uint32_t explicitPairs;        /* pairs routed through the explicit (asymmetric) path */
   uint32_t collisionPairs;       /* pairs found in the last substep (uncapped)          */
   uint32_t kernelLaunchesPerStep;
-  float    ms[12];               /* per-kernel ms of the last step (KERNEL_TIMING only) */
+  float    ms[12];               /* WEED_FLAG_KERNEL_TIMING: ms of the last frame's spans: 0 k_cell_key,
+                                    1 k_cell_scan, 2 k_scatter_ids, 3 k_build_slots+k_slot_prep, 4 k_neighbors,
+                                    5 k_capped_rescan+k_sort_lists, 6 all k_substep launches,
+                                    7 k_writeback+k_pair_scan+k_pair_emit                  */
 } weed_stats;
 
 typedef struct weed_ctx weed_ctx;

@@ -122,7 +122,10 @@ extern "C" void weed_default_config(weed_config* c) {
 // =============================================================================================
 // context
 // =============================================================================================
-enum KernelSlot { KS_KEY = 0, KS_SCAN, KS_SCATTER, KS_BUILD, KS_NEIGH, KS_XCAP, KS_SUBSTEP, KS_WB, KS_COUNT };
+// timed spans of one frame (WEED_FLAG_KERNEL_TIMING): ms[k] = ev[k] -> ev[k+1]
+//   0 k_cell_key, 1 k_cell_scan, 2 k_scatter_ids, 3 k_build_slots + k_slot_prep, 4 k_neighbors,
+//   5 k_capped_rescan + k_sort_lists, 6 all k_substep launches, 7 k_writeback + k_pair_scan + k_pair_emit
+static constexpr int kTimedSpans = 8;
 
 struct weed_ctx {
   weed_config cfg;
@@ -136,7 +139,6 @@ struct weed_ctx {
 
   // host buffers (owned by the caller)
   void* host[WEED_BUF_COUNT] = {};
-  size_t hostBytes[WEED_BUF_COUNT] = {};
   bool registered[WEED_BUF_COUNT] = {};
 
   std::vector<void*> allocs;
@@ -166,7 +168,7 @@ struct weed_ctx {
   cudaGraphExec_t frameGraph = nullptr;
   int graphSubSteps = -1;
   bool spatialValid = false;  // rows/slots of the current frame exist (weed_spatial ran)
-  cudaEvent_t ev[KS_COUNT + 8] = {};
+  cudaEvent_t ev[kTimedSpans + 1] = {};
   float ms[12] = {};
   uint32_t launchesPerStep = 0;
   // slabs
@@ -380,7 +382,6 @@ extern "C" int weed_bind(weed_ctx* ctx, weed_buffer_id id, void* host_base, size
     return fail(ctx, WEED_E_SIZE, "buffer " + std::to_string((int)id) + ": " + std::to_string(bytes) + " B < " + std::to_string(need) + " B");
   if (ctx->registered[id]) { cudaHostUnregister(ctx->host[id]); ctx->registered[id] = false; }
   ctx->host[id] = host_base;
-  ctx->hostBytes[id] = bytes;
   if (host_base && id <= WEED_BUF_COLLIDER) {
     // pin the SAB for the context lifetime so column copies are true async DMA; optional
     if (cudaHostRegister(host_base, need, cudaHostRegisterDefault) == cudaSuccess) ctx->registered[id] = true;
@@ -574,7 +575,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   }
   if (timing && frames) {
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < 8; k++) cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]);
+    for (int k = 0; k < kTimedSpans; k++) cudaEventElapsedTime(&ctx->ms[k], ctx->ev[k], ctx->ev[k + 1]);
   }
   ctx->spatialValid = false;
   return WEED_OK;
