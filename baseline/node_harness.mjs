@@ -28,7 +28,7 @@ const url = (rel) => pathToFileURL(path.join(refRoot, rel)).href;
 
 const workers = {};
 {
-  const { AbstractWorker } = await import(url("src/workers/AbstractWorker.js").replace(/^/, ""));
+  const { AbstractWorker } = await import(url("src/workers/AbstractWorker.js"));
   // capture the module-private singletons when they report ready (AbstractWorker.js:336-339)
   AbstractWorker.prototype.reportReady = function () { workers[this.constructor.name] = this; };
   AbstractWorker.prototype.reportLog = function () {};
