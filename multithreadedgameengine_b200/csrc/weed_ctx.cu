@@ -491,11 +491,17 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
-  const unsigned kb = blocks_for(g.N, K4_THREADS);
-  if (ctx->nd)
-    k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
-  else
-    k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+  // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
+  // short rows (the large synthetic worlds) -> one thread per entity with staged flush
+  if (g.M >= 256) {
+    const unsigned wb = blocks_for((size_t)g.N * 32, 256);
+    if (ctx->nd) k_neighbors_wide<true><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+    else         k_neighbors_wide<false><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+  } else {
+    const unsigned kb = blocks_for(g.N, K4_THREADS);
+    if (ctx->nd) k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+    else         k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+  }
   TIME_MARK(ctx, timing, 5);
   k_capped_rescan<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);

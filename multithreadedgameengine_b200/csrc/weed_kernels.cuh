@@ -471,6 +471,79 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   s.NCNT[e] = n;
 }
 
+// ---- K4 (wide variant): one WARP per entity -------------------------------------------------------
+// For scenes with long rows (maxNeighbors in the hundreds, windows of 25+ cells: the reference's
+// own demos) a thread per entity leaves the GPU mostly idle and serialises hundreds of candidates.
+// Here the 32 lanes test 32 consecutive candidates at a time; an ordered ballot compaction keeps
+// the reference's scan order and cap, and every accepting lane writes its own row words (they are
+// consecutive within the row, so the stores coalesce).
+template <bool WRITE_ROWS>
+__global__ void __launch_bounds__(256)
+k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
+                 float* __restrict__ dd, Counters* ctr) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= cellStart[g.cells]) return;
+  const uint32_t M = g.M;
+  const float2 q = s.QXY[e];
+  const float4 hi = s.SA[2 * (size_t)e + 1];
+  const float vr = hi.z;
+  const uint32_t id = __float_as_uint(hi.w);
+  const int4 win = s.WIN[e];
+  const uint32_t lid = s.SLID ? s.SLID[e] : id;
+  const double myX = q.x, myY = q.y;
+  const double vrSq = dmul((double)vr, (double)vr);
+  const float vrSqF = vr * vr * 1.00001f;
+  int32_t myCol, myRow;
+  cell_of(g, q.x, q.y, myCol, myRow);
+  const size_t rowBase = (size_t)lid * (1 + (size_t)M);
+  uint32_t n = 0;
+  for (int32_t row = win.x; row <= win.y && n < M && M > 0; row++) {
+    const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
+    const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+    for (uint32_t t0 = a; t0 < b && n < M; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      bool acc = false;
+      double d2 = 0;
+      if (t < b) {
+        const float2 c = s.QXY[t];
+        const float fx = c.x - q.x, fy = c.y - q.y;
+        if (!(__fmaf_rn(fx, fx, fy * fy) > vrSqF)) {
+          const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);   // :252-254
+          d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+          acc = d2 < vrSq && d2 > 0;                                              // :257, :249
+        }
+      }
+      const uint32_t bits = __ballot_sync(0xffffffffu, acc);
+      const uint32_t pos = n + __popc(bits & ((1u << lane) - 1));
+      if (acc && pos < M) {
+        const uint4 pw = s.PW[t];
+        const float vrT = __uint_as_float(pw.x);
+        bool back = (uint32_t)myRow >= (pw.z & 0xFFFFu) && (uint32_t)myRow <= (pw.z >> 16) &&
+                    (uint32_t)myCol >= (pw.w & 0xFFFFu) && (uint32_t)myCol <= (pw.w >> 16);
+        if (back && vrT != vr) back = d2 < dmul((double)vrT, (double)vrT);
+        const bool out = pw.y > id;
+        s.NST[(size_t)pos * g.Npad + e] = t | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
+        if (WRITE_ROWS) {
+          nd[rowBase + 1 + pos] = (int32_t)pw.y;        // :259
+          dd[rowBase + 1 + pos] = fround(d2);           // :260
+        }
+        if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
+      }
+      n = min(M, n + (uint32_t)__popc(bits));           // :264
+    }
+  }
+  if (lane == 0) {
+    if (WRITE_ROWS) { nd[rowBase] = (int32_t)n; dd[rowBase] = (float)n; }   // :274-275
+    if (n >= M && M > 0) {
+      reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+      ctr->anyCapped = 1;
+      s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
+    }
+    s.NCNT[e] = n;
+  }
+}
+
 // is slot `key` listed in the (ascending) internal row of entity k?  returns position or -1
 __device__ __forceinline__ int row_find(const GridDims& g, const BySlot& s, uint32_t k, uint32_t key) {
   int lo = 0, hi = (int)s.NCNT[k] - 1;
