@@ -493,7 +493,9 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   TIME_MARK(ctx, timing, 4);
   // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
   // short rows (the large synthetic worlds) -> one thread per entity with staged flush
-  if (g.M >= 256) {
+  const char* k4 = getenv("WEED_K4");   // diagnostic override: "wide" / "thread"
+  const bool wide = k4 ? (strcmp(k4, "wide") == 0) : (g.M >= 256);
+  if (wide) {
     const unsigned wb = blocks_for((size_t)g.N * 32, 256);
     if (ctx->nd) k_neighbors_wide<true><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
     else         k_neighbors_wide<false><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
