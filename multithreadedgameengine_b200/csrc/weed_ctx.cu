@@ -489,7 +489,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
     k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   else
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
-  k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart);
+  k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
   // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
   // short rows (the large synthetic worlds) -> one thread per entity with staged flush

@@ -6,10 +6,10 @@
 //   id order   k_build_slots   K3b stable position inside the cell (ascending id), Verlet
 //                                  integration (K5) + derived speed/angle fused, one 32 B
 //                                  slot record per entity (the only scattered write)
-//   slot order k_slot_prep     K3c query positions, scan windows, list heads (coalesced)
+//   slot order k_slot_prep     K3c query positions, scan windows, list heads, first bounds pass
 //   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
 //                                  warp-cooperative coalesced row flush
-//   slot order k_substep<LAST> K6  bounds + circle-circle correction, J-order
+//   slot order k_substep<LAST> K6  circle-circle correction, J-order (+ next sweep's bounds)
 //   id order   k_writeback     WB  gather results by id; per-tile outgoing pair counts
 //   tiles      k_pair_scan     K7a prefix of the tile counts, pair count
 //   id order   k_pair_emit     K7b collisionData emission by the tiles below the cap
@@ -290,6 +290,8 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   uint32_t keep = 0;
   if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
     keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & F_CAPPED;   // query position stays the pre-move one
+    // no k_slot_prep follows on this path: the first sweep's boundary pass happens here
+    if (INTEGRATE && moved && !clear_of_walls(g, dp.x, dp.y, at.y)) apply_bounds(g, p.boundaryElasticity, at.y, dp.x, dp.y, dp.z, dp.w);
   }
   s.SA[2 * (size_t)slot] = make_float4(dp.x, dp.y, at.y, __uint_as_float(f | keep | moved | owned | (cc << F_CC_SHIFT)));
   s.SA[2 * (size_t)slot + 1] = make_float4(dp.z, dp.w, at.z, __uint_as_float(gid));
@@ -297,13 +299,21 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
 
 // ---- K3c: coalesced slot-order pass: query positions, scan windows, list heads ----------------
 __global__ void __launch_bounds__(256)
-k_slot_prep(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart) {
+k_slot_prep(GridDims g, const Params* __restrict__ pp, BySlot s, const uint32_t* __restrict__ cellStart) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
-  const float4 lo = s.SA[2 * (size_t)e], hi = s.SA[2 * (size_t)e + 1];
+  float4 lo = s.SA[2 * (size_t)e], hi = s.SA[2 * (size_t)e + 1];
   const bool moved = (__float_as_uint(lo.w) & F_MOVED) != 0;     // integrated: px,py hold the pre-move position
   const float x0 = moved ? hi.x : lo.x, y0 = moved ? hi.y : lo.y;
   s.QXY[e] = make_float2(x0, y0);
+  // The boundary pass of the FIRST sweep (physics_worker.js:344-376) is applied here, once the
+  // query position is safe in QXY: every sweep then reads positions that already had their
+  // pass, and k_substep applies the NEXT sweep's pass to its own result before storing it.
+  if (moved && !clear_of_walls(g, lo.x, lo.y, lo.z)) {
+    apply_bounds(g, pp->boundaryElasticity, lo.z, lo.x, lo.y, hi.x, hi.y);
+    s.SA[2 * (size_t)e] = lo;
+    s.SA[2 * (size_t)e + 1] = hi;
+  }
   Window w;
   int4 wi = make_int4(1, 0, 1, 0);
   if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
@@ -659,9 +669,9 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
 }
 
 // ---- K6: one constraint substep (physics_worker.js:323-395, 405-568), J-order ---------------
-// Each entity applies its own boundary pass, then evaluates every pair of P it belongs to on
-// the start-of-sweep positions (partners' boundary pass re-applied on the fly) and
-// accumulates its own corrections in ascending partner-slot order, rounding to float32 after
+// Stored positions already had this sweep's boundary pass (k_slot_prep applies the first one,
+// each sweep applies the next one to its own result).  Each entity evaluates every pair of P it
+// belongs to on the start-of-sweep positions and accumulates its own corrections in ascending partner-slot order, rounding to float32 after
 // each one exactly like the reference's `x[i] += ...` on a Float32Array.
 //
 // Pair membership (P = {(i,j): i<j, j in row(i), both active colliders}), seen from entity e:
@@ -676,10 +686,9 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
 // exact binary64 pair code on the staged ones, in order.
 struct SubstepAcc { float x, y; uint32_t hits, outHits; };
 
-// partner position after ITS boundary pass
-__device__ __forceinline__ void partner_pos(const GridDims& g, float4 gt, float& xt, float& yt) {
+// partner position: stored positions already had the boundary pass of the sweep that reads them
+__device__ __forceinline__ void partner_pos(const GridDims&, float4 gt, float& xt, float& yt) {
   xt = gt.x; yt = gt.y;
-  if ((__float_as_uint(gt.w) & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, xt, yt, gt.z)) apply_bounds_pos(g, gt.z, xt, yt);
 }
 
 // float32 pre-filter of :455 (dist2 >= minDist^2): true = certainly no overlap
@@ -762,7 +771,6 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
   float x = gme.x, y = gme.y;
   const float r = gme.z;
   const uint32_t fw = __float_as_uint(gme.w);
-  if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, x, y, r)) apply_bounds(g, p.boundaryElasticity, r, x, y, pxy.x, pxy.y);
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e];
@@ -811,6 +819,9 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
     o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
     o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
   } else {
+    // boundary pass of the next sweep on my own result (:344-376)
+    if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
+      apply_bounds(g, p.boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
     Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
     s.PXY[e] = pxy;
   }
@@ -909,7 +920,6 @@ k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   const float4 gme = Glast[(size_t)slot * gs];
   float x = gme.x, y = gme.y;
   const uint32_t fw = __float_as_uint(gme.w);
-  if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL) apply_bounds_pos(g, gme.z, x, y);
   const uint32_t cnt = s.NCNT[slot];
   const uint32_t frame = ctr->frame;
   for (uint32_t k = 0; k < cnt && base < g.maxPairs; k++) {
