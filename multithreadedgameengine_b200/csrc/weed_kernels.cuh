@@ -199,6 +199,8 @@ struct ById {
 struct BySlot {
   float4* SA;        // slot record: SA[2s] = (x, y, radius, flagword), SA[2s+1] = (px, py, visualRange, id bits)
   float2* QXY;       // position at grid-build time (query position)
+  float4* CXY;       // candidate record of the thread-per-entity scan: query x, y, visualRange, id bits;
+                     // bit 31 of the id word = "centre cell outside the grid" (CX_EDGE)
   int4* WIN;         // clamped scan window of the entity: r0, r1, c0, c1 (r0 > r1: no scan)
   uint4* PW;         // what a neighbour needs about me in one 16 B gather: visualRange bits, id,
                      // r0 | r1 << 16, c0 | c1 << 16 (grid dimensions are limited to 65535)
@@ -320,6 +322,12 @@ k_slot_prep(GridDims g, const Params* __restrict__ pp, BySlot s, const uint32_t*
   s.WIN[e] = wi;
   s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
                        (uint32_t)wi.z | ((uint32_t)wi.w << 16));
+  // CX_EDGE clear: my unclamped centre cell is my (clamped) grid cell and trunc == floor.  Two
+  // such entities with the same visualRange that pass 0 < d2 < vr^2 always lie in each other's
+  // window: |x_a - x_b| < vr  =>  |floor(x_a inv) - floor(x_b inv)| <= ceil(vr inv).
+  const int32_t ucol = js_toint32(dmul((double)x0, g.inv)), urow = js_toint32(dmul((double)y0, g.inv));
+  const bool inside = x0 >= 0.f && y0 >= 0.f && ucol >= 0 && ucol < g.cols && urow >= 0 && urow < g.rows;
+  s.CXY[e] = make_float4(x0, y0, hi.z, __uint_as_float(__float_as_uint(hi.w) | (inside ? 0u : CX_EDGE)));
   s.XHEAD[e] = 0;
 }
 
@@ -365,12 +373,12 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   const bool live = e < A;
   float2 q = make_float2(0.f, 0.f);
   float vr = 0.f;
-  uint32_t id = 0;
+  uint32_t id = 0, edge = CX_EDGE;
   int4 win = make_int4(1, 0, 1, 0);
   if (live) {
-    q = s.QXY[e];
-    const float4 hi = s.SA[2 * (size_t)e + 1];
-    vr = hi.z; id = __float_as_uint(hi.w);
+    const float4 me = s.CXY[e];
+    q = make_float2(me.x, me.y);
+    vr = me.z; id = __float_as_uint(me.w) & ~CX_EDGE; edge = __float_as_uint(me.w) & CX_EDGE;
     win = s.WIN[e];
   }
   const uint32_t lid = (live && s.SLID) ? s.SLID[e] : id;    // row address: local index
@@ -378,6 +386,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
   const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf compare false)
+  const uint32_t vrBits = __float_as_uint(vr);
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
   const size_t rowBase = (size_t)lid * (1 + (size_t)M);
@@ -390,7 +399,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   }
   do {
     // ---- phase 1: scan -----------------------------------------------------------------------
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, slow = 0;
     while (!done && cnt < K4_CH) {
       if (t >= b) {
         if (++row > win.y) { done = true; break; }
@@ -398,53 +407,56 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
         b = cellStart[(uint32_t)row * g.cols + win.w + 1];
         continue;
       }
-      // four candidate positions in flight (consecutive slots), then decide one by one
+      // four candidate records in flight (consecutive slots), then decide one by one
       const uint32_t m = min(4u, b - t);
-      float2 cand[4];
+      float4 cand[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) cand[u] = s.QXY[min(t + (uint32_t)u, b - 1)];
+      for (int u = 0; u < 4; u++) cand[u] = s.CXY[min(t + (uint32_t)u, b - 1)];
       uint32_t used = m;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if ((uint32_t)u >= used) break;
-        const float2 c = cand[u];
+        const float4 c = cand[u];
         const float fx = c.x - q.x, fy = c.y - q.y;
         if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;   // certainly d2 >= vr2
         const double dX = dsub((double)c.x, myX);           // :252-254
         const double dY = dsub((double)c.y, myY);
         const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
         if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
-        myW[cnt] = t + (uint32_t)u;
+        // Would the partner's own scan accept me (ignoring its cap)?  Same visualRange and both
+        // centre cells inside the grid: yes (see k_slot_prep).  Anything else: phase 2 looks.
+        const uint32_t jw = __float_as_uint(c.w);
+        const uint32_t jid = jw & ~CX_EDGE;
+        const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
+        myW[cnt] = (t + (uint32_t)u) | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
+        myId[cnt] = jid;
         myD2[cnt] = fround(d2);
+        if (!sure) slow |= 1u << cnt;
         cnt++;
         if (++n >= M) { done = true; used = (uint32_t)u + 1; }          // :264
         else if (cnt == K4_CH) used = (uint32_t)u + 1;
       }
       t += used;
     }
-    // ---- phase 2: partner attributes of the staged entries -------------------------------------
+    // ---- phase 2: staged entries whose partner differs in visualRange or sits on the rim ---------
     const uint32_t first = n - cnt;                       // row position of my first staged entry
-    for (uint32_t k = 0; k < cnt; k++) {
-      const uint32_t tc = myW[k];
-      const uint4 pw = s.PW[tc];
-      const uint32_t jid = pw.y;
-      const float vrT = __uint_as_float(pw.x);
-      // would partner tc's own scan accept me (ignoring its cap)?  d2 is bitwise symmetric and
-      // d2 > 0 holds; with equal visual ranges d2 < vr_t^2 is the predicate that just passed.
+    while (slow) {
+      const uint32_t k = (uint32_t)__ffs(slow) - 1u;
+      slow &= slow - 1u;
+      const uint32_t wd = myW[k];
+      const uint32_t tc = wd & NS_SLOT_MASK;
+      const float4 c = s.CXY[tc];
+      const int4 wt = s.WIN[tc];
       // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
-      bool back = (uint32_t)myRow >= (pw.z & 0xFFFFu) && (uint32_t)myRow <= (pw.z >> 16) &&
-                  (uint32_t)myCol >= (pw.w & 0xFFFFu) && (uint32_t)myCol <= (pw.w >> 16);
-      if (back && vrT != vr) {
-        const float2 c = s.QXY[tc];
+      bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+      if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
         const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
         const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        back = d2 < dmul((double)vrT, (double)vrT);
+        back = d2 < dmul((double)c.z, (double)c.z);
       }
-      const bool out = jid > id;
-      myW[k] = tc | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
-      myId[k] = jid;
+      if (back) myW[k] = wd | NS_BACK;
       // pair (id, jid) is in P but the partner cannot infer it from its own row
-      if (out && !back) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
+      else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
     }
     __syncwarp();
     // ---- warp-cooperative flush -------------------------------------------------------------
