@@ -242,6 +242,60 @@ typedef struct weed_boids_params {
 int weed_system_boids(weed_ctx* ctx, const weed_boids_params* params, const float* protectedRange,
                       double dtRatio);
 
+/* ---- collision Enter / Stay / Exit ------------------------------------------
+ * Replaces the bookkeeping of LogicWorker.processCollisionCallbacks (src/workers/
+ * logic_worker.js:429-526): the pair list the last weed_physics / weed_step left in
+ * collisionData is compared ON THE DEVICE with the list of the previous call.
+ *   state[k], k < pairs : 1 = the pair k of collisionData is new (onCollisionEnter, :471-480),
+ *                         2 = it was there last time (onCollisionStay, :481-489)
+ *   exitData[0]         : number of ended pairs; then (a, b) couples in the ORDER of the
+ *                         previous frame's list, which is the reference's Set iteration order
+ *                         (:493-516).  Each ended pair is listed once; the reference fires
+ *                         its Exit callbacks twice (once per Cantor key), see INTEGRATION.md.
+ * Pairs are compared as exact 64-bit (a, b) keys; the reference's Cantor keys (:417-421) are
+ * doubles and alias above ~2^26 ids.  state has room for maxCollisionPairs bytes, exitData
+ * for 1 + 2 * maxCollisionPairs int32; either may be NULL.  Call once per frame.            */
+#define WEED_EVENTS_FORGET_PREVIOUS 1u   /* start from an empty previous set (scene reload)   */
+typedef struct weed_collision_event_counts {
+  uint32_t pairs, entered, stayed, exited;
+} weed_collision_event_counts;
+int weed_system_collision_events(weed_ctx* ctx, uint32_t flags, weed_collision_event_counts* counts,
+                                 uint8_t* state, int32_t* exitData);
+
+/* ---- screen visibility and shadow sprites -----------------------------------
+ * weed_system_screen_visibility restates ParticleWorker.updateEntityScreenVisibility
+ * (src/workers/particle_worker.js:1012-1062): SpriteRenderer.screenX / screenY /
+ * isItOnScreen of every Transform.active entity from the device-resident positions; entries of
+ * inactive entities keep their previous values.  Host arrays (entityCount each) may be NULL:
+ * the device copies stay for weed_system_shadows.                                           */
+typedef struct weed_camera {
+  double zoom, cameraX, cameraY;     /* cameraData[0..2], particle_worker.js:1029-1031 */
+  double canvasWidth, canvasHeight;  /* :1036-1041 (15 % margin on each side)          */
+} weed_camera;
+int weed_system_screen_visibility(weed_ctx* ctx, const weed_camera* cam, float* screenX, float* screenY,
+                                  uint8_t* isItOnScreen);
+/* weed_system_shadows restates ParticleWorker.updateShadowSprites (particle_worker.js:861-1003):
+ * lights in id order (LightEmitter.active, Transform.active, on screen, intensity > 0; at most
+ * maxShadowCastingLights), each walking its neighbor row in order for ShadowCaster entities,
+ * at most maxShadowsPerLight each and maxShadowSprites in all; unused sprite slots get
+ * active = 0.  The five component columns are uploaded once with weed_system_shadows_upload
+ * (again when they change); isItOnScreen is the one weed_system_screen_visibility left on the
+ * device; neighbor rows are the ones of the last weed_spatial / weed_step.                  */
+typedef struct weed_shadow_columns {
+  const uint8_t* lightActive;     /* LightEmitter.active            */
+  const float* lightIntensity;    /* LightEmitter.lightIntensity    */
+  const uint8_t* casterActive;    /* ShadowCaster.active            */
+  const float* shadowRadius;      /* ShadowCaster.shadowRadius      */
+  const float* height;            /* ShadowCaster.height            */
+} weed_shadow_columns;
+typedef struct weed_shadow_sprites {  /* host arrays of maxShadowSprites elements, any may be NULL */
+  uint8_t* active;
+  float *radius, *x, *y, *rotation, *scaleX, *scaleY, *alpha;
+} weed_shadow_sprites;
+int weed_system_shadows_upload(weed_ctx* ctx, const weed_shadow_columns* cols);
+int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLights, uint32_t maxShadowsPerLight,
+                        uint32_t maxShadowSprites, const weed_shadow_sprites* out, uint32_t* spriteCount);
+
 /* ---- multi-GPU slabs (SURVEY §8 e) ----------------------------------------
  * A slab context (slabRowEnd > 0) holds a LOCAL entity table of `entityCount` slots; every
  * slot carries a global entity id.  Component buffers, neighbor rows and column masks are

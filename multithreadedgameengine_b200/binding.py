@@ -64,6 +64,22 @@ class BoidsParams(C.Structure):
                 ("turnFactor", C.c_double), ("margin", C.c_double), ("mouseEntityType", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class CollisionEventCounts(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("pairs", "entered", "stayed", "exited")]
+
+
+class Camera(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("zoom", "cameraX", "cameraY", "canvasWidth", "canvasHeight")]
+
+
+class ShadowColumns(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("lightActive", "lightIntensity", "casterActive", "shadowRadius", "height")]
+
+
+class ShadowSprites(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("active", "radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha")]
+
+
 class SlabStats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("top", "capacity", "owned", "sentLow", "sentHigh", "receivedLow",
                                            "receivedHigh", "overflow")]
@@ -102,6 +118,10 @@ SYMBOLS = {
     "weed_last_error": (C.c_char_p, [C.c_void_p]),
     "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "weed_system_boids": (C.c_int, [C.c_void_p, C.POINTER(BoidsParams), C.c_void_p, C.c_double]),
+    "weed_system_collision_events": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CollisionEventCounts), C.c_void_p, C.c_void_p]),
+    "weed_system_screen_visibility": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "weed_system_shadows_upload": (C.c_int, [C.c_void_p, C.POINTER(ShadowColumns)]),
+    "weed_system_shadows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShadowSprites), C.POINTER(C.c_uint32)]),
     "weed_slab_set_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -109,6 +129,8 @@ SYMBOLS = {
     "weed_slab_status": (C.c_int, [C.c_void_p, C.POINTER(SlabStats)]),
 }
 SLAB_RECORD_BYTES = 64
+EVENTS_FORGET_PREVIOUS = 1
+COLLISION_ENTER, COLLISION_STAY, COLLISION_EXIT = 1, 2, 3
 
 _LIB = None
 

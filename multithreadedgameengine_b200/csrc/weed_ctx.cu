@@ -14,6 +14,7 @@
 
 #include "../../include/weedgpu.h"
 #include "weed_kernels.cuh"
+#include "weed_systems.cuh"
 
 using namespace weed;
 
@@ -171,6 +172,16 @@ struct weed_ctx {
   cudaEvent_t ev[kTimedSpans + 1] = {};
   float ms[12] = {};
   uint32_t launchesPerStep = 0;
+  // device-side systems (allocated on first use)
+  unsigned long long *evTable[2] = {}, *evList[2] = {};
+  uint32_t evMask = 0, evCur = 0;
+  uint8_t* evState = nullptr; int32_t* evExit = nullptr; EvCounters* dEv = nullptr;
+  uint32_t *sysTileCount = nullptr, *sysTilePrefix = nullptr; size_t sysTiles = 0;
+  float *screenX = nullptr, *screenY = nullptr; uint8_t* onScreen = nullptr;
+  uint8_t *shLightActive = nullptr, *shCasterActive = nullptr;
+  float *shIntensity = nullptr, *shRadius = nullptr, *shHeight = nullptr;
+  uint32_t *shLightId = nullptr, *shLightCount = nullptr, *shScalars = nullptr;
+  uint8_t* shOutActive = nullptr; float* shOut = nullptr; uint32_t shOutCap = 0, shLightCap = 0;
   // slabs
   bool slab = false;
   uint32_t* holes = nullptr;
@@ -802,5 +813,156 @@ extern "C" int weed_system_boids(weed_ctx* ctx, const weed_boids_params* p, cons
                                                               protectedRange ? ctx->protRange : nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+// tile scratch shared by the ordered-compaction passes of the systems
+static int sys_tiles(weed_ctx* ctx, size_t elements) {
+  const size_t tiles = (elements + SYS_TILE - 1) / SYS_TILE + 1;
+  if (tiles <= ctx->sysTiles) return WEED_OK;
+  int rc = dalloc(ctx, &ctx->sysTileCount, tiles); if (rc) return rc;
+  rc = dalloc(ctx, &ctx->sysTilePrefix, tiles); if (rc) return rc;
+  ctx->sysTiles = tiles;
+  return WEED_OK;
+}
+
+extern "C" int weed_system_collision_events(weed_ctx* ctx, uint32_t flags, weed_collision_event_counts* counts,
+                                            uint8_t* state, int32_t* exitData) {
+  GUARD(ctx);
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "systems are not available on slab contexts yet");
+  const size_t maxPairs = ctx->g.maxPairs;
+  cudaStream_t st = ctx->stream;
+  if (!ctx->dEv) {
+    size_t cap = 1024;
+    while (cap < 2 * maxPairs) cap <<= 1;
+    if (cap > (1ull << 31)) return fail(ctx, WEED_E_INVALID, "maxCollisionPairs too large for the event tables");
+    ctx->evMask = (uint32_t)(cap - 1);
+    for (int t = 0; t < 2; t++) {
+      int rc = dalloc(ctx, &ctx->evTable[t], cap, false); if (rc) return rc;
+      rc = dalloc(ctx, &ctx->evList[t], maxPairs); if (rc) return rc;
+    }
+    int rc = dalloc(ctx, &ctx->evState, maxPairs); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->evExit, 1 + 2 * maxPairs); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->dEv, 1); if (rc) return rc;
+    rc = sys_tiles(ctx, maxPairs); if (rc) return rc;
+    ctx->evCur = 0;
+  }
+  const uint32_t cur = ctx->evCur, prev = cur ^ 1u;
+  const size_t cap = (size_t)ctx->evMask + 1;
+  const unsigned blocks = (unsigned)((maxPairs + SYS_TILE - 1) / SYS_TILE);
+  CK(cudaMemsetAsync(ctx->evTable[cur], 0xFF, cap * 8, st));
+  k_ev_begin<<<1, 32, 0, st>>>(ctx->coll, ctx->dEv, flags & WEED_EVENTS_FORGET_PREVIOUS);
+  if (blocks) {
+    k_ev_insert<<<blocks, SYS_TILE, 0, st>>>(ctx->coll, ctx->evTable[cur], ctx->evMask, ctx->evList[cur], ctx->dEv);
+    k_ev_classify<<<blocks, SYS_TILE, 0, st>>>(ctx->evList[cur], ctx->evTable[cur], ctx->evList[prev], ctx->evTable[prev],
+                                               ctx->evMask, ctx->evState, ctx->sysTileCount, ctx->dEv);
+    k_tile_scan<<<1, 1024, 0, st>>>(ctx->sysTileCount, ctx->sysTilePrefix, blocks, &ctx->dEv->exit);
+    k_ev_exits<<<blocks, SYS_TILE, 0, st>>>(ctx->evTable[cur], ctx->evList[prev], ctx->evMask, ctx->sysTilePrefix,
+                                            ctx->evExit, ctx->dEv);
+  }
+  EvCounters ec;
+  CK(cudaMemcpyAsync(&ec, ctx->dEv, sizeof(ec), cudaMemcpyDeviceToHost, st));
+  k_ev_end<<<1, 32, 0, st>>>(ctx->dEv, ctx->evExit);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  ctx->evCur = prev;
+  if (counts) { counts->pairs = ec.cur; counts->entered = ec.enter; counts->stayed = ec.stay; counts->exited = ec.exit; }
+  if (state && ec.cur) CK(cudaMemcpyAsync(state, ctx->evState, ec.cur, cudaMemcpyDeviceToHost, st));
+  if (exitData) {
+    exitData[0] = (int32_t)ec.exit;
+    if (ec.exit) CK(cudaMemcpyAsync(exitData + 1, ctx->evExit + 1, (size_t)ec.exit * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return WEED_OK;
+}
+
+extern "C" int weed_system_screen_visibility(weed_ctx* ctx, const weed_camera* cam, float* screenX, float* screenY,
+                                             uint8_t* isItOnScreen) {
+  GUARD(ctx);
+  if (!cam) return WEED_E_INVALID;
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "systems are not available on slab contexts yet");
+  const size_t N = ctx->g.N;
+  cudaStream_t st = ctx->stream;
+  if (!ctx->onScreen) {
+    int rc = dalloc(ctx, &ctx->screenX, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->screenY, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->onScreen, N); if (rc) return rc;
+  }
+  CameraParams c{cam->zoom, cam->cameraX, cam->cameraY, cam->canvasWidth, cam->canvasHeight};
+  k_screen_visibility<<<blocks_for(N, 256), 256, 0, st>>>((uint32_t)N, c, ctx->d.DP, ctx->d.F, ctx->screenX, ctx->screenY, ctx->onScreen);
+  CK(cudaGetLastError());
+  if (screenX) CK(cudaMemcpyAsync(screenX, ctx->screenX, N * 4, cudaMemcpyDeviceToHost, st));
+  if (screenY) CK(cudaMemcpyAsync(screenY, ctx->screenY, N * 4, cudaMemcpyDeviceToHost, st));
+  if (isItOnScreen) CK(cudaMemcpyAsync(isItOnScreen, ctx->onScreen, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return WEED_OK;
+}
+
+extern "C" int weed_system_shadows_upload(weed_ctx* ctx, const weed_shadow_columns* cols) {
+  GUARD(ctx);
+  if (!cols || !cols->lightActive || !cols->lightIntensity || !cols->casterActive || !cols->shadowRadius || !cols->height)
+    return WEED_E_INVALID;
+  const size_t N = ctx->g.N;
+  if (!ctx->shLightActive) {
+    int rc = dalloc(ctx, &ctx->shLightActive, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shCasterActive, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shIntensity, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shRadius, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shHeight, N); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shScalars, 4); if (rc) return rc;
+  }
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->shLightActive, cols->lightActive, N, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->shCasterActive, cols->casterActive, N, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->shIntensity, cols->lightIntensity, N * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->shRadius, cols->shadowRadius, N * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->shHeight, cols->height, N * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return WEED_OK;
+}
+
+extern "C" int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLights, uint32_t maxShadowsPerLight,
+                                   uint32_t maxShadowSprites, const weed_shadow_sprites* out, uint32_t* spriteCount) {
+  GUARD(ctx);
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "systems are not available on slab contexts yet");
+  if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
+  if (!ctx->shLightActive) return fail(ctx, WEED_E_STATE, "weed_system_shadows_upload has not been called");
+  if (!ctx->onScreen) return fail(ctx, WEED_E_STATE, "weed_system_screen_visibility has not been called");
+  const size_t N = ctx->g.N;
+  cudaStream_t st = ctx->stream;
+  if (maxShadowSprites > ctx->shOutCap) {
+    int rc = dalloc(ctx, &ctx->shOutActive, maxShadowSprites); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shOut, 7 * (size_t)maxShadowSprites); if (rc) return rc;
+    ctx->shOutCap = maxShadowSprites;
+  }
+  if (maxShadowCastingLights > ctx->shLightCap) {
+    int rc = dalloc(ctx, &ctx->shLightId, maxShadowCastingLights); if (rc) return rc;
+    rc = dalloc(ctx, &ctx->shLightCount, maxShadowCastingLights); if (rc) return rc;
+    ctx->shLightCap = maxShadowCastingLights;
+  }
+  int rc = sys_tiles(ctx, N); if (rc) return rc;
+  ShadowParams p{maxShadowCastingLights, maxShadowsPerLight, maxShadowSprites, (uint32_t)ctx->g.M};
+  ShadowIn in{ctx->shLightActive, ctx->shIntensity, ctx->shCasterActive, ctx->shRadius, ctx->shHeight, ctx->onScreen};
+  const size_t S = maxShadowSprites;
+  ShadowOut o{ctx->shOutActive, ctx->shOut, ctx->shOut + S, ctx->shOut + 2 * S, ctx->shOut + 3 * S,
+              ctx->shOut + 4 * S, ctx->shOut + 5 * S, ctx->shOut + 6 * S};
+  const unsigned blocks = (unsigned)((N + SYS_TILE - 1) / SYS_TILE);
+  k_shadow_lights<<<blocks, SYS_TILE, 0, st>>>((uint32_t)N, in, ctx->d.F, ctx->sysTileCount);
+  k_tile_scan<<<1, 1024, 0, st>>>(ctx->sysTileCount, ctx->sysTilePrefix, blocks, ctx->shScalars);
+  k_shadow_count<<<blocks, SYS_TILE, 0, st>>>((uint32_t)N, p, in, ctx->d.F, ctx->sysTilePrefix, ctx->nd, ctx->dd,
+                                              ctx->shLightId, ctx->shLightCount);
+  k_shadow_emit<<<1, 256, 0, st>>>(p, in, ctx->d.F, ctx->d.DP, ctx->shScalars, ctx->nd, ctx->dd, ctx->shLightId,
+                                   ctx->shLightCount, o, ctx->shScalars + 1);
+  CK(cudaGetLastError());
+  uint32_t n = 0;
+  CK(cudaMemcpyAsync(&n, ctx->shScalars + 1, 4, cudaMemcpyDeviceToHost, st));
+  if (out && S) {
+    float* const dst[7] = {out->radius, out->x, out->y, out->rotation, out->scaleX, out->scaleY, out->alpha};
+    if (out->active) CK(cudaMemcpyAsync(out->active, ctx->shOutActive, S, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < 7; k++)
+      if (dst[k]) CK(cudaMemcpyAsync(dst[k], ctx->shOut + k * S, S * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  if (spriteCount) *spriteCount = n;
   return WEED_OK;
 }

@@ -204,6 +204,80 @@ class GameEngine:
             ptr = self._prot.ctypes.data
         B.check(self.ctx, B.lib().weed_system_boids(self.ctx, C.byref(p), ptr, float(dtRatio)))
 
+    # ---- device-side consumers of collisionData / positions / rows ----------
+    def collision_events(self, forget_previous=False):
+        """Enter / Stay / Exit diff of this frame's collisionData against the previous call's
+        (logic_worker.js:429-526), computed on the device (weed_system_collision_events).
+        Returns {"pairs": int32[n,2], "state": uint8[n] (1 Enter, 2 Stay), "exits": int32[m,2]}."""
+        maxPairs = self.maxCollisionPairs
+        if not hasattr(self, "_ev_state"):
+            self._ev_state = np.zeros(max(1, maxPairs), np.uint8)
+            self._ev_exit = np.zeros(1 + 2 * maxPairs, np.int32)
+        c = B.CollisionEventCounts()
+        B.check(self.ctx, B.lib().weed_system_collision_events(
+            self.ctx, B.EVENTS_FORGET_PREVIOUS if forget_previous else 0, C.byref(c),
+            self._ev_state.ctypes.data, self._ev_exit.ctypes.data))
+        self.download(B.COL_COLLISIONS)
+        n = int(self.collisionData[0])
+        assert n == c.pairs
+        return {"pairs": self.collisionData[1:1 + 2 * n].reshape(n, 2).copy(),
+                "state": self._ev_state[:n].copy(),
+                "exits": self._ev_exit[1:1 + 2 * c.exited].reshape(c.exited, 2).copy(),
+                "entered": c.entered, "stayed": c.stayed, "exited": c.exited}
+
+    @staticmethod
+    def collision_callbacks(ev):
+        """The reference's callback sequence for one frame as (type, self, other) triples:
+        both objects of every current pair in list order (logic_worker.js:471-489), then the
+        Exit calls — which the reference issues once per Cantor key of an ended pair, i.e.
+        (A,B),(B,A) for keyAB and (B,A),(A,B) for keyBA (:493-516)."""
+        calls = []
+        for (a, b), st in zip(ev["pairs"].tolist(), ev["state"].tolist()):
+            calls.append((st, a, b))
+            calls.append((st, b, a))
+        for a, b in ev["exits"].tolist():
+            calls += [(B.COLLISION_EXIT, a, b), (B.COLLISION_EXIT, b, a), (B.COLLISION_EXIT, b, a), (B.COLLISION_EXIT, a, b)]
+        return calls
+
+    def screen_visibility(self, zoom, cameraX, cameraY, canvasWidth, canvasHeight, download=True):
+        """particle_worker.js:1012-1062 on the device (weed_system_screen_visibility).  Returns
+        (screenX, screenY, isItOnScreen) host arrays (persistent across calls, like the SAB)."""
+        cam = B.Camera(float(zoom), float(cameraX), float(cameraY), float(canvasWidth), float(canvasHeight))
+        if not hasattr(self, "_screenX"):
+            N = self.totalEntityCount
+            self._screenX = np.zeros(N, np.float32)
+            self._screenY = np.zeros(N, np.float32)
+            self._onScreen = np.zeros(N, np.uint8)
+        ptrs = (self._screenX.ctypes.data, self._screenY.ctypes.data, self._onScreen.ctypes.data) if download else (None, None, None)
+        B.check(self.ctx, B.lib().weed_system_screen_visibility(self.ctx, C.byref(cam), *ptrs))
+        return self._screenX, self._screenY, self._onScreen
+
+    def shadows_upload(self, lightActive, lightIntensity, casterActive, shadowRadius, height):
+        """LightEmitter / ShadowCaster columns the shadow system reads (weed_system_shadows_upload)."""
+        N = self.totalEntityCount
+        self._sh_cols = [np.ascontiguousarray(lightActive, np.uint8), np.ascontiguousarray(lightIntensity, np.float32),
+                         np.ascontiguousarray(casterActive, np.uint8), np.ascontiguousarray(shadowRadius, np.float32),
+                         np.ascontiguousarray(height, np.float32)]
+        assert all(a.shape == (N,) for a in self._sh_cols)
+        cols = B.ShadowColumns(*[a.ctypes.data for a in self._sh_cols])
+        B.check(self.ctx, B.lib().weed_system_shadows_upload(self.ctx, C.byref(cols)))
+
+    def shadows(self, maxShadowCastingLights=20, maxShadowsPerLight=15, maxShadowSprites=None):
+        """particle_worker.js:861-1003 on the device (weed_system_shadows).  Defaults as
+        gameEngine.js:148-151.  Returns a dict of the eight shadow-sprite arrays + "count"."""
+        if maxShadowSprites is None:
+            maxShadowSprites = maxShadowCastingLights * maxShadowsPerLight
+        S = int(maxShadowSprites)
+        out = {"active": np.zeros(S, np.uint8)}
+        for k in ("radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha"):
+            out[k] = np.zeros(S, np.float32)
+        sp = B.ShadowSprites(*[out[k].ctypes.data for k in ("active", "radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha")])
+        n = C.c_uint32(0)
+        B.check(self.ctx, B.lib().weed_system_shadows(self.ctx, int(maxShadowCastingLights), int(maxShadowsPerLight), S,
+                                                      C.byref(sp), C.byref(n)))
+        out["count"] = int(n.value)
+        return out
+
     def updatePhysicsConfig(self, partial):
         """gameEngine.js:1304-1325 -> applyPhysicsConfig + validatePhysicsConfig."""
         phys = self.config["physics"]

@@ -26,9 +26,10 @@ COLS = {  # key -> (component id, schema name, dtype)
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libweedoracle.so")
     src = os.path.join(_HERE, "weed_oracle.c")
+    src2 = os.path.join(_HERE, "weed_oracle_systems.c")
     hdr = os.path.join(_HERE, "..", "include", "weed_nudge.h")
     stale = (not os.path.exists(so)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, src2, hdr))
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libweedoracle.so"])
     return so
@@ -61,8 +62,64 @@ def lib():
         L.wo_nudge_dir.argtypes = [C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.wo_nudge_hash.restype = C.c_uint32
         L.wo_nudge_hash.argtypes = [C.c_uint32] * 5
+        L.wo_events_create.restype = C.c_void_p
+        L.wo_events_destroy.argtypes = [C.c_void_p]
+        L.wo_events_process.restype = C.c_int64
+        L.wo_events_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.wo_screen_visibility.argtypes = [C.c_int32] + [C.c_void_p] * 3 + [C.c_double] * 5 + [C.c_void_p] * 3
+        L.wo_shadow_sprites.restype = C.c_int32
+        L.wo_shadow_sprites.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 3 + [C.c_void_p] * 8
         _LIB = L
     return _LIB
+
+
+class CollisionEventsC:
+    """LogicWorker.processCollisionCallbacks (logic_worker.js:429-526), one logic worker."""
+
+    def __init__(self):
+        self.h = lib().wo_events_create()
+
+    def process(self, collisionData):
+        cd = np.ascontiguousarray(collisionData, np.int32)
+        cap = 8 * int(cd[0]) + 8 * getattr(self, "_last", 0) + 16
+        calls = np.zeros(3 * cap, np.int32)
+        n = lib().wo_events_process(self.h, cd.ctypes.data, calls.ctypes.data, cap)
+        assert n <= cap
+        self._last = int(cd[0])
+        return [tuple(t) for t in calls[:3 * n].reshape(n, 3).tolist()]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().wo_events_destroy(self.h)
+            self.h = None
+
+
+def screen_visibility_c(active, x, y, zoom, cameraX, cameraY, canvasWidth, canvasHeight, screenX, screenY, isItOnScreen):
+    """particle_worker.js:1012-1062; the three output arrays are updated in place."""
+    active = np.ascontiguousarray(active, np.uint8); x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    lib().wo_screen_visibility(len(active), active.ctypes.data, x.ctypes.data, y.ctypes.data, float(zoom), float(cameraX),
+                               float(cameraY), float(canvasWidth), float(canvasHeight), screenX.ctypes.data,
+                               screenY.ctypes.data, isItOnScreen.ctypes.data)
+
+
+def shadow_sprites_c(maxNeighbors, neighborData, distanceData, transformActive, worldX, worldY, lightEnabled, lightIntensity,
+                     shadowCasterActive, shadowRadius, shadowHeight, isOnScreen, maxLights=20, perLight=15, maxSprites=None):
+    """particle_worker.js:861-1003.  Returns the dict of shadow-sprite arrays + "count"."""
+    if maxSprites is None:
+        maxSprites = maxLights * perLight
+    ins = [np.ascontiguousarray(neighborData, np.int32), np.ascontiguousarray(distanceData, np.float32),
+           np.ascontiguousarray(transformActive, np.uint8), np.ascontiguousarray(worldX, np.float32),
+           np.ascontiguousarray(worldY, np.float32), np.ascontiguousarray(lightEnabled, np.uint8),
+           np.ascontiguousarray(lightIntensity, np.float32), np.ascontiguousarray(shadowCasterActive, np.uint8),
+           np.ascontiguousarray(shadowRadius, np.float32), np.ascontiguousarray(shadowHeight, np.float32),
+           np.ascontiguousarray(isOnScreen, np.uint8)]
+    out = {"active": np.zeros(maxSprites, np.uint8)}
+    for k in ("radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha"):
+        out[k] = np.zeros(maxSprites, np.float32)
+    n = lib().wo_shadow_sprites(len(ins[2]), int(maxNeighbors), *[a.ctypes.data for a in ins], int(maxLights), int(perLight),
+                                int(maxSprites), *[out[k].ctypes.data for k in ("active", "radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha")])
+    out["count"] = int(n)
+    return out
 
 
 class OracleC:

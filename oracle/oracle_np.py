@@ -458,3 +458,117 @@ def _div(a, b):
         if a != a or a == 0:
             return math.nan
         return math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+
+# =========================================================================================
+# Consumers of the hot path's outputs — second, independent restatement.
+# Uses Python containers (an insertion-ordered dict stands in for the JS Set / Map) where
+# weed_oracle_systems.c uses sorted arrays.
+# =========================================================================================
+class CollisionEventsNP:
+    """LogicWorker.processCollisionCallbacks with one logic worker (logic_worker.js:429-526)."""
+
+    def __init__(self):
+        self.previous = {}   # Set -> dict keyed by Cantor key (insertion ordered)
+        self.cache = {}      # collisionPairCache
+
+    @staticmethod
+    def key(a, b):           # :417-421 — float arithmetic like a JS number
+        a = float(a); b = float(b)
+        return ((a + b) * (a + b + 1.0)) / 2.0 + b
+
+    def process(self, collisionData):
+        calls = []
+        pairCount = int(collisionData[0])
+        current = {}
+        for i in range(pairCount):
+            A = int(collisionData[1 + 2 * i]); B = int(collisionData[2 + 2 * i])
+            kab, kba = self.key(A, B), self.key(B, A)
+            current.setdefault(kab, None)
+            current.setdefault(kba, None)
+            if kab not in self.previous:                     # :462-465
+                self.cache[kab] = (A, B)
+                self.cache[kba] = (B, A)
+            t = 1 if kab not in self.previous else 2         # :467
+            calls.append((t, A, B))
+            calls.append((t, B, A))
+        for k in self.previous:                               # :493
+            if k not in current:
+                pair = self.cache.get(k)
+                if pair is None:
+                    continue
+                calls.append((3, pair[0], pair[1]))
+                calls.append((3, pair[1], pair[0]))
+                del self.cache[k]                             # :514
+        self.previous = current                               # :521-523
+        return calls
+
+
+def screen_visibility_np(active, x, y, zoom, cameraX, cameraY, canvasWidth, canvasHeight, screenX, screenY, isItOnScreen):
+    """particle_worker.js:1012-1062, vectorised in binary64; outputs updated in place."""
+    act = np.asarray(active) != 0
+    sx = np.asarray(x, np.float64) * float(zoom) - float(cameraX) * float(zoom)
+    sy = np.asarray(y, np.float64) * float(zoom) - float(cameraY) * float(zoom)
+    mx, my = canvasWidth * 0.15, canvasHeight * 0.15
+    vis = (sx > -mx) & (sx < canvasWidth + mx) & (sy > -my) & (sy < canvasHeight + my)
+    screenX[act] = sx[act].astype(np.float32)
+    screenY[act] = sy[act].astype(np.float32)
+    isItOnScreen[act] = vis[act].astype(np.uint8)
+
+
+def shadow_sprites_np(maxNeighbors, neighborData, distanceData, transformActive, worldX, worldY, lightEnabled,
+                      lightIntensity, shadowCasterActive, shadowRadius, shadowHeight, isOnScreen, maxLights=20,
+                      perLight=15, maxSprites=None):
+    """particle_worker.js:861-1003 as plain Python loops."""
+    if maxSprites is None:
+        maxSprites = maxLights * perLight
+    out = {"active": np.zeros(maxSprites, np.uint8)}
+    for k in ("radius", "x", "y", "rotation", "scaleX", "scaleY", "alpha"):
+        out[k] = np.zeros(maxSprites, np.float32)
+    stride = 1 + maxNeighbors
+    idx = 0
+    lights = 0
+    for li in range(len(transformActive)):
+        if idx >= maxSprites or lights >= maxLights:
+            break
+        if not lightEnabled[li] or not transformActive[li] or not isOnScreen[li]:
+            continue
+        intensity = float(lightIntensity[li])
+        if intensity <= 0:
+            continue
+        lights += 1
+        lx, ly = float(worldX[li]), float(worldY[li])
+        off = li * stride
+        mine = 0
+        for k in range(int(neighborData[off])):
+            if mine >= perLight or idx >= maxSprites:
+                break
+            j = int(neighborData[off + 1 + k])
+            if not shadowCasterActive[j] or not transformActive[j] or not isOnScreen[j]:
+                continue
+            d2 = float(distanceData[off + 1 + k])
+            r = float(shadowRadius[j]) or 10.0
+            if r != r:
+                r = 10.0
+            h = float(shadowHeight[j])
+            if h == 0 or h != h:
+                h = r
+            dx, dy = float(worldX[j]) - lx, float(worldY[j]) - ly
+            dist = math.sqrt(d2) if d2 >= 0 else math.nan
+            if dist < 1:
+                continue
+            inv = 1 / dist
+            ratio = dist * 0.00390625
+            ratio = 1 if ratio > 1 else ratio
+            out["active"][idx] = 1
+            out["radius"][idx] = F32(r)
+            out["x"][idx] = F32(float(worldX[j]) + (dx * inv) * -r)
+            out["y"][idx] = F32(float(worldY[j]) + (dy * inv) * -r)
+            out["rotation"][idx] = F32(math.atan2(dy, dx) - 1.5707963267948966)
+            out["scaleX"][idx] = F32(r * 0.0714)
+            out["scaleY"][idx] = F32((0.3 + ratio * 0.9) * (h * 0.025))
+            out["alpha"][idx] = F32(_div(intensity, d2 * 2))
+            idx += 1
+            mine += 1
+    out["count"] = idx
+    return out
