@@ -495,6 +495,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr);
   TIME_MARK(ctx, timing, 2);
   k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds, ctx->d.GID);
+  k_slot_rank<<<nb, 256, 0, st>>>(g, ctx->d.F, ctx->d.GID, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   TIME_MARK(ctx, timing, 3);
   if (integrate)
     k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
@@ -579,7 +580,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -704,7 +705,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 13 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 14 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   return WEED_OK;
 }

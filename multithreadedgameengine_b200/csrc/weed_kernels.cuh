@@ -216,6 +216,24 @@ struct BySlot {
   uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
 };
 
+// stable position: number of ids in my cell smaller than mine (cell lists are ascending in the
+// reference because it inserts i = 0..N-1 in order, spatial_worker.js:146,168).  A kernel of its
+// own: the dependent gathers key -> cellStart -> ids of the cell need occupancy, not registers.
+__global__ void __launch_bounds__(256)
+k_slot_rank(GridDims g, const uint8_t* __restrict__ F, const uint32_t* __restrict__ GID,
+            const uint32_t* __restrict__ key, const uint32_t* __restrict__ cellStart,
+            const uint32_t* __restrict__ arrIds, uint32_t* __restrict__ slotOf) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.N) return;
+  const uint32_t k = key[i];
+  if (!(F[i] & F_T_ACTIVE) || k == KEY_INVALID) { slotOf[i] = SLOT_NONE; return; }
+  const uint32_t gid = GID ? GID[i] : i;
+  const uint32_t s0 = cellStart[k], s1 = cellStart[k + 1];
+  uint32_t r = 0;
+  for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < gid;
+  slotOf[i] = s0 + r;
+}
+
 template <bool INTEGRATE>
 __global__ void __launch_bounds__(256)
 k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afterSpatial, ById d, BySlot s,
@@ -281,11 +299,7 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   // stable position: number of ids in my cell smaller than mine (cell lists are ascending
   // in the reference because it inserts i = 0..N-1 in order, spatial_worker.js:146,168)
   const uint32_t gid = d.GID ? d.GID[i] : i;
-  const uint32_t s0 = cellStart[k], s1 = cellStart[k + 1];
-  uint32_t r = 0;
-  for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < gid;
-  const uint32_t slot = s0 + r;
-  slotOf[i] = slot;
+  const uint32_t slot = slotOf[i];                               // k_slot_rank
   const int32_t crow = (int32_t)(k / (uint32_t)g.cols);
   const uint32_t owned = (crow >= g.slabBegin && crow < g.slabEnd) ? F_OWNED : 0u;
   if (s.SLID) s.SLID[slot] = i;
