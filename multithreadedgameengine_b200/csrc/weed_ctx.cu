@@ -165,6 +165,9 @@ struct weed_ctx {
   // staging for host<->device columns
   void* stage[20] = {};
   float* protRange = nullptr;
+  // second stream + events of the pipelined weed_step (column copies overlap the frame)
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evUp = nullptr, evBuilt = nullptr, evCopied = nullptr;
   // graph of one full frame
   cudaGraphExec_t frameGraph = nullptr;
   int graphSubSteps = -1;
@@ -286,6 +289,9 @@ extern "C" void weed_destroy(weed_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+  for (cudaEvent_t e : {ctx->evUp, ctx->evBuilt, ctx->evCopied})
+    if (e) cudaEventDestroy(e);
   if (ctx->frameGraph) cudaGraphExecDestroy(ctx->frameGraph);
   for (int b = 0; b < WEED_BUF_COUNT; b++)
     if (ctx->registered[b]) cudaHostUnregister(ctx->host[b]);
@@ -412,7 +418,8 @@ static int check_bound(weed_ctx* ctx, uint32_t mask) {
   return WEED_OK;
 }
 
-static int upload_async(weed_ctx* ctx, uint32_t mask) {
+static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   mask &= WEED_COLS_INPUT_ALL;
   if (!mask) return WEED_OK;
   int rc = check_bound(ctx, mask);
@@ -420,17 +427,18 @@ static int upload_async(weed_ctx* ctx, uint32_t mask) {
   const size_t N = ctx->g.N;
   for (int c = 0; c < 20; c++)
     if ((mask >> c) & 1u)
-      CK(cudaMemcpyAsync(ctx->stage[c], host_col(ctx, c), N * kHot[c].bytes, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->stage[c], host_col(ctx, c), N * kHot[c].bytes, cudaMemcpyHostToDevice, stream));
   Staging st;
   const void** sp = reinterpret_cast<const void**>(&st);
   for (int c = 0; c < 20; c++) sp[c] = ctx->stage[c];
-  k_pack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, mask, st, ctx->d);
+  k_pack<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((uint32_t)N, mask, st, ctx->d);
   CK(cudaGetLastError());
   ctx->spatialValid = false;
   return WEED_OK;
 }
 
-static int download_async(weed_ctx* ctx, uint32_t mask) {
+static int download_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   const uint32_t cols = mask & WEED_COLS_INPUT_ALL;
   const size_t N = ctx->g.N;
   if (cols) {
@@ -439,11 +447,11 @@ static int download_async(weed_ctx* ctx, uint32_t mask) {
     StagingOut st;
     void** sp = reinterpret_cast<void**>(&st);
     for (int c = 0; c < 20; c++) sp[c] = ctx->stage[c];
-    k_unpack<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((uint32_t)N, cols, st, ctx->d);
+    k_unpack<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((uint32_t)N, cols, st, ctx->d);
     CK(cudaGetLastError());
     for (int c = 0; c < 20; c++)
       if ((cols >> c) & 1u)
-        CK(cudaMemcpyAsync(host_col(ctx, c), ctx->stage[c], N * kHot[c].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(host_col(ctx, c), ctx->stage[c], N * kHot[c].bytes, cudaMemcpyDeviceToHost, stream));
   }
   if (mask & WEED_COL_NEIGHBORS) {
     if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
@@ -484,7 +492,8 @@ static inline unsigned blocks_for(size_t threads, unsigned bs) { return (unsigne
 
 #define TIME_MARK(ctx, timing, k) do { if (timing) cudaEventRecord((ctx)->ev[k], (ctx)->stream); } while (0)
 
-static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
+static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_t waitBeforeBuild = nullptr,
+                          cudaEvent_t recordAfterBuild = nullptr) {
   const GridDims& g = ctx->g;
   cudaStream_t st = ctx->stream;
   const unsigned nb = blocks_for(g.N, 256);
@@ -497,10 +506,12 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing) {
   k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds, ctx->d.GID);
   k_slot_rank<<<nb, 256, 0, st>>>(g, ctx->d.F, ctx->d.GID, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   TIME_MARK(ctx, timing, 3);
+  if (waitBeforeBuild) CK(cudaStreamWaitEvent(st, waitBeforeBuild, 0));
   if (integrate)
     k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
   else
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+  if (recordAfterBuild) CK(cudaEventRecord(recordAfterBuild, st));
   k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
   // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
@@ -625,8 +636,68 @@ extern "C" int weed_physics(weed_ctx* ctx, double dtRatio) {
   return WEED_OK;
 }
 
+// Columns that are final once k_build_slots ran (velocities, derived properties, the zeroed
+// accelerations, every pure input): their device->host copies overlap K4..K7 on a second stream.
+// x, y, px, py and collisionCount are final only after the write-back.
+static constexpr uint32_t kLateCols = WEED_COL_T_X | WEED_COL_T_Y | WEED_COL_RB_PX | WEED_COL_RB_PY | WEED_COL_RB_COLLCNT;
+static constexpr uint32_t kAccCols = WEED_COL_RB_AX | WEED_COL_RB_AY;
+static constexpr size_t kPipelineMinEntities = 1u << 18;
+
+static int ensure_copy_stream(weed_ctx* ctx) {
+  if (ctx->copyStream) return WEED_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->evUp, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->evBuilt, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming));
+  return WEED_OK;
+}
+
+// weed_step for large worlds: the frame is launched kernel by kernel so that
+//   * an upload of only ax / ay (what tick() writes) runs beside K1-K3, which do not read them,
+//   * the early columns leave for the host as soon as k_build_slots is done.
+static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, uint32_t download_mask) {
+  int rc = ensure_copy_stream(ctx);
+  if (rc) return rc;
+  rc = push_params(ctx, dtRatio);
+  if (rc) return rc;
+  const uint32_t upCols = upload_mask & WEED_COLS_INPUT_ALL;
+  cudaEvent_t waitUp = nullptr;
+  if (upCols && !(upCols & ~kAccCols)) {
+    CK(cudaEventRecord(ctx->evUp, ctx->stream));                 // order after everything already queued
+    CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evUp, 0));
+    rc = upload_async(ctx, upCols, ctx->copyStream);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->evUp, ctx->copyStream));
+    waitUp = ctx->evUp;
+  } else {
+    rc = upload_async(ctx, upload_mask);
+    if (rc) return rc;
+  }
+  const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
+  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
+  rc = launch_spatial(ctx, true, false, waitUp, early ? ctx->evBuilt : nullptr);
+  if (rc) return rc;
+  if (early) {
+    CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evBuilt, 0));
+    rc = download_async(ctx, early, ctx->copyStream);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->evCopied, ctx->copyStream));
+  }
+  rc = launch_constraints(ctx, false);
+  if (rc) return rc;
+  ctx->spatialValid = false;
+  rc = download_async(ctx, download_mask & ~early);
+  if (rc) return rc;
+  if (early) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied, 0));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
 extern "C" int weed_step(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, uint32_t download_mask) {
   GUARD(ctx);
+  const bool direct = (ctx->cfg.flags & (WEED_FLAG_KERNEL_TIMING | WEED_FLAG_NO_GRAPH)) != 0;
+  const bool hasCopies = ((upload_mask | download_mask) & WEED_COLS_INPUT_ALL) != 0;
+  if (!direct && hasCopies && ctx->g.N >= kPipelineMinEntities) return step_pipelined(ctx, dtRatio, upload_mask, download_mask);
   int rc = upload_async(ctx, upload_mask);
   if (rc) return rc;
   rc = run_frames(ctx, dtRatio, 1);

@@ -266,8 +266,10 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
       dp.y = fround(dadd((double)y0, ddy));
       moved = F_MOVED;
       float4 v;
-      v.x = fround(ddiv(ddx, p.dtRatio));                                      // :309-310
-      v.y = fround(ddiv(ddy, p.dtRatio));
+      // :309-310; x / 1 is x (a headless run has dtRatio = 1): skip the two binary64 divisions
+      const bool unit = p.dtRatio == 1.0;
+      v.x = fround(unit ? ddx : ddiv(ddx, p.dtRatio));
+      v.y = fround(unit ? ddy : ddiv(ddy, p.dtRatio));
       const double sp = __dsqrt_rn(dadd(dmul((double)v.x, (double)v.x), dmul((double)v.y, (double)v.y)));
       v.z = fround(sp); v.w = 0.f;
       d.V[i] = v;

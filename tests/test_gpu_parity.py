@@ -247,6 +247,33 @@ def test_graph_and_direct_launch_agree():
         e.close()
 
 
+def test_pipelined_step_equals_plain_step():
+    """Above 2^18 entities weed_step overlaps the ax/ay upload with K1-K3 and the early columns'
+    download with K4-K7 on a second stream; the host must see exactly what the plain path gives."""
+    cfg, cols = scenes.balls_synthetic(300_000, (8192.0, 4096.0), 16.0, 32, 2, (2.0, 5.0), 16.0, seed=21)
+    a = make_engine(cfg, cols, host_neighbor_rows=False)                       # pipelined
+    b = make_engine(cfg, cols, host_neighbor_rows=False, flags=B.FLAG_NO_GRAPH)  # plain, direct launches
+    rng = np.random.default_rng(1)
+    up = a.mask("RB.ax", "RB.ay")
+    dl = B.COLS_OUTPUT_ALL | B.COL_COLLISIONS
+    for frame in range(4):
+        ax = rng.normal(0, 0.3, cfg["entityCount"]).astype(np.float32)
+        for e in (a, b):
+            e.col["RB.ax"][:] = ax
+            e.col["RB.ay"][:] = -ax
+            e.step(1.0, up, dl)
+        assert_cols_equal(a.col, b.col, what=f"frame {frame}")
+        n = int(a.collisionData[0])
+        assert n == int(b.collisionData[0]) and np.array_equal(a.collisionData[:1 + 2 * n], b.collisionData[:1 + 2 * n])
+        assert not a.col["RB.ax"][1:].any()      # balls: zeroed by the integration, downloaded early
+    # a full upload (spawn / teleport) takes the ordered path of the same function
+    for e in (a, b):
+        e.col["T.x"][5] = 100.0; e.col["RB.px"][5] = 100.0
+        e.step(1.0, B.COLS_INPUT_ALL, dl)
+    assert_cols_equal(a.col, b.col, what="after full upload")
+    a.close(); b.close()
+
+
 def test_errors_are_codes_not_crashes():
     from multithreadedgameengine_b200.engine import GameEngine
     cfg, cols = scenes.balls_readme(n_balls=50, seed=1, world=(400.0, 300.0))
