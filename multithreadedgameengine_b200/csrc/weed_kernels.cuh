@@ -783,7 +783,7 @@ static constexpr int K6_THREADS = 256;
 static constexpr int K6_STAGE = 8;      // staged possible overlaps per thread
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(K6_THREADS, 6)
+__global__ void __launch_bounds__(K6_THREADS, 5)
 k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin, uint32_t gs,
           float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
           uint32_t substep) {
