@@ -376,13 +376,14 @@ template <bool WRITE_ROWS>
 __global__ void __launch_bounds__(K4_THREADS)
 k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
             float* __restrict__ dd, Counters* ctr) {
-  __shared__ uint32_t sW[K4_THREADS / 32][32 * K4_STRIDE];
-  __shared__ uint32_t sId[K4_THREADS / 32][32 * K4_STRIDE];
-  __shared__ float sD2[K4_THREADS / 32][32 * K4_STRIDE];
+  // staged entries: three planes (row word, partner id, float32 d2 bits) of one array, so an
+  // accept is three stores off ONE running pointer
+  constexpr uint32_t PLANE = (K4_THREADS / 32) * 32 * K4_STRIDE;
+  __shared__ uint32_t sStage[3 * PLANE];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* myW = &sW[warp][lane * K4_STRIDE];
-  uint32_t* myId = &sId[warp][lane * K4_STRIDE];
-  float* myD2 = &sD2[warp][lane * K4_STRIDE];
+  uint32_t* const myW = &sStage[warp * 32 * K4_STRIDE + lane * K4_STRIDE];
+  uint32_t* const sId = &sStage[PLANE + warp * 32 * K4_STRIDE];
+  const float* const sD2 = reinterpret_cast<const float*>(&sStage[2 * PLANE + warp * 32 * K4_STRIDE]);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t A = cellStart[g.cells];
   const uint32_t M = g.M;
@@ -415,8 +416,10 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   }
   do {
     // ---- phase 1: scan -----------------------------------------------------------------------
-    uint32_t cnt = 0, slow = 0;
-    while (!done && cnt < K4_CH) {
+    uint32_t* sp = myW;                                   // next free staged entry
+    bool anySlow = false;
+    uint32_t room = done ? 0u : min((uint32_t)K4_CH, M - n);   // stage size and the cap (:264)
+    while (room) {
       if (t >= b) {
         if (++row > win.y) { done = true; break; }
         t = cellStart[(uint32_t)row * g.cols + win.z];
@@ -440,39 +443,45 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
         const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
         if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
         // Would the partner's own scan accept me (ignoring its cap)?  Same visualRange and both
-        // centre cells inside the grid: yes (see k_slot_prep).  Anything else: phase 2 looks.
+        // centre cells inside the grid: yes (see k_slot_prep).  Anything else: phase 2 looks
+        // (flagged in the top bit of the staged id).
         const uint32_t jw = __float_as_uint(c.w);
         const uint32_t jid = jw & ~CX_EDGE;
         const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
-        myW[cnt] = (t + (uint32_t)u) | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
-        myId[cnt] = jid;
-        myD2[cnt] = fround(d2);
-        if (!sure) slow |= 1u << cnt;
-        cnt++;
-        if (++n >= M) { done = true; used = (uint32_t)u + 1; }          // :264
-        else if (cnt == K4_CH) used = (uint32_t)u + 1;
+        sp[0] = (t + (uint32_t)u) | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
+        sp[PLANE] = sure ? jid : (jid | CX_EDGE);
+        sp[2 * PLANE] = __float_as_uint(fround(d2));
+        sp++;
+        anySlow |= !sure;
+        if (--room == 0) used = (uint32_t)u + 1;
       }
       t += used;
     }
+    const uint32_t cnt = (uint32_t)(sp - myW);
+    const uint32_t first = n;                             // row position of my first staged entry
+    n += cnt;
+    if (n >= M) done = true;
     // ---- phase 2: staged entries whose partner differs in visualRange or sits on the rim ---------
-    const uint32_t first = n - cnt;                       // row position of my first staged entry
-    while (slow) {
-      const uint32_t k = (uint32_t)__ffs(slow) - 1u;
-      slow &= slow - 1u;
-      const uint32_t wd = myW[k];
-      const uint32_t tc = wd & NS_SLOT_MASK;
-      const float4 c = s.CXY[tc];
-      const int4 wt = s.WIN[tc];
-      // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
-      bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
-      if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
-        const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        back = d2 < dmul((double)c.z, (double)c.z);
+    if (anySlow) {
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t jraw = myW[PLANE + k];
+        if (!(jraw & CX_EDGE)) continue;
+        myW[PLANE + k] = jraw & ~CX_EDGE;
+        const uint32_t wd = myW[k];
+        const uint32_t tc = wd & NS_SLOT_MASK;
+        const float4 c = s.CXY[tc];
+        const int4 wt = s.WIN[tc];
+        // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
+        bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+        if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
+          const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+          const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+          back = d2 < dmul((double)c.z, (double)c.z);
+        }
+        if (back) myW[k] = wd | NS_BACK;
+        // pair (id, jid) is in P but the partner cannot infer it from its own row
+        else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
       }
-      if (back) myW[k] = wd | NS_BACK;
-      // pair (id, jid) is in P but the partner cannot infer it from its own row
-      else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
     }
     __syncwarp();
     // ---- warp-cooperative flush -------------------------------------------------------------
@@ -490,9 +499,9 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
         if (f == 0 && fin) {
           // whole row in this round: header + entries in one contiguous store
           if (l == 0) { nd[rb] = (int32_t)c; dd[rb] = (float)c; }       // :274-275
-          else if (l <= c) { nd[rb + l] = (int32_t)sId[warp][src * K4_STRIDE + l - 1]; dd[rb + l] = sD2[warp][src * K4_STRIDE + l - 1]; }
+          else if (l <= c) { nd[rb + l] = (int32_t)sId[src * K4_STRIDE + l - 1]; dd[rb + l] = sD2[src * K4_STRIDE + l - 1]; }
         } else {
-          if (l < c) { nd[rb + 1 + f + l] = (int32_t)sId[warp][src * K4_STRIDE + l]; dd[rb + 1 + f + l] = sD2[warp][src * K4_STRIDE + l]; }  // :259-260
+          if (l < c) { nd[rb + 1 + f + l] = (int32_t)sId[src * K4_STRIDE + l]; dd[rb + 1 + f + l] = sD2[src * K4_STRIDE + l]; }  // :259-260
           if (fin && l == 15) { nd[rb] = (int32_t)(f + c); dd[rb] = (float)(f + c); }
         }
       }
