@@ -242,6 +242,36 @@ typedef struct weed_boids_params {
 int weed_system_boids(weed_ctx* ctx, const weed_boids_params* params, const float* protectedRange,
                       double dtRatio);
 
+/* weed_system_flock: the whole predators demo tick() on the device — Boid (boid.js:115-124),
+ * Prey (prey.js:120-137: flocking + applyFleeing :176-189 fed by processNeighbor :154-169) and
+ * Predator (predator.js: flocking + applyHunting :195-215 fed by processNeighbor :172-187), then
+ * avoidMouse (boid.js:281-316) and keepWithinBounds (:318-341), in that order, with the
+ * per-class numbers each constructor sets.  An entity runs the class whose entityType matches
+ * its Transform.entityType (WEED_FLOCK_ANY_TYPE matches all); entities of no listed class and
+ * entity 0 (the Mouse) are left alone.                                                        */
+#define WEED_FLOCK_BOID 0u
+#define WEED_FLOCK_PREY 1u
+#define WEED_FLOCK_PREDATOR 2u
+#define WEED_FLOCK_ANY_TYPE 0xFFFFFFFFu
+#define WEED_FLOCK_MAX_CLASSES 8
+typedef struct weed_flock_class {
+  uint32_t entityType;         /* Transform.entityType of the class                              */
+  uint32_t role;               /* WEED_FLOCK_BOID / _PREY / _PREDATOR                            */
+  uint32_t otherEntityType;    /* PREY: Predator.entityType (prey.js:164); PREDATOR: Prey's (predator.js:182) */
+  uint32_t _pad;
+  double protectedRangeScale;  /* protectedRange = fround(scale * Collider.radius) when no array is
+                                  given: boid.js:64 2, prey.js:55 1.25, predator.js:57 0          */
+  double centeringFactor, avoidFactor, matchingFactor, turnFactor, margin;   /* Flocking.*        */
+  double roleFactor;           /* PREY: predatorAvoidFactor (prey.js:37); PREDATOR: huntFactor (predator.js:43) */
+} weed_flock_class;
+typedef struct weed_flock_params {
+  uint32_t mouseEntityType;    /* Mouse.entityType: such neighbors are skipped, boid.js:179-180   */
+  uint32_t mouseDown;          /* Mouse.x && Mouse.isDown (boid.js:282-283)                       */
+  double dtRatio;
+} weed_flock_params;
+int weed_system_flock(weed_ctx* ctx, const weed_flock_class* classes, uint32_t classCount,
+                      const weed_flock_params* params, const float* protectedRange);
+
 /* ---- collision Enter / Stay / Exit ------------------------------------------
  * Replaces the bookkeeping of LogicWorker.processCollisionCallbacks (src/workers/
  * logic_worker.js:429-526): the pair list the last weed_physics / weed_step left in

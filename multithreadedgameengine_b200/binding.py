@@ -64,6 +64,16 @@ class BoidsParams(C.Structure):
                 ("turnFactor", C.c_double), ("margin", C.c_double), ("mouseEntityType", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class FlockClass(C.Structure):
+    _fields_ = [("entityType", C.c_uint32), ("role", C.c_uint32), ("otherEntityType", C.c_uint32), ("_pad", C.c_uint32),
+                ("protectedRangeScale", C.c_double), ("centeringFactor", C.c_double), ("avoidFactor", C.c_double),
+                ("matchingFactor", C.c_double), ("turnFactor", C.c_double), ("margin", C.c_double), ("roleFactor", C.c_double)]
+
+
+class FlockParams(C.Structure):
+    _fields_ = [("mouseEntityType", C.c_uint32), ("mouseDown", C.c_uint32), ("dtRatio", C.c_double)]
+
+
 class CollisionEventCounts(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("pairs", "entered", "stayed", "exited")]
 
@@ -118,6 +128,7 @@ SYMBOLS = {
     "weed_last_error": (C.c_char_p, [C.c_void_p]),
     "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "weed_system_boids": (C.c_int, [C.c_void_p, C.POINTER(BoidsParams), C.c_void_p, C.c_double]),
+    "weed_system_flock": (C.c_int, [C.c_void_p, C.POINTER(FlockClass), C.c_uint32, C.POINTER(FlockParams), C.c_void_p]),
     "weed_system_collision_events": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CollisionEventCounts), C.c_void_p, C.c_void_p]),
     "weed_system_screen_visibility": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]),
     "weed_system_shadows_upload": (C.c_int, [C.c_void_p, C.POINTER(ShadowColumns)]),
@@ -129,6 +140,7 @@ SYMBOLS = {
     "weed_slab_status": (C.c_int, [C.c_void_p, C.POINTER(SlabStats)]),
 }
 SLAB_RECORD_BYTES = 64
+FLOCK_BOID, FLOCK_PREY, FLOCK_PREDATOR, FLOCK_ANY_TYPE = 0, 1, 2, 0xFFFFFFFF
 EVENTS_FORGET_PREVIOUS = 1
 COLLISION_ENTER, COLLISION_STAY, COLLISION_EXIT = 1, 2, 3
 

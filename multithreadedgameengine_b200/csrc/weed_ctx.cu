@@ -868,9 +868,7 @@ extern "C" int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out) {
 // =============================================================================================
 // device-side systems
 // =============================================================================================
-extern "C" int weed_system_boids(weed_ctx* ctx, const weed_boids_params* p, const float* protectedRange, double dtRatio) {
-  GUARD(ctx);
-  if (!p) return WEED_E_INVALID;
+static int run_flock(weed_ctx* ctx, const FlockParams& fp, const float* protectedRange) {
   if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
   if (ctx->slab) return fail(ctx, WEED_E_STATE, "systems are not available on slab contexts yet");
   const size_t N = ctx->g.N;
@@ -878,14 +876,42 @@ extern "C" int weed_system_boids(weed_ctx* ctx, const weed_boids_params* p, cons
     if (!ctx->protRange) { int rc = dalloc(ctx, &ctx->protRange, N); if (rc) return rc; }
     CK(cudaMemcpyAsync(ctx->protRange, protectedRange, N * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
-  BoidsParams bp;
-  bp.centering = p->centeringFactor; bp.avoid = p->avoidFactor; bp.matching = p->matchingFactor;
-  bp.turn = p->turnFactor; bp.margin = p->margin; bp.dtRatio = dtRatio; bp.mouseType = p->mouseEntityType;
-  k_system_boids<<<blocks_for(N, 128), 128, 0, ctx->stream>>>(ctx->g, bp, ctx->d, ctx->nd, ctx->dd,
+  k_system_flock<<<blocks_for(N, 128), 128, 0, ctx->stream>>>(ctx->g, fp, ctx->d, ctx->nd, ctx->dd,
                                                               protectedRange ? ctx->protRange : nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
+}
+
+extern "C" int weed_system_boids(weed_ctx* ctx, const weed_boids_params* p, const float* protectedRange, double dtRatio) {
+  GUARD(ctx);
+  if (!p) return WEED_E_INVALID;
+  FlockParams fp{};
+  fp.nClasses = 1; fp.mouseType = p->mouseEntityType; fp.mouseDown = 0; fp.dtRatio = dtRatio;
+  FlockClass& c = fp.cls[0];
+  c.type = FLOCK_ANY_TYPE; c.role = 0; c.other = 0; c.prScale = 2.0;     // boid.js:64
+  c.centering = p->centeringFactor; c.avoid = p->avoidFactor; c.matching = p->matchingFactor;
+  c.turn = p->turnFactor; c.margin = p->margin; c.roleFactor = 0;
+  return run_flock(ctx, fp, protectedRange);
+}
+
+extern "C" int weed_system_flock(weed_ctx* ctx, const weed_flock_class* classes, uint32_t classCount,
+                                 const weed_flock_params* params, const float* protectedRange) {
+  GUARD(ctx);
+  if (!classes || !params || classCount == 0 || classCount > FLOCK_MAX_CLASSES)
+    return fail(ctx, WEED_E_INVALID, "weed_system_flock: 1.." + std::to_string(FLOCK_MAX_CLASSES) + " classes");
+  FlockParams fp{};
+  fp.nClasses = classCount; fp.mouseType = params->mouseEntityType; fp.mouseDown = params->mouseDown ? 1u : 0u;
+  fp.dtRatio = params->dtRatio;
+  for (uint32_t k = 0; k < classCount; k++) {
+    if (classes[k].role > WEED_FLOCK_PREDATOR) return fail(ctx, WEED_E_INVALID, "weed_system_flock: bad role");
+    FlockClass& c = fp.cls[k];
+    c.type = classes[k].entityType; c.role = classes[k].role; c.other = classes[k].otherEntityType;
+    c.prScale = classes[k].protectedRangeScale; c.centering = classes[k].centeringFactor; c.avoid = classes[k].avoidFactor;
+    c.matching = classes[k].matchingFactor; c.turn = classes[k].turnFactor; c.margin = classes[k].margin;
+    c.roleFactor = classes[k].roleFactor;
+  }
+  return run_flock(ctx, fp, protectedRange);
 }
 
 // tile scratch shared by the ordered-compaction passes of the systems

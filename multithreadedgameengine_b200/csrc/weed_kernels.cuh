@@ -15,6 +15,7 @@
 //   id order   k_pair_emit     K7b collisionData emission by the tiles below the cap
 #pragma once
 #include <cooperative_groups.h>
+#include <math_constants.h>
 
 #include "weed_device.cuh"
 
@@ -1225,61 +1226,116 @@ __global__ void __launch_bounds__(256) k_unpack(uint32_t N, uint32_t mask, Stagi
 // demos/predators/boid.js:137-240 + :318-341, one thread per entity, evaluation order and
 // rounding of the JavaScript: accumulators are binary64, every `rbAX[i] += ...` rounds to
 // float32.  Reads the API rows where the spatial pass left them.
-struct BoidsParams { double centering, avoid, matching, turn, margin, dtRatio; uint32_t mouseType; };
+// Per-class parameters: Boid (boid.js:64-69), Prey (prey.js:37, 55-60) and Predator
+// (predator.js:43, 57-62) differ only in these numbers and in their processNeighbor hook.
+static constexpr uint32_t FLOCK_ANY_TYPE = 0xFFFFFFFFu;
+static constexpr int FLOCK_MAX_CLASSES = 8;
+struct FlockClass {
+  uint32_t type, role, other, _pad;       // role: 0 boid, 1 prey (flees `other`), 2 predator (hunts `other`)
+  double prScale, centering, avoid, matching, turn, margin, roleFactor;
+};
+struct FlockParams {
+  FlockClass cls[FLOCK_MAX_CLASSES];
+  uint32_t nClasses, mouseType, mouseDown, _pad;
+  double dtRatio;
+};
 
 __global__ void __launch_bounds__(128)
-k_system_boids(GridDims g, BoidsParams bp, ById d, const int32_t* __restrict__ nd, const float* __restrict__ dd,
+k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ nd, const float* __restrict__ dd,
                const float* __restrict__ protectedRange) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.N || i == 0) return;                   // index 0 is the Mouse: its tick() is empty
   if (!(d.F[i] & F_T_ACTIVE)) return;
+  const uint32_t myType = d.ET[i];
+  int ci = -1;
+  for (uint32_t c = 0; c < fp.nClasses; c++)
+    if (fp.cls[c].type == myType || fp.cls[c].type == FLOCK_ANY_TYPE) { ci = (int)c; break; }
+  if (ci < 0) return;                               // not a boid: some other tick()
+  const FlockClass& k = fp.cls[ci];
+  const double dt = fp.dtRatio;
   const size_t off = (size_t)i * (1 + (size_t)g.M);
   const int32_t cnt = nd[off];
   const float4 me = d.DP[i];
   const double myX = me.x, myY = me.y;
   float2 acc = d.ACC[i];
-  if (cnt > 0) {
-    const float pr = protectedRange ? protectedRange[i] : d.AT[i].y * 2.0f;   // boid.js:64
+  if (cnt > 0) {                                                                 // boid.js:138
+    const float pr = protectedRange ? protectedRange[i] : fround(dmul((double)d.AT[i].y, k.prScale));
     const double pr2 = dmul((double)pr, (double)pr);
     double cx = 0, cy = 0, avx = 0, avy = 0, sx = 0, sy = 0;
-    uint32_t same = 0;
-    const uint32_t myType = d.ET[i];
+    double fleeX = 0, fleeY = 0, closest2 = CUDART_INF;
+    uint32_t same = 0, predators = 0;
+    int32_t closest = -1;
     for (int32_t n = 0; n < cnt; n++) {
       const int32_t j = nd[off + 1 + n];
       const uint32_t nt = d.ET[j];
-      if (nt == bp.mouseType) continue;                                        // :179
+      if (nt == fp.mouseType) continue;                                          // :179-180
       const double d2 = (double)dd[off + 1 + n];
       const float4 pj = d.DP[j];
       const double dx = dsub((double)pj.x, myX), dy = dsub((double)pj.y, myY);
-      if (d2 < pr2 && d2 > 0) {                                                // :192-196
+      if (d2 < pr2 && d2 > 0) {                                                  // :192-196
         sx = dsub(sx, ddiv(dx, d2));
         sy = dsub(sy, ddiv(dy, d2));
         continue;
       }
-      if (nt == myType) {                                                      // :199-206
+      if (nt == myType) {                                                        // :199-206
         const float4 vj = d.V[j];
         cx = dadd(cx, (double)pj.x); cy = dadd(cy, (double)pj.y);
         avx = dadd(avx, (double)vj.x); avy = dadd(avy, (double)vj.y);
         same++;
       }
+      // processNeighbor hooks (:209-217)
+      if (k.role == 1) {                                                         // prey.js:154-169
+        if (nt == k.other && d2 > 0) {
+          fleeX = dadd(fleeX, ddiv(-dx, d2));
+          fleeY = dadd(fleeY, ddiv(-dy, d2));
+          predators++;
+        }
+      } else if (k.role == 2) {                                                  // predator.js:172-187
+        if (nt == k.other && d2 < closest2) { closest2 = d2; closest = j; }
+      }
     }
-    if (same) {                                                                // :221-232
+    if (same) {                                                                  // :221-232
       const float4 vi = d.V[i];
       cx = ddiv(cx, (double)same); cy = ddiv(cy, (double)same);
-      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(cx, myX), bp.centering), bp.dtRatio)));
-      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(cy, myY), bp.centering), bp.dtRatio)));
+      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(cx, myX), k.centering), dt)));
+      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(cy, myY), k.centering), dt)));
       avx = ddiv(avx, (double)same); avy = ddiv(avy, (double)same);
-      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(avx, (double)vi.x), bp.matching), bp.dtRatio)));
-      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(avy, (double)vi.y), bp.matching), bp.dtRatio)));
+      acc.x = fround(dadd((double)acc.x, dmul(dmul(dsub(avx, (double)vi.x), k.matching), dt)));
+      acc.y = fround(dadd((double)acc.y, dmul(dmul(dsub(avy, (double)vi.y), k.matching), dt)));
     }
-    acc.x = fround(dadd((double)acc.x, dmul(dmul(sx, bp.avoid), bp.dtRatio)));  // :235-236
-    acc.y = fround(dadd((double)acc.y, dmul(dmul(sy, bp.avoid), bp.dtRatio)));
+    acc.x = fround(dadd((double)acc.x, dmul(dmul(sx, k.avoid), dt)));             // :235-236
+    acc.y = fround(dadd((double)acc.y, dmul(dmul(sy, k.avoid), dt)));
+    if (k.role == 1 && predators) {                                              // prey.js:176-189
+      acc.x = fround(dadd((double)acc.x, dmul(dmul(fleeX, k.roleFactor), dt)));
+      acc.y = fround(dadd((double)acc.y, dmul(dmul(fleeY, k.roleFactor), dt)));
+    }
+    if (k.role == 2 && closest >= 0) {                                           // predator.js:195-215
+      const float4 pp = d.DP[closest];
+      const double dx = dsub((double)pp.x, myX), dy = dsub((double)pp.y, myY);
+      const double dist = __dsqrt_rn(closest2);
+      if (dist > 0) {
+        acc.x = fround(dadd((double)acc.x, dmul(dmul(ddiv(dx, dist), k.roleFactor), dt)));
+        acc.y = fround(dadd((double)acc.y, dmul(dmul(ddiv(dy, dist), k.roleFactor), dt)));
+      }
+    }
   }
-  const double turn = dmul(bp.turn, bp.dtRatio);                               // :334-340
-  if (myX < bp.margin) acc.x = fround(dadd((double)acc.x, turn));
-  if (myX > dsub(g.worldW, bp.margin)) acc.x = fround(dsub((double)acc.x, turn));
-  if (myY < bp.margin) acc.y = fround(dadd((double)acc.y, turn));
-  if (myY > dsub(g.worldH, bp.margin)) acc.y = fround(dsub((double)acc.y, turn));
+  if (fp.mouseDown) {                                                            // boid.js:281-316
+    for (int32_t n = 0; n < cnt; n++) {
+      if (nd[off + 1 + n] != 0) continue;                                        // the Mouse is entity 0
+      const double d2 = (double)dd[off + 1 + n];
+      if (d2 != d2 || d2 == 0) break;                                            // `!dist2`
+      const float4 pm = d.DP[0];
+      const double dx = dsub((double)pm.x, myX), dy = dsub((double)pm.y, myY);
+      acc.x = fround(dsub((double)acc.x, dmul(dmul(ddiv(dx, d2), 1000.0), dt)));
+      acc.y = fround(dsub((double)acc.y, dmul(dmul(ddiv(dy, d2), 1000.0), dt)));
+      break;
+    }
+  }
+  const double turn = dmul(k.turn, dt);                                          // :334-340
+  if (myX < k.margin) acc.x = fround(dadd((double)acc.x, turn));
+  if (myX > dsub(g.worldW, k.margin)) acc.x = fround(dsub((double)acc.x, turn));
+  if (myY < k.margin) acc.y = fround(dadd((double)acc.y, turn));
+  if (myY > dsub(g.worldH, k.margin)) acc.y = fround(dsub((double)acc.y, turn));
   d.ACC[i] = acc;
 }
 

@@ -204,6 +204,25 @@ class GameEngine:
             ptr = self._prot.ctypes.data
         B.check(self.ctx, B.lib().weed_system_boids(self.ctx, C.byref(p), ptr, float(dtRatio)))
 
+    def system_flock(self, classes, dtRatio=1.0, mouseDown=False, mouseEntityType=0, protectedRange=None):
+        """The predators demo's tick() on the device (weed_system_flock): `classes` is a list of
+        dicts with entityType, role ("boid" | "prey" | "predator"), otherEntityType and the
+        Flocking numbers each constructor sets (boid.js:64-69, prey.js:37,55-60,
+        predator.js:43,57-62); see scenes.PREDATORS_DEMO_CLASSES."""
+        roles = {"boid": B.FLOCK_BOID, "prey": B.FLOCK_PREY, "predator": B.FLOCK_PREDATOR}
+        arr = (B.FlockClass * len(classes))()
+        for k, c in enumerate(classes):
+            arr[k] = B.FlockClass(int(c["entityType"]), roles[c.get("role", "boid")], int(c.get("otherEntityType", 0)), 0,
+                                  float(c.get("protectedRangeScale", 2.0)), float(c.get("centeringFactor", 0.001)),
+                                  float(c.get("avoidFactor", 0.3)), float(c.get("matchingFactor", 0.1)),
+                                  float(c.get("turnFactor", 0.01)), float(c.get("margin", 20.0)), float(c.get("roleFactor", 0.0)))
+        fp = B.FlockParams(int(mouseEntityType), 1 if mouseDown else 0, float(dtRatio))
+        ptr = None
+        if protectedRange is not None:
+            self._prot = np.ascontiguousarray(protectedRange, dtype=np.float32)
+            ptr = self._prot.ctypes.data
+        B.check(self.ctx, B.lib().weed_system_flock(self.ctx, arr, len(classes), C.byref(fp), ptr))
+
     # ---- device-side consumers of collisionData / positions / rows (SURVEY §8 f2, f3) ----------
     def collision_events(self, forget_previous=False):
         """Enter / Stay / Exit diff of this frame's collisionData against the previous call's

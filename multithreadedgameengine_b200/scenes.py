@@ -175,3 +175,13 @@ def scaled(name, n_balls, seed=1234):
     h = max(cs * 2, round(H * f / cs) * cs)
     k = max(1, round(clusters * n_balls / n_full)) if clusters else 0
     return balls_synthetic(n_balls, (w, h), cs, M, S, radius, vr, seed, clusters=k)
+
+
+# Flocking numbers of the predators demo, per class (entityType 1 = Prey, 2 = Predator as laid
+# out by scenes.boids): demos/predators/prey.js:37,55-60 and predator.js:43,57-62.
+PREDATORS_DEMO_CLASSES = [
+    dict(entityType=1, role="prey", otherEntityType=2, protectedRangeScale=1.25, centeringFactor=0.0005, avoidFactor=6.0,
+         matchingFactor=0.05, turnFactor=0.001, margin=20.0, roleFactor=10.0),
+    dict(entityType=2, role="predator", otherEntityType=1, protectedRangeScale=0.0, centeringFactor=0.0, avoidFactor=0.0,
+         matchingFactor=0.0, turnFactor=0.1, margin=20.0, roleFactor=0.2),
+]

@@ -489,6 +489,50 @@ def test_device_side_boids_system_matches_host_tick():
     dev.close(); host.close()
 
 
+def test_device_side_predators_demo_tick_matches_host_tick():
+    """Config 2 complete (SURVEY §8 d): Prey flee, Predators hunt, the Mouse repels while its
+    button is down — weed_system_flock against the host-side restatement of prey.js /
+    predator.js / boid.js fed with fetched rows, bit for bit over several frames."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    from boids_tick import tick_classes
+
+    cfg, cols = scenes.boids(n_prey=1500, n_pred=80, seed=9)
+    cfg["worldWidth"], cfg["worldHeight"] = 1500.0, 750.0
+    for k, f in (("T.x", 1500 / 5000), ("RB.px", 1500 / 5000), ("T.y", 750 / 2000), ("RB.py", 750 / 2000)):
+        cols[k] = (cols[k] * np.float32(f)).astype(np.float32)
+    for k, v in (("T.x", 700.0), ("RB.px", 700.0), ("T.y", 380.0), ("RB.py", 380.0)):
+        cols[k][0] = v                       # the Mouse in the middle of the herd
+    cfg["spatial"]["maxNeighbors"] = 160
+    N, M = cfg["entityCount"], 160
+    etype = np.zeros(N, dtype=np.uint8)
+    etype[1:1501] = 1
+    etype[1501:] = 2
+    dev = make_engine(cfg, cols)
+    host = make_engine(cfg, cols)
+    for e in (dev, host):
+        e.Transform.entityType[:] = etype
+        e.upload(e.mask("T.entityType"))
+    up = host.mask("RB.ax", "RB.ay")
+    fled = hunted = 0
+    for frame in range(6):
+        down = frame >= 2                    # button pressed from the third frame on
+        dev.step(1.0, 0, 0)
+        host.step(1.0, up if frame else 0, B.COLS_OUTPUT_ALL | B.COL_NEIGHBORS)
+        before = host.col["RB.ax"].copy()
+        dev.system_flock(scenes.PREDATORS_DEMO_CLASSES, 1.0, mouseDown=down)
+        tick_classes(host.col, etype, host.neighborData, host.distanceData, M, cfg["worldWidth"], cfg["worldHeight"],
+                     scenes.PREDATORS_DEMO_CLASSES, 1.0, mouseDown=down)
+        dev.download(B.COLS_OUTPUT_ALL)
+        for k in ("RB.ax", "RB.ay", "T.x", "T.y", "RB.vx", "RB.vy"):
+            assert np.array_equal(bits(dev.col[k]), bits(host.col[k])), f"frame {frame} {k}"
+        fled += int((host.col["RB.ax"][1:1501] != before[1:1501]).sum())
+        hunted += int((host.col["RB.ax"][1501:] != before[1501:]).sum())
+    assert fled > 0 and hunted > 0
+    dev.close(); host.close()
+
+
 def test_full_size_config4_16M_properties():
     """BASELINE config 4 at its full size (16M entities, clustered, capped rows): sampled rows
     against a brute-force float64 evaluation over ALL entities, plus frame invariants.  Rows are
