@@ -326,6 +326,30 @@ int weed_system_shadows_upload(weed_ctx* ctx, const weed_shadow_columns* cols);
 int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLights, uint32_t maxShadowsPerLight,
                         uint32_t maxShadowSprites, const weed_shadow_sprites* out, uint32_t* spriteCount);
 
+/* ---- spawn / despawn pools ----------------------------------------------------
+ * GameObject.spawn / despawn / despawnAll (src/core/gameObject.js:840-951, 668-690, 1001-1034)
+ * for whole batches, on the device-resident columns.  A pool is one entity class: the index
+ * range [startIndex, startIndex + totalCount) with the reference's LIFO free list in its
+ * interleaved initial order (initializeFreeList, :794-833 — like the reference it lists EVERY
+ * index of the class as free, whatever Transform.active says).  A batch of n spawns takes the
+ * indices n successive spawn() calls would take and leaves each entity as spawn() does:
+ * ax = ay = 0, vx, vy, x, y from the record, speed = velocityAngle = 0, px = x - vx,
+ * py = y - vy (:936-939), component active flags then Transform.active set.  indices_out[k] is
+ * -1 once the pool is empty (:868-873).  A batch of despawns clears the active flags and pushes
+ * the indices in batch order; inactive entities and repeats are skipped (:669-670).  Host-only
+ * parts of spawn() (sprite state, onSpawned / onDespawned callbacks, other components) stay
+ * with the caller, which gets the indices; the host copies of the touched columns are stale
+ * until downloaded.                                                                           */
+#define WEED_POOL_HAS_RIGIDBODY 1u
+#define WEED_POOL_HAS_COLLIDER 2u
+typedef struct weed_spawn_record { float x, y, vx, vy; } weed_spawn_record;   /* spawnConfig x, y, vx, vy */
+int weed_pool_create(weed_ctx* ctx, uint32_t startIndex, uint32_t totalCount, uint32_t components, uint32_t* pool_out);
+int weed_pool_spawn(weed_ctx* ctx, uint32_t pool, const weed_spawn_record* records, uint32_t n, int32_t* indices_out);
+int weed_pool_despawn(weed_ctx* ctx, uint32_t pool, const int32_t* indices, uint32_t n, uint32_t* despawned_out);
+int weed_pool_despawn_all(weed_ctx* ctx, uint32_t pool, uint32_t* despawned_out);
+/* getPoolStats (:959-990): total and available (= free list entries)                          */
+int weed_pool_stats(weed_ctx* ctx, uint32_t pool, uint32_t* total, uint32_t* available);
+
 /* ---- multi-GPU slabs (SURVEY §8 e) ----------------------------------------
  * A slab context (slabRowEnd > 0) holds a LOCAL entity table of `entityCount` slots; every
  * slot carries a global entity id.  Component buffers, neighbor rows and column masks are

@@ -133,6 +133,11 @@ SYMBOLS = {
     "weed_system_screen_visibility": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_void_p, C.c_void_p]),
     "weed_system_shadows_upload": (C.c_int, [C.c_void_p, C.POINTER(ShadowColumns)]),
     "weed_system_shadows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ShadowSprites), C.POINTER(C.c_uint32)]),
+    "weed_pool_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "weed_pool_spawn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "weed_pool_despawn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "weed_pool_despawn_all": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "weed_pool_stats": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "weed_slab_set_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -141,6 +146,7 @@ SYMBOLS = {
 }
 SLAB_RECORD_BYTES = 64
 FLOCK_BOID, FLOCK_PREY, FLOCK_PREDATOR, FLOCK_ANY_TYPE = 0, 1, 2, 0xFFFFFFFF
+POOL_HAS_RIGIDBODY, POOL_HAS_COLLIDER = 1, 2
 EVENTS_FORGET_PREVIOUS = 1
 COLLISION_ENTER, COLLISION_STAY, COLLISION_EXIT = 1, 2, 3
 

@@ -185,6 +185,10 @@ struct weed_ctx {
   float *shIntensity = nullptr, *shRadius = nullptr, *shHeight = nullptr;
   uint32_t *shLightId = nullptr, *shLightCount = nullptr, *shScalars = nullptr;
   uint8_t* shOutActive = nullptr; float* shOut = nullptr; uint32_t shOutCap = 0, shLightCap = 0;
+  struct Pool { uint32_t start, count, components; int32_t* freeList; PoolState* st; };
+  std::vector<Pool> pools;
+  void* poolStage = nullptr; size_t poolStageBytes = 0;   // device staging for a batch (records / indices)
+  uint32_t* poolScalars = nullptr;
   // slabs
   bool slab = false;
   uint32_t* holes = nullptr;
@@ -1062,5 +1066,120 @@ extern "C" int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLight
   }
   CK(cudaStreamSynchronize(st));
   if (spriteCount) *spriteCount = n;
+  return WEED_OK;
+}
+
+// =============================================================================================
+// spawn / despawn pools
+// =============================================================================================
+static int pool_stage(weed_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->poolStageBytes) return WEED_OK;
+  uint8_t* p = nullptr;
+  int rc = dalloc(ctx, &p, bytes, false);
+  if (rc) return rc;
+  ctx->poolStage = p; ctx->poolStageBytes = bytes;
+  return WEED_OK;
+}
+static int pool_get(weed_ctx* ctx, uint32_t pool, weed_ctx::Pool** out) {
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "pools are not available on slab contexts yet");
+  if (pool >= ctx->pools.size()) return fail(ctx, WEED_E_INVALID, "no such pool");
+  *out = &ctx->pools[pool];
+  return WEED_OK;
+}
+
+extern "C" int weed_pool_create(weed_ctx* ctx, uint32_t startIndex, uint32_t totalCount, uint32_t components, uint32_t* pool_out) {
+  GUARD(ctx);
+  if (ctx->slab) return fail(ctx, WEED_E_STATE, "pools are not available on slab contexts yet");
+  if (!pool_out || totalCount == 0 || (size_t)startIndex + totalCount > ctx->g.N) return fail(ctx, WEED_E_INVALID, "pool range out of bounds");
+  weed_ctx::Pool p{startIndex, totalCount, components, nullptr, nullptr};
+  int rc = dalloc(ctx, &p.freeList, totalCount, false); if (rc) return rc;
+  rc = dalloc(ctx, &p.st, 1); if (rc) return rc;
+  if (!ctx->poolScalars) { rc = dalloc(ctx, &ctx->poolScalars, 4); if (rc) return rc; }
+  k_pool_init<<<blocks_for(totalCount, 256), 256, 0, ctx->stream>>>(startIndex, totalCount, p.freeList, p.st);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->pools.push_back(p);
+  *pool_out = (uint32_t)ctx->pools.size() - 1;
+  return WEED_OK;
+}
+
+extern "C" int weed_pool_spawn(weed_ctx* ctx, uint32_t pool, const weed_spawn_record* records, uint32_t n, int32_t* indices_out) {
+  GUARD(ctx);
+  weed_ctx::Pool* p;
+  int rc = pool_get(ctx, pool, &p); if (rc) return rc;
+  if (n == 0) return WEED_OK;
+  if (!records || !indices_out) return WEED_E_INVALID;
+  rc = pool_stage(ctx, (size_t)n * (sizeof(SpawnRec) + 4)); if (rc) return rc;
+  SpawnRec* dRecs = (SpawnRec*)ctx->poolStage;
+  int32_t* dIdx = (int32_t*)((uint8_t*)ctx->poolStage + (size_t)n * sizeof(SpawnRec));
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dRecs, records, (size_t)n * sizeof(SpawnRec), cudaMemcpyHostToDevice, st));
+  k_pool_spawn<<<blocks_for(n, 256), 256, 0, st>>>(n, p->components, dRecs, p->freeList, p->st, ctx->d, dIdx);
+  k_pool_spawn_end<<<1, 32, 0, st>>>(n, p->st);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(indices_out, dIdx, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->spatialValid = false;
+  return WEED_OK;
+}
+
+static int pool_despawn(weed_ctx* ctx, weed_ctx::Pool* p, const int32_t* indices, uint32_t n, uint32_t* despawned) {
+  cudaStream_t st = ctx->stream;
+  int32_t* dIdx = nullptr;
+  if (indices) {
+    for (uint32_t k = 0; k < n; k++)
+      if (indices[k] < (int32_t)p->start || indices[k] >= (int32_t)(p->start + p->count))
+        return fail(ctx, WEED_E_INVALID, "index " + std::to_string(indices[k]) + " is not in the pool");
+    int rc = pool_stage(ctx, (size_t)n * 4); if (rc) return rc;
+    dIdx = (int32_t*)ctx->poolStage;
+    CK(cudaMemcpyAsync(dIdx, indices, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    // `rank` is by-id scratch that only lives inside a frame
+    k_pool_mark<<<blocks_for(n, 256), 256, 0, st>>>(n, dIdx, ctx->rank, true);
+    k_pool_mark<<<blocks_for(n, 256), 256, 0, st>>>(n, dIdx, ctx->rank, false);
+  }
+  int rc = sys_tiles(ctx, n); if (rc) return rc;
+  const unsigned blocks = blocks_for(n, SYS_TILE);
+  k_pool_despawn_count<<<blocks, SYS_TILE, 0, st>>>(n, dIdx, p->start, ctx->rank, ctx->d.F, ctx->sysTileCount);
+  k_tile_scan<<<1, 1024, 0, st>>>(ctx->sysTileCount, ctx->sysTilePrefix, blocks, ctx->poolScalars);
+  k_pool_despawn_emit<<<blocks, SYS_TILE, 0, st>>>(n, p->count, p->components, dIdx, p->start, ctx->rank, ctx->d.F,
+                                                   ctx->sysTilePrefix, p->freeList, p->st);
+  k_pool_despawn_end<<<1, 32, 0, st>>>(ctx->poolScalars, p->count, p->st, ctx->poolScalars + 1);
+  CK(cudaGetLastError());
+  uint32_t cnt = 0; PoolState ps;
+  CK(cudaMemcpyAsync(&cnt, ctx->poolScalars + 1, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&ps, p->st, sizeof(ps), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->spatialValid = false;
+  if (despawned) *despawned = cnt;
+  if (ps.overflow) return fail(ctx, WEED_E_OVERFLOW, "free list overflow: entities were despawned that the pool had never handed out");
+  return WEED_OK;
+}
+
+extern "C" int weed_pool_despawn(weed_ctx* ctx, uint32_t pool, const int32_t* indices, uint32_t n, uint32_t* despawned_out) {
+  GUARD(ctx);
+  weed_ctx::Pool* p;
+  int rc = pool_get(ctx, pool, &p); if (rc) return rc;
+  if (despawned_out) *despawned_out = 0;
+  if (n == 0) return WEED_OK;
+  if (!indices) return WEED_E_INVALID;
+  return pool_despawn(ctx, p, indices, n, despawned_out);
+}
+
+extern "C" int weed_pool_despawn_all(weed_ctx* ctx, uint32_t pool, uint32_t* despawned_out) {
+  GUARD(ctx);
+  weed_ctx::Pool* p;
+  int rc = pool_get(ctx, pool, &p); if (rc) return rc;
+  return pool_despawn(ctx, p, nullptr, p->count, despawned_out);
+}
+
+extern "C" int weed_pool_stats(weed_ctx* ctx, uint32_t pool, uint32_t* total, uint32_t* available) {
+  GUARD(ctx);
+  weed_ctx::Pool* p;
+  int rc = pool_get(ctx, pool, &p); if (rc) return rc;
+  PoolState ps;
+  CK(cudaMemcpyAsync(&ps, p->st, sizeof(ps), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total) *total = p->count;
+  if (available) *available = (uint32_t)(ps.top + 1);
   return WEED_OK;
 }

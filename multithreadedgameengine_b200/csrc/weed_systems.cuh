@@ -316,3 +316,119 @@ k_shadow_emit(ShadowParams p, ShadowIn in, const uint8_t* __restrict__ F, const 
 }
 
 }  // namespace weed
+
+// =============================================================================================
+// f4: spawn / despawn pools (src/core/gameObject.js:794-951, 668-690, 1001-1034)
+// =============================================================================================
+// One pool per entity class (a contiguous index range).  The free list is the reference's LIFO
+// stack with its interleaved initial order (:794-833); a batch of n spawns pops what n
+// sequential spawn() calls would pop, a batch of despawns pushes what n sequential despawn()
+// calls would push (inactive entities and repeats inside the batch are skipped, :669-670).
+namespace weed {
+
+struct PoolState { int32_t top; uint32_t overflow; };
+static constexpr uint32_t POOL_HAS_RIGIDBODY = 1u, POOL_HAS_COLLIDER = 2u;
+
+// :818-831: offsets 0..7, each walking the range with stride 8
+__global__ void __launch_bounds__(256)
+k_pool_init(uint32_t start, uint32_t count, int32_t* __restrict__ freeList, PoolState* st) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;     // write index
+  if (w == 0) { st->top = (int32_t)count - 1; st->overflow = 0; }
+  if (w >= count) return;
+  // entries of offset o occupy [base(o), base(o) + len(o)), len(o) = ceil((count - o) / 8)
+  uint32_t base = 0, o = 0;
+  for (; o < 8; o++) {
+    const uint32_t len = count > o ? (count - o + 7) / 8 : 0;
+    if (w < base + len) break;
+    base += len;
+  }
+  freeList[w] = (int32_t)(start + o + 8u * (w - base));
+}
+
+struct SpawnRec { float x, y, vx, vy; };
+
+// :878-945 for record k of the batch
+__global__ void __launch_bounds__(256)
+k_pool_spawn(uint32_t n, uint32_t components, const SpawnRec* __restrict__ recs, const int32_t* __restrict__ freeList,
+             const PoolState* __restrict__ st, ById d, int32_t* __restrict__ indicesOut) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int32_t slot = st->top - (int32_t)k;                    // :876 freeList[freeListTop--]
+  if (slot < 0) { indicesOut[k] = -1; return; }                  // :868-873 pool exhausted
+  const int32_t i = freeList[slot];
+  indicesOut[k] = i;
+  const SpawnRec r = recs[k];
+  uint32_t f = d.F[i];
+  float4 dp = d.DP[i];
+  dp.x = r.x; dp.y = r.y;                                        // :901-905, then spawnConfig (:927-931)
+  if (components & POOL_HAS_RIGIDBODY) {                         // :888-899
+    f |= F_RB_ACTIVE;
+    d.ACC[i] = make_float2(0.f, 0.f);
+    d.V[i] = make_float4(r.vx, r.vy, 0.f, 0.f);
+    reinterpret_cast<float*>(d.AT + i)[3] = 0.f;                 // velocityAngle
+    dp.z = fround(dsub((double)r.x, (double)r.vx));              // :936-939
+    dp.w = fround(dsub((double)r.y, (double)r.vy));
+  }
+  if (components & POOL_HAS_COLLIDER) f |= F_C_ACTIVE;           // :907-909
+  d.DP[i] = dp;
+  d.F[i] = (uint8_t)(f | F_T_ACTIVE);                            // :948
+}
+__global__ void k_pool_spawn_end(uint32_t n, PoolState* st) {
+  if (threadIdx.x == 0) { const int32_t t = st->top - (int32_t)n; st->top = t < -1 ? -1 : t; }
+}
+
+// despawn pass 1/2: first occurrence of every index in the batch (scratch is a by-id u32 array)
+__global__ void __launch_bounds__(256)
+k_pool_mark(uint32_t n, const int32_t* __restrict__ indices, uint32_t* __restrict__ scratch, bool reset) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  if (reset) scratch[indices[k]] = 0xFFFFFFFFu;
+  else atomicMin(&scratch[indices[k]], k);
+}
+__device__ __forceinline__ bool pool_gone(uint32_t k, uint32_t n, const int32_t* __restrict__ indices, uint32_t start,
+                                          const uint32_t* __restrict__ scratch, const uint8_t* __restrict__ F, int32_t& i) {
+  if (k >= n) return false;
+  i = indices ? indices[k] : (int32_t)(start + k);               // despawnAll walks the range (:1013)
+  if (indices && scratch[i] != k) return false;                  // a repeat: inactive by then (:669-670)
+  return (F[i] & F_T_ACTIVE) != 0;
+}
+__global__ void __launch_bounds__(SYS_TILE)
+k_pool_despawn_count(uint32_t n, const int32_t* __restrict__ indices, uint32_t start, const uint32_t* __restrict__ scratch,
+                     const uint8_t* __restrict__ F, uint32_t* __restrict__ tileCount) {
+  __shared__ uint32_t s_warp[SYS_TILE / 32];
+  int32_t i;
+  const uint32_t g = pool_gone(blockIdx.x * blockDim.x + threadIdx.x, n, indices, start, scratch, F, i);
+  uint32_t tot;
+  block_exclusive(g, s_warp, tot);
+  if (threadIdx.x == 0) tileCount[blockIdx.x] = tot;
+}
+// :678-689: flags off, index pushed (freeList[++freeListTop] = index) in batch order
+__global__ void __launch_bounds__(SYS_TILE)
+k_pool_despawn_emit(uint32_t n, uint32_t capacity, uint32_t components, const int32_t* __restrict__ indices, uint32_t start,
+                    const uint32_t* __restrict__ scratch, uint8_t* __restrict__ F, const uint32_t* __restrict__ tilePrefix,
+                    int32_t* __restrict__ freeList, PoolState* st) {
+  __shared__ uint32_t s_warp[SYS_TILE / 32];
+  int32_t i = 0;
+  const uint32_t g = pool_gone(blockIdx.x * blockDim.x + threadIdx.x, n, indices, start, scratch, F, i);
+  uint32_t tot;
+  const uint32_t off = tilePrefix[blockIdx.x] + block_exclusive(g, s_warp, tot);
+  __syncthreads();                                               // every pool_gone read F before any write
+  if (!g) return;
+  uint32_t clear = F_T_ACTIVE;
+  if (components & POOL_HAS_RIGIDBODY) clear |= F_RB_ACTIVE;
+  if (components & POOL_HAS_COLLIDER) clear |= F_C_ACTIVE;
+  F[i] = (uint8_t)(F[i] & ~clear);
+  const int64_t pos = (int64_t)st->top + 1 + off;
+  if (pos < (int64_t)capacity) freeList[pos] = i;
+  else st->overflow = 1;                                         // JS: out-of-bounds typed-array store is dropped
+}
+__global__ void k_pool_despawn_end(const uint32_t* total, uint32_t capacity, PoolState* st, uint32_t* despawnedOut) {
+  if (threadIdx.x == 0) {
+    *despawnedOut = *total;
+    int64_t t = (int64_t)st->top + *total;
+    if (t > (int64_t)capacity - 1) { t = (int64_t)capacity - 1; st->overflow = 1; }
+    st->top = (int32_t)t;
+  }
+}
+
+}  // namespace weed

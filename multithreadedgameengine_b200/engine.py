@@ -297,6 +297,41 @@ class GameEngine:
         out["count"] = int(n.value)
         return out
 
+    # ---- spawn / despawn pools ---------------------------------------------------
+    def create_pool(self, startIndex, totalCount, rigidBody=True, collider=True):
+        """One entity class = one pool (GameObject.initializeFreeList, gameObject.js:794-833)."""
+        pid = C.c_uint32(0)
+        comps = (B.POOL_HAS_RIGIDBODY if rigidBody else 0) | (B.POOL_HAS_COLLIDER if collider else 0)
+        B.check(self.ctx, B.lib().weed_pool_create(self.ctx, int(startIndex), int(totalCount), comps, C.byref(pid)))
+        return int(pid.value)
+
+    def spawn(self, pool, records):
+        """GameObject.spawn (:840-951) for a batch: records = float32[n,4] (x, y, vx, vy).  Returns
+        the entity indices (-1 where the pool was exhausted).  Host columns are stale until
+        downloaded."""
+        rec = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, 4)
+        out = np.full(len(rec), -1, np.int32)
+        B.check(self.ctx, B.lib().weed_pool_spawn(self.ctx, int(pool), rec.ctypes.data, len(rec), out.ctypes.data))
+        return out
+
+    def despawn(self, pool, indices):
+        """GameObject.despawn (:668-690) for a batch, in order.  Returns how many were active."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        n = C.c_uint32(0)
+        B.check(self.ctx, B.lib().weed_pool_despawn(self.ctx, int(pool), idx.ctypes.data, len(idx), C.byref(n)))
+        return int(n.value)
+
+    def despawn_all(self, pool):
+        """GameObject.despawnAll (:1001-1034)."""
+        n = C.c_uint32(0)
+        B.check(self.ctx, B.lib().weed_pool_despawn_all(self.ctx, int(pool), C.byref(n)))
+        return int(n.value)
+
+    def pool_stats(self, pool):
+        t, a = C.c_uint32(0), C.c_uint32(0)
+        B.check(self.ctx, B.lib().weed_pool_stats(self.ctx, int(pool), C.byref(t), C.byref(a)))
+        return {"total": int(t.value), "available": int(a.value), "active": int(t.value) - int(a.value)}
+
     def updatePhysicsConfig(self, partial):
         """gameEngine.js:1304-1325 -> applyPhysicsConfig + validatePhysicsConfig."""
         phys = self.config["physics"]

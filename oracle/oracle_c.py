@@ -69,8 +69,55 @@ def lib():
         L.wo_screen_visibility.argtypes = [C.c_int32] + [C.c_void_p] * 3 + [C.c_double] * 5 + [C.c_void_p] * 3
         L.wo_shadow_sprites.restype = C.c_int32
         L.wo_shadow_sprites.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 3 + [C.c_void_p] * 8
+        L.wo_pool_create.restype = C.c_void_p
+        L.wo_pool_create.argtypes = [C.c_int32, C.c_int32, C.c_int, C.c_int]
+        L.wo_pool_destroy.argtypes = [C.c_void_p]
+        L.wo_pool_available.restype = C.c_int32
+        L.wo_pool_available.argtypes = [C.c_void_p]
+        L.wo_pool_spawn.restype = C.c_int32
+        L.wo_pool_spawn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 4
+        L.wo_pool_despawn.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.wo_pool_despawn_all.restype = C.c_int32
+        L.wo_pool_despawn_all.argtypes = [C.c_void_p, C.c_void_p]
+        L.wo_pool_free_list.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+class PoolC:
+    """GameObject.initializeFreeList / spawn / despawn / despawnAll (gameObject.js:794-951, 668-690,
+    1001-1034) over a dict of numpy columns keyed like OracleC.col."""
+    _KEYS = ["T.active", "RB.active", "C.active", "T.x", "T.y", "RB.vx", "RB.vy", "RB.ax", "RB.ay", "RB.px", "RB.py",
+             "RB.speed", "RB.velocityAngle"]
+
+    def __init__(self, col, startIndex, totalCount, rigidBody=True, collider=True):
+        self.col = col
+        self.total = totalCount
+        self.h = lib().wo_pool_create(int(startIndex), int(totalCount), int(rigidBody), int(collider))
+        self._cols = (C.c_void_p * len(self._KEYS))(*[col[k].ctypes.data for k in self._KEYS])
+
+    def spawn(self, records):
+        rec = np.asarray(records, np.float32).reshape(-1, 4)
+        return np.array([lib().wo_pool_spawn(self.h, self._cols, *[float(v) for v in r]) for r in rec], np.int32)
+
+    def despawn(self, indices):
+        return sum(lib().wo_pool_despawn(self.h, self._cols, int(i)) for i in indices)
+
+    def despawn_all(self):
+        return int(lib().wo_pool_despawn_all(self.h, self._cols))
+
+    def available(self):
+        return int(lib().wo_pool_available(self.h))
+
+    def free_list(self):
+        out = np.zeros(self.total, np.int32)
+        lib().wo_pool_free_list(self.h, out.ctypes.data)
+        return out[:self.available()]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().wo_pool_destroy(self.h)
+            self.h = None
 
 
 class CollisionEventsC:

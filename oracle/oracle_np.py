@@ -572,3 +572,63 @@ def shadow_sprites_np(maxNeighbors, neighborData, distanceData, transformActive,
             mine += 1
     out["count"] = idx
     return out
+
+
+class PoolNP:
+    """GameObject spawn pool (gameObject.js:794-951, 668-690, 1001-1034) with a Python list as the
+    free-list stack."""
+
+    def __init__(self, col, startIndex, totalCount, rigidBody=True, collider=True):
+        self.col, self.start, self.total = col, startIndex, totalCount
+        self.rb, self.cl = rigidBody, collider
+        self.free = [startIndex + i for offset in range(8) for i in range(offset, totalCount, 8)]   # :818-832
+
+    def spawn(self, records):
+        out = []
+        c = self.col
+        for x, y, vx, vy in np.asarray(records, np.float32).reshape(-1, 4):
+            if not self.free:
+                out.append(-1)
+                continue
+            i = self.free.pop()
+            if self.rb:
+                c["RB.active"][i] = 1
+                for k in ("RB.ax", "RB.ay", "RB.speed", "RB.velocityAngle"):
+                    c[k][i] = 0
+                c["RB.vx"][i] = vx
+                c["RB.vy"][i] = vy
+            if self.cl:
+                c["C.active"][i] = 1
+            c["T.x"][i] = x
+            c["T.y"][i] = y
+            if self.rb:
+                c["RB.px"][i] = F32(float(c["T.x"][i]) - float(c["RB.vx"][i]))
+                c["RB.py"][i] = F32(float(c["T.y"][i]) - float(c["RB.vy"][i]))
+            c["T.active"][i] = 1
+            out.append(i)
+        return np.array(out, np.int32)
+
+    def despawn(self, indices):
+        n = 0
+        c = self.col
+        for i in indices:
+            if not c["T.active"][i]:
+                continue
+            c["T.active"][i] = 0
+            if self.rb:
+                c["RB.active"][i] = 0
+            if self.cl:
+                c["C.active"][i] = 0
+            if len(self.free) < self.total:
+                self.free.append(int(i))
+            n += 1
+        return n
+
+    def despawn_all(self):
+        return self.despawn([i for i in range(self.start, self.start + self.total) if self.col["T.active"][i]])
+
+    def available(self):
+        return len(self.free)
+
+    def free_list(self):
+        return np.array(self.free, np.int32)

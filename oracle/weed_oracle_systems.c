@@ -163,3 +163,69 @@ WO_EXPORT int32_t wo_shadow_sprites(int32_t entityCount, int32_t maxNeighbors, c
   for (int32_t i = shadowIdx; i < maxShadowSprites; i++) shadowActive[i] = 0;   /* :1002-1004 */
   return shadowIdx;
 }
+
+/* ---- f4: spawn / despawn pools (src/core/gameObject.js:794-951, 668-690, 1001-1034) -------- */
+/* The oracle works on plain column pointers (the SAB views the reference's accessors write). */
+typedef struct {
+  int32_t startIndex, totalCount, freeListTop;
+  int32_t* freeList;
+  int hasRigidBody, hasCollider;
+} wo_pool;
+
+WO_EXPORT wo_pool* wo_pool_create(int32_t startIndex, int32_t totalCount, int hasRigidBody, int hasCollider) {
+  wo_pool* p = calloc(1, sizeof(wo_pool));
+  p->startIndex = startIndex; p->totalCount = totalCount;
+  p->hasRigidBody = hasRigidBody; p->hasCollider = hasCollider;
+  p->freeList = malloc(sizeof(int32_t) * (size_t)totalCount);          /* :802 */
+  p->freeListTop = totalCount - 1;                                     /* :803 */
+  const int interleaveFactor = 8;                                      /* :821 */
+  int32_t writeIndex = 0;
+  for (int offset = 0; offset < interleaveFactor; offset++)            /* :828-832 */
+    for (int32_t i = offset; i < totalCount; i += interleaveFactor) p->freeList[writeIndex++] = startIndex + i;
+  return p;
+}
+WO_EXPORT void wo_pool_destroy(wo_pool* p) { if (p) { free(p->freeList); free(p); } }
+WO_EXPORT int32_t wo_pool_available(const wo_pool* p) { return p->freeListTop + 1; }   /* :968-969 */
+
+typedef struct {
+  uint8_t *tActive, *rbActive, *cActive;
+  float *x, *y, *vx, *vy, *ax, *ay, *px, *py, *speed, *velocityAngle;
+} wo_pool_cols;
+
+/* GameObject.spawn with spawnConfig {x, y, vx, vy}; returns the index or -1 (:868-873) */
+WO_EXPORT int32_t wo_pool_spawn(wo_pool* p, const wo_pool_cols* c, float x, float y, float vx, float vy) {
+  if (p->freeListTop < 0) return -1;
+  const int32_t i = p->freeList[p->freeListTop--];                     /* :876 */
+  if (p->hasRigidBody) {                                               /* :888-899 */
+    c->rbActive[i] = 1;
+    c->ax[i] = 0; c->ay[i] = 0; c->vx[i] = 0; c->vy[i] = 0; c->speed[i] = 0; c->velocityAngle[i] = 0;
+    c->px[i] = 0; c->py[i] = 0;
+  }
+  c->x[i] = 0; c->y[i] = 0;                                            /* :901-905 */
+  if (p->hasCollider) c->cActive[i] = 1;                               /* :907-909 */
+  c->x[i] = x; c->y[i] = y;                                            /* :927-931 spawnConfig */
+  if (p->hasRigidBody) {
+    c->vx[i] = vx; c->vy[i] = vy;
+    c->px[i] = (float)((double)c->x[i] - (double)c->vx[i]);            /* :936-939 */
+    c->py[i] = (float)((double)c->y[i] - (double)c->vy[i]);
+  }
+  c->tActive[i] = 1;                                                   /* :948 */
+  return i;
+}
+/* GameObject.despawn (:668-690); returns 1 when the entity was active */
+WO_EXPORT int wo_pool_despawn(wo_pool* p, const wo_pool_cols* c, int32_t index) {
+  if (c->tActive[index] == 0) return 0;                                /* :670 */
+  c->tActive[index] = 0;                                               /* :679-681 */
+  if (p->hasRigidBody) c->rbActive[index] = 0;
+  if (p->hasCollider) c->cActive[index] = 0;
+  ++p->freeListTop;                                                    /* :688 */
+  if (p->freeListTop < p->totalCount) p->freeList[p->freeListTop] = index;   /* an out-of-range typed-array store is dropped */
+  return 1;
+}
+WO_EXPORT int32_t wo_pool_despawn_all(wo_pool* p, const wo_pool_cols* c) {   /* :1001-1034 */
+  int32_t n = 0;
+  for (int32_t i = p->startIndex; i < p->startIndex + p->totalCount; i++)
+    if (c->tActive[i]) n += wo_pool_despawn(p, c, i);
+  return n;
+}
+WO_EXPORT void wo_pool_free_list(const wo_pool* p, int32_t* out) { memcpy(out, p->freeList, sizeof(int32_t) * (size_t)p->totalCount); }

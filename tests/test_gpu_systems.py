@@ -92,3 +92,47 @@ def test_systems_report_state_errors():
     with pytest.raises(B.WeedError):
         eng.shadows()            # no columns uploaded, no visibility pass yet
     eng.close()
+
+
+def test_pools_spawn_and_despawn_like_the_reference():
+    """batches of GameObject.spawn / despawn / despawnAll on the device against the
+    sequential CPU restatement — same indices, same columns, same free-list order — and the
+    simulation keeps matching the oracle afterwards."""
+    from helpers import make_oracle
+    from oracle.oracle_c import OracleC, PoolC
+    from test_gpu_parity import ALL_DL, compare_state
+
+    cfg, cols = scenes.balls_synthetic(3000, (1200.0, 600.0), 24.0, 48, 2, (4.0, 9.0), 24.0, seed=17)
+    N = cfg["entityCount"]
+    # entities 1001..3000 form one class that starts inactive (the engine spawns them later)
+    for k in ("T.active", "RB.active", "C.active"):
+        cols[k][1001:] = 0
+    eng = make_engine(cfg, cols)
+    ora = make_oracle(OracleC, cfg, cols)
+    pool = eng.create_pool(1001, 2000)
+    opool = PoolC(ora.col, 1001, 2000)
+    rng = np.random.default_rng(23)
+    live = []
+    for step in range(10):
+        rec = np.column_stack([rng.uniform(20, 1180, 150), rng.uniform(20, 580, 150), rng.normal(0, 2, 150),
+                               rng.normal(0, 2, 150)]).astype(np.float32)
+        got, want = eng.spawn(pool, rec), opool.spawn(rec)
+        assert np.array_equal(got, want), step
+        live += got.tolist()
+        if step % 3 == 2:
+            pick = rng.choice(live, 120).tolist()          # repeats and already-despawned entities
+            assert eng.despawn(pool, pick) == opool.despawn(pick)
+            live = [i for i in live if i not in set(pick)]
+        assert eng.pool_stats(pool)["available"] == opool.available()
+        eng.step(1.0, 0, ALL_DL)
+        ora.step(1.0, 1)
+        compare_state(eng, ora, f"step {step}")
+    assert eng.despawn_all(pool) == opool.despawn_all() > 0
+    assert eng.pool_stats(pool) == {"total": 2000, "available": 2000, "active": 0}
+    # drain: the whole free-list order must agree, then the pool is exhausted
+    z = np.zeros((2005, 4), np.float32)
+    got, want = eng.spawn(pool, z), opool.spawn(z)
+    assert np.array_equal(got, want) and (got[-5:] == -1).all() and (got[:2000] >= 1001).all()
+    with pytest.raises(B.WeedError):
+        eng.despawn(pool, [5])                               # not an index of this pool
+    eng.close()

@@ -140,3 +140,61 @@ def test_shadow_hand_derived():
         assert o["scaleY"][0] == np.float32((0.3 + (50 * 0.00390625) * 0.9) * (10 * 0.025))
         assert o["alpha"][0] == np.float32(200 / 5000)
         assert o["rotation"][0] == np.float32(np.arctan2(40.0, 30.0) - 1.5707963267948966)
+
+
+# ---- f4: spawn / despawn pools (gameObject.js:794-951, 668-690, 1001-1034) ----------------------
+def blank_cols(N):
+    c = {k: np.zeros(N, np.uint8) for k in ("T.active", "RB.active", "C.active")}
+    for k in ("T.x", "T.y", "RB.vx", "RB.vy", "RB.ax", "RB.ay", "RB.px", "RB.py", "RB.speed", "RB.velocityAngle"):
+        c[k] = np.full(N, 7.0, np.float32)      # stale garbage spawn() has to reset
+    return c
+
+
+def test_pool_hand_derived_interleaved_order_and_spawn_state():
+    """count 20 at startIndex 100: the free list is written offset by offset (0,8,16, 1,9,17, ...
+    7,15) and popped from the END: 115, 107, 114, 106, 113 (gameObject.js:818-832, :876)."""
+    from oracle.oracle_c import PoolC
+    from oracle.oracle_np import PoolNP
+    for cls in (PoolC, PoolNP):
+        col = blank_cols(200)
+        p = cls(col, 100, 20)
+        got = p.spawn([[10.5, 20.25, 1.5, -2.0]] * 5)
+        assert got.tolist() == [115, 107, 114, 106, 113]
+        i = 115
+        assert col["T.active"][i] == 1 and col["RB.active"][i] == 1 and col["C.active"][i] == 1
+        assert col["T.x"][i] == 10.5 and col["T.y"][i] == 20.25 and col["RB.vx"][i] == 1.5 and col["RB.vy"][i] == -2.0
+        assert col["RB.px"][i] == 9.0 and col["RB.py"][i] == 22.25          # px = x - vx (:936-939)
+        assert col["RB.ax"][i] == 0 and col["RB.speed"][i] == 0 and col["RB.velocityAngle"][i] == 0
+        assert col["T.x"][116] == 7.0 and col["T.active"][116] == 0           # untouched
+        assert p.available() == 15
+        # despawn pushes in call order; a second despawn of the same entity is ignored (:669-670)
+        assert p.despawn([107, 115, 107]) == 2
+        assert p.spawn([[0, 0, 0, 0]] * 2).tolist() == [115, 107]
+        assert p.despawn_all() == 5 and p.available() == 20
+        # despawnAll walks the index range upward (:1013), so the stack now ends ..., 113, 114, 115
+        assert p.spawn([[0, 0, 0, 0]] * 3).tolist() == [115, 114, 113]
+
+
+def test_pool_c_equals_np_random_sequences_and_exhaustion():
+    from oracle.oracle_c import PoolC
+    from oracle.oracle_np import PoolNP
+    rng = np.random.default_rng(13)
+    ca, cb = blank_cols(600), blank_cols(600)
+    a, b = PoolC(ca, 50, 333), PoolNP(cb, 50, 333)
+    live = []
+    for step in range(60):
+        if rng.random() < 0.55:
+            rec = rng.normal(0, 50, (int(rng.integers(1, 80)), 4)).astype(np.float32)
+            ia, ib = a.spawn(rec), b.spawn(rec)
+            assert np.array_equal(ia, ib)
+            live += [int(i) for i in ia if i >= 0]
+        elif live:
+            k = int(rng.integers(1, len(live) + 1))
+            pick = rng.choice(live, k).tolist()            # with repeats
+            assert a.despawn(pick) == b.despawn(pick)
+            live = [i for i in live if i not in set(pick)]
+        assert a.available() == b.available() and np.array_equal(a.free_list(), b.free_list())
+        for key in ca:
+            assert np.array_equal(ca[key].view(np.uint8), cb[key].view(np.uint8)), (step, key)
+    ia = a.spawn(np.zeros((400, 4), np.float32))
+    assert np.array_equal(ia, b.spawn(np.zeros((400, 4), np.float32))) and (ia == -1).any() and a.available() == 0
