@@ -212,7 +212,7 @@ def run_ours(args):
         dist.barrier()
     from multithreadedgameengine_b200 import binding as B
     from multithreadedgameengine_b200.engine import GameEngine
-    from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs, replan_from_times
+    from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs, replan_from_times, row_costs
 
     name = args.workload
     cfg, cols = workload(name, args.entities)      # every rank builds the same seeded scene
@@ -225,6 +225,7 @@ def run_ours(args):
     if world > 1 and args.autobalance:
         # measured-feedback balancing (outside the timed region, like an autotuning pass): run a
         # few frames from the start scene, gather every slab's kernel time, move the cuts, restart
+        row_weight = row_costs(cfg, cols)[0]
         for it in range(args.autobalance):
             with torch.cuda.stream(stream):
                 sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan)
@@ -245,7 +246,7 @@ def run_ours(args):
             allt = [torch.zeros_like(tt) for _ in range(world)]
             dist.all_gather(allt, tt)
             times = [float(t.item()) for t in allt]
-            plan = (replan_from_times(plan[0], times), plan[1])
+            plan = (replan_from_times(plan[0], times, row_weight), plan[1])
         balance_note = f"cost model + {args.autobalance} measured-feedback re-plans before the timed run"
 
     def make(flags=0):

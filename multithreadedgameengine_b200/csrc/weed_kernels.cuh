@@ -999,13 +999,18 @@ static_assert(sizeof(SlabRec) == 64, "slab record must be 64 bytes");
 
 // device-resident state of the exchange: the host never has to read it between frames
 struct SlabCounters {
+  // words the pack / drop kernels update with atomics: a 128-byte line of their own, so that the
+  // per-thread read of `top` below is not served by a line under atomic traffic
   uint32_t nLow, nHigh;     // records packed for the low / high neighbour this frame
   uint32_t nHoles;          // free slots found by the drop pass
+  uint32_t owned;           // entities owned during the frame being packed
+  uint32_t _hot[28];
   uint32_t top;             // slots in use (persistent)
   uint32_t overflow;        // sticky: bit0 exchange quota exceeded, bit1 entity table full
-  uint32_t owned;           // entities owned during the frame being packed
   uint32_t lastOwned, lastLow, lastHigh, lastFromLow, lastFromHigh;   // previous exchange, for reporting
+  uint32_t _pad[25];
 };
+static_assert(sizeof(SlabCounters) == 256, "two 128-byte lines");
 
 __device__ __forceinline__ bool present_row(const GridDims& g, const ById& d, uint32_t i, int32_t& row) {
   const uint32_t f = d.F[i];
@@ -1022,16 +1027,48 @@ __global__ void __launch_bounds__(256)
 k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __restrict__ low,
             SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sc->top) return;
-  const uint32_t k = key[i];
-  if (k == KEY_INVALID) return;
-  const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
-  if (row0 < g.slabBegin || row0 >= g.slabEnd) return;          // not authoritative here
-  atomicAdd(&sc->owned, 1u);
+  const uint32_t lane = threadIdx.x & 31;
+  bool owned = false;
+  if (i < sc->top) {
+    const uint32_t k = key[i];
+    if (k != KEY_INVALID) {
+      const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
+      owned = row0 >= g.slabBegin && row0 < g.slabEnd;            // authoritative here during the frame
+    }
+  }
+  // one counter update per BLOCK: same-address atomics serialise at ~2 ns each, and one per warp
+  // is still 30 000 of them per million entities
+  __shared__ uint32_t s_owned[256 / 32];
+  const uint32_t nOwned = __reduce_add_sync(0xffffffffu, (uint32_t)owned);
+  if (lane == 0) s_owned[threadIdx.x >> 5] = nOwned;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 256 / 32; w++) t += s_owned[w];
+    if (t) atomicAdd(&sc->owned, t);
+  }
+  bool toLow = false, toHigh = false;
   int32_t row;
-  if (!present_row(g, d, i, row)) return;
-  const bool toLow = g.slabBegin > 0 && row < g.slabBegin + g.slabHalo;
-  const bool toHigh = g.slabEnd < g.rows && row >= g.slabEnd - g.slabHalo;
+  if (owned && present_row(g, d, i, row)) {
+    toLow = g.slabBegin > 0 && row < g.slabBegin + g.slabHalo;
+    toHigh = g.slabEnd < g.rows && row >= g.slabEnd - g.slabHalo;
+  }
+  // positions in the two exchange buffers: ballot inside the warp, shared memory across the
+  // warps, ONE atomic per block and direction
+  __shared__ uint32_t s_low[256 / 32], s_high[256 / 32], s_base[2];
+  const uint32_t mLow = __ballot_sync(0xffffffffu, toLow), mHigh = __ballot_sync(0xffffffffu, toHigh);
+  const uint32_t warp = threadIdx.x >> 5;
+  if (lane == 0) { s_low[warp] = (uint32_t)__popc(mLow); s_high[warp] = (uint32_t)__popc(mHigh); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tl = 0, th = 0;
+    for (int w = 0; w < 256 / 32; w++) { tl += s_low[w]; th += s_high[w]; }
+    s_base[0] = tl ? atomicAdd(&sc->nLow, tl) : 0u;
+    s_base[1] = th ? atomicAdd(&sc->nHigh, th) : 0u;
+  }
+  __syncthreads();
+  uint32_t baseLow = s_base[0], baseHigh = s_base[1];
+  for (uint32_t w = 0; w < warp; w++) { baseLow += s_low[w]; baseHigh += s_high[w]; }
   if (!toLow && !toHigh) return;
   SlabRec r;
   r.gid = d.GID[i];
@@ -1039,12 +1076,13 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
   const float2 a = d.ACC[i];
   r.ax = a.x; r.ay = a.y;
   r.dp = d.DP[i]; r.at = d.AT[i]; r.v = d.V[i];
+  const uint32_t below = (1u << lane) - 1u;
   if (toLow) {
-    const uint32_t p = atomicAdd(&sc->nLow, 1u);
+    const uint32_t p = baseLow + (uint32_t)__popc(mLow & below);
     if (p < quota) low[1 + p] = r;
   }
   if (toHigh) {
-    const uint32_t p = atomicAdd(&sc->nHigh, 1u);
+    const uint32_t p = baseHigh + (uint32_t)__popc(mHigh & below);
     if (p < quota) high[1 + p] = r;
   }
 }
@@ -1059,18 +1097,27 @@ __global__ void k_slab_headers(SlabRec* __restrict__ low, SlabRec* __restrict__ 
 __global__ void __launch_bounds__(256)
 k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t* __restrict__ holes, SlabCounters* sc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sc->top) return;
-  const uint32_t k = key[i];
-  bool keep = false;
-  if (k != KEY_INVALID) {
-    const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
-    keep = row0 >= g.slabBegin && row0 < g.slabEnd;
-  } else {
-    keep = (d.F[i] & F_T_ACTIVE) != 0;    // active but never in the grid (NaN position): stays where it is
+  const uint32_t lane = threadIdx.x & 31;
+  bool drop = false;
+  if (i < sc->top) {
+    const uint32_t k = key[i];
+    bool keep;
+    if (k != KEY_INVALID) {
+      const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
+      keep = row0 >= g.slabBegin && row0 < g.slabEnd;
+    } else {
+      keep = (d.F[i] & F_T_ACTIVE) != 0;    // active but never in the grid (NaN position): stays where it is
+    }
+    drop = !keep;
   }
-  if (!keep) {
+  const uint32_t m = __ballot_sync(0xffffffffu, drop);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&sc->nHoles, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (drop) {
     d.F[i] = 0;
-    holes[atomicAdd(&sc->nHoles, 1u)] = i;
+    holes[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
   }
 }
 

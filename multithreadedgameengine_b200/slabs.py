@@ -91,15 +91,20 @@ def plan_slabs(cfg, cols, world, balance="cost"):
     return [(cuts[k], cuts[k + 1]) for k in range(world)], halo_rows(cfg, cols)
 
 
-def replan_from_times(blocks, times_ms):
+def replan_from_times(blocks, times_ms, row_weight=None):
     """Measured-feedback balancing: given the frame time of every slab under the current cuts,
-    spread each slab's time uniformly over its rows and cut the cumulative curve into equal
-    parts.  Returns the new (rowBegin, rowEnd) list (same halo)."""
+    spread each slab's time over its rows — in proportion to `row_weight` (the cost model of
+    row_costs, so that dense rows inside a slab keep their share) or uniformly — and cut the
+    cumulative curve into equal parts.  Returns the new (rowBegin, rowEnd) list (same halo)."""
     rows = blocks[-1][1]
     world = len(blocks)
     per_row = np.zeros(rows, dtype=np.float64)
     for (a, b), t in zip(blocks, times_ms):
-        per_row[a:b] = float(t) / max(1, b - a)
+        w = None if row_weight is None else np.asarray(row_weight[a:b], dtype=np.float64)
+        if w is not None and w.sum() > 0:
+            per_row[a:b] = float(t) * w / w.sum()
+        else:
+            per_row[a:b] = float(t) / max(1, b - a)
     cum = np.cumsum(per_row)
     total = float(cum[-1])
     cuts = [0]

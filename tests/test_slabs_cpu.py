@@ -61,6 +61,16 @@ def test_cost_balanced_plan_equalises_estimated_work():
     assert max(per) <= max(per_c) + 1e-6      # never worse than count balancing on its own objective
 
 
+def test_replan_with_row_weights_keeps_dense_rows_heavy():
+    # two slabs of 10 rows; inside the slow first one all the work sits in rows 6-9
+    w = np.ones(20); w[:6] = 0.001; w[6:10] = 10.0
+    new = replan_from_times([(0, 10), (10, 20)], [3.0, 1.0], w)
+    # total 4, half = 2: rows 6, 7, 8 carry 0.75 each -> the cut falls after row 8
+    assert new == [(0, 9), (9, 20)]
+    flat = replan_from_times([(0, 10), (10, 20)], [3.0, 1.0])
+    assert flat[0][1] < new[0][1]                        # uniform spreading would overshoot
+
+
 def test_replan_from_times_moves_cuts_toward_the_slow_slab():
     blocks = [(0, 100), (100, 200), (200, 300), (300, 400)]
     new = replan_from_times(blocks, [1.0, 1.0, 1.0, 3.0])       # the last slab is 3x slower per row
