@@ -151,6 +151,71 @@ static napi_value FetchNeighbors(napi_env env, napi_callback_info info) {
   return nullptr;
 }
 
+// ---- device-side consumers (weed_system_*) --------------------------------------------------
+static void* typed_data(napi_env env, napi_value v) {     // TypedArray -> base pointer (or NULL)
+  napi_valuetype t;
+  if (napi_typeof(env, v, &t) != napi_ok || t != napi_object) return nullptr;
+  bool is = false;
+  if (napi_is_typedarray(env, v, &is) != napi_ok || !is) return nullptr;
+  void* data = nullptr;
+  napi_typedarray_type ty; size_t len; napi_value ab; size_t off;
+  if (napi_get_typedarray_info(env, v, &ty, &len, &data, &ab, &off) != napi_ok) return nullptr;
+  return data;
+}
+
+// collisionEvents(ctx, stateU8, exitI32, forgetPrevious) -> {pairs, entered, stayed, exited}
+// replaces the Set bookkeeping of LogicWorker.processCollisionCallbacks (logic_worker.js:429-526)
+static napi_value CollisionEvents(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value a[4];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  bool forget = false;
+  if (argc > 3) napi_get_value_bool(env, a[3], &forget);
+  weed_collision_event_counts c;
+  const int rc = weed_system_collision_events(ctx, forget ? WEED_EVENTS_FORGET_PREVIOUS : 0u, &c,
+                                              (uint8_t*)typed_data(env, a[1]), (int32_t*)typed_data(env, a[2]));
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  napi_value out, v;
+  NAPI_OK(napi_create_object(env, &out));
+  const struct { const char* k; uint32_t n; } f[] = {{"pairs", c.pairs}, {"entered", c.entered}, {"stayed", c.stayed}, {"exited", c.exited}};
+  for (const auto& e : f) { NAPI_OK(napi_create_uint32(env, e.n, &v)); NAPI_OK(napi_set_named_property(env, out, e.k, v)); }
+  return out;
+}
+
+// screenVisibility(ctx, cameraDataF32, canvasWidth, canvasHeight, screenX, screenY, isItOnScreen)
+// replaces ParticleWorker.updateEntityScreenVisibility (particle_worker.js:1012-1062)
+static napi_value ScreenVisibility(napi_env env, napi_callback_info info) {
+  size_t argc = 7;
+  napi_value a[7];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  const float* cam = (const float*)typed_data(env, a[1]);
+  if (!cam) { napi_throw_error(env, nullptr, "weed_napi: cameraData must be a Float32Array"); return nullptr; }
+  weed_camera c{cam[0], cam[1], cam[2], 0, 0};
+  NAPI_OK(napi_get_value_double(env, a[2], &c.canvasWidth));
+  NAPI_OK(napi_get_value_double(env, a[3], &c.canvasHeight));
+  const int rc = weed_system_screen_visibility(ctx, &c, (float*)typed_data(env, a[4]), (float*)typed_data(env, a[5]),
+                                               (uint8_t*)typed_data(env, a[6]));
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
+// spawn(ctx, pool, recordsF32 /* x, y, vx, vy per entity */, indicesI32)   GameObject.spawn for a batch
+static napi_value Spawn(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value a[4];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+  weed_ctx* ctx = ctx_of(env, a[0]);
+  uint32_t pool;
+  NAPI_OK(napi_get_value_uint32(env, a[1], &pool));
+  napi_typedarray_type ty; size_t len = 0; void* recs = nullptr; napi_value ab; size_t off;
+  NAPI_OK(napi_get_typedarray_info(env, a[2], &ty, &len, &recs, &ab, &off));
+  const int rc = weed_pool_spawn(ctx, pool, (const weed_spawn_record*)recs, (uint32_t)(len / 4), (int32_t*)typed_data(env, a[3]));
+  if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  return nullptr;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor props[] = {
       {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -158,6 +223,9 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"step", nullptr, Step, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"setPhysics", nullptr, SetPhysics, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"fetchNeighbors", nullptr, FetchNeighbors, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"collisionEvents", nullptr, CollisionEvents, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"screenVisibility", nullptr, ScreenVisibility, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"spawn", nullptr, Spawn, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
   return exports;
