@@ -229,7 +229,7 @@ def run_ours(args):
         for it in range(args.autobalance):
             with torch.cuda.stream(stream):
                 sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan)
-                for _ in range(2):
+                for _ in range(args.warmup + args.steps // 2):     # the scene evolves: balance for the frames that get timed
                     sl.step_dist()
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 tsum = 0.0
@@ -247,7 +247,8 @@ def run_ours(args):
             dist.all_gather(allt, tt)
             times = [float(t.item()) for t in allt]
             plan = (replan_from_times(plan[0], times, row_weight), plan[1])
-        balance_note = f"cost model + {args.autobalance} measured-feedback re-plans before the timed run"
+        balance_note = (f"cost model + {args.autobalance} measured-feedback re-plans before the timed run, each measured "
+                        f"{args.warmup + args.steps // 2} frames into the scene (static cuts during the run)")
 
     def make(flags=0):
         if world == 1:
@@ -323,6 +324,14 @@ def run_ours(args):
             local_active = st_t["activeInGrid"]
             kbar_t = st_t["neighborsTotal"] / max(1, local_active)
             (obj_t.close if world > 1 else eng_t.close)()
+        # every rank's frame kernels (sum of the spans, k_substep counted S times): the slab balance
+        kernel_ms_per_rank = None
+        if world > 1 and not args.quick:
+            mine = float(np.nansum(kms) + kms[6] * (S - 1))
+            t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+            allk = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allk, t)
+            kernel_ms_per_rank = [round(float(x.item()), 3) for x in allk]
         top = 4 if args.quick else int(np.argmax(kms))
         F, per_kernel = algorithmic_bytes(kbar_t, S)
         alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
@@ -385,6 +394,7 @@ def run_ours(args):
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
                      "collision_pairs_last_substep": st["collisionPairs"],
                      "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes,
+                     "frame_kernels_ms_per_rank": kernel_ms_per_rank,
                      "slab_balance": balance_note if world > 1 else None})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -408,7 +418,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
-    ap.add_argument("--autobalance", type=int, default=2, help="measured-feedback slab re-plans before timing (N>1)")
+    ap.add_argument("--autobalance", type=int, default=3, help="measured-feedback slab re-plans before timing (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
