@@ -248,14 +248,17 @@ def run_ours(args):
             times = [float(t.item()) for t in allt]
             plan = (replan_from_times(plan[0], times, row_weight), plan[1])
         balance_note = (f"cost model + {args.autobalance} measured-feedback re-plans before the timed run, each measured "
-                        f"{args.warmup + args.steps // 2} frames into the scene (static cuts during the run)")
+                        f"{args.warmup + args.steps // 2} frames into the scene"
+                        + (f"; during the run every cut follows the measured load by up to {args.balance_rows} rows per frame (weed_slab_balance)"
+                           if args.balance_rows else " (static cuts during the run)"))
 
     def make(flags=0):
         if world == 1:
             e = GameEngine(cfg, device=local, flags=flags, stream=stream.cuda_stream, host_neighbor_rows=False)
             e.load_columns(cols)
             return e, e
-        sl = SlabEngine(cfg, cols, rank, world, device=local, flags=flags, stream=stream.cuda_stream, plan=plan)
+        sl = SlabEngine(cfg, cols, rank, world, device=local, flags=flags, stream=stream.cuda_stream, plan=plan,
+                        balance_rows=args.balance_rows)
         return sl, sl.eng
 
     def frames(obj, k):
@@ -324,6 +327,12 @@ def run_ours(args):
             local_active = st_t["activeInGrid"]
             kbar_t = st_t["neighborsTotal"] / max(1, local_active)
             (obj_t.close if world > 1 else eng_t.close)()
+        slab_rows = None
+        if world > 1:
+            t = torch.tensor([slab_st["rowBegin"], slab_st["rowEnd"], slab_st["cutMoves"]], device="cuda", dtype=torch.int64)
+            allr = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            slab_rows = [[int(v) for v in x.tolist()] for x in allr]      # [rowBegin, rowEnd, cutMoves] per rank after the timed run
         # every rank's frame kernels (sum of the spans, k_substep counted S times): the slab balance
         kernel_ms_per_rank = None
         if world > 1 and not args.quick:
@@ -394,7 +403,7 @@ def run_ours(args):
                      "explicit_pairs": st["explicitPairs"], "capped_rows": st["cappedRows"],
                      "collision_pairs_last_substep": st["collisionPairs"],
                      "halo_replica_fraction": halo_frac, "exchange_bytes_per_frame": xbytes,
-                     "frame_kernels_ms_per_rank": kernel_ms_per_rank,
+                     "frame_kernels_ms_per_rank": kernel_ms_per_rank, "slab_rows_begin_end_moves_per_rank": slab_rows,
                      "slab_balance": balance_note if world > 1 else None})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -418,6 +427,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
+    ap.add_argument("--balance-rows", type=int, default=2, help="N>1: rows a cut may move per frame toward the slower slab (weed_slab_balance; 0 = static cuts)")
     ap.add_argument("--autobalance", type=int, default=3, help="measured-feedback slab re-plans before timing (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -376,7 +376,19 @@ typedef struct weed_slab_stats {
   uint32_t owned;                  /* entities owned during the last packed frame            */
   uint32_t sentLow, sentHigh, receivedLow, receivedHigh;   /* records of the last exchange   */
   uint32_t overflow;               /* sticky: 1 = quota exceeded, 2 = table full             */
+  int32_t rowBegin, rowEnd;        /* the rows this context owns in the NEXT frame           */
+  uint32_t cutMoves;               /* times one of its cuts moved (weed_slab_balance)        */
+  uint32_t loadNs;                 /* smoothed device time of its frame kernels              */
 } weed_slab_stats;
+/* Dynamic balancing (SURVEY §8 e: cuts follow the load).  Every message header carries the
+ * sender's smoothed frame time (device %globaltimer around the frame's kernels) and its cuts,
+ * so the two neighbours of a cut decide — on identical numbers, hence identically, without
+ * any extra communication or host involvement — to move it by up to maxShiftRows rows toward
+ * the slower slab when the two times differ by more than hysteresisPercent (0 = 3 %).  The
+ * new cut is known one frame ahead: the exchange that precedes its first frame packs the
+ * bands around it, so the halo rule holds unchanged and results stay bit-identical to the
+ * unpartitioned world whatever the cuts do.  maxShiftRows = 0 (default) keeps the cuts static. */
+int weed_slab_balance(weed_ctx* ctx, uint32_t maxShiftRows, uint32_t hysteresisPercent);
 /* synchronises; returns WEED_E_OVERFLOW if a quota or the table overflowed at any time      */
 int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out);
 

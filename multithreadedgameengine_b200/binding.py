@@ -91,8 +91,9 @@ class ShadowSprites(C.Structure):
 
 
 class SlabStats(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("top", "capacity", "owned", "sentLow", "sentHigh", "receivedLow",
-                                           "receivedHigh", "overflow")]
+    _fields_ = ([(n, C.c_uint32) for n in ("top", "capacity", "owned", "sentLow", "sentHigh", "receivedLow",
+                                            "receivedHigh", "overflow")]
+                + [("rowBegin", C.c_int32), ("rowEnd", C.c_int32), ("cutMoves", C.c_uint32), ("loadNs", C.c_uint32)])
 
 
 class Stats(C.Structure):
@@ -142,6 +143,7 @@ SYMBOLS = {
     "weed_slab_get_gids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "weed_slab_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "weed_slab_balance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "weed_slab_status": (C.c_int, [C.c_void_p, C.POINTER(SlabStats)]),
 }
 SLAB_RECORD_BYTES = 64

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -492,6 +493,9 @@ extern "C" int weed_download(weed_ctx* ctx, uint32_t mask) {
 }
 
 // ---- launches --------------------------------------------------------------------------------
+// slab contexts keep their cuts in device memory (they may move between frames)
+static inline const int32_t* slab_cuts(weed_ctx* ctx) { return ctx->slab ? &ctx->dSlab->curBegin : nullptr; }
+
 static inline unsigned blocks_for(size_t threads, unsigned bs) { return (unsigned)((threads + bs - 1) / bs); }
 
 #define TIME_MARK(ctx, timing, k) do { if (timing) cudaEventRecord((ctx)->ev[k], (ctx)->stream); } while (0)
@@ -512,9 +516,9 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   TIME_MARK(ctx, timing, 3);
   if (waitBeforeBuild) CK(cudaStreamWaitEvent(st, waitBeforeBuild, 0));
   if (integrate)
-    k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+    k_build_slots<true><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf, slab_cuts(ctx));
   else
-    k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+    k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf, slab_cuts(ctx));
   if (recordAfterBuild) CK(cudaEventRecord(recordAfterBuild, st));
   k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
@@ -632,7 +636,7 @@ extern "C" int weed_physics(weed_ctx* ctx, double dtRatio) {
   if (rc) return rc;
   const GridDims& g = ctx->g;
   k_build_slots<true><<<blocks_for(g.N, 256), 256, 0, ctx->stream>>>(g, ctx->dParams, ctx->phys.subStepCount, true, ctx->d, ctx->s,
-                                                                      ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);
+                                                                      ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf, slab_cuts(ctx));
   rc = launch_constraints(ctx, false);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -815,6 +819,9 @@ extern "C" int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t 
   SlabCounters sc;
   memset(&sc, 0, sizeof(sc));
   sc.top = count;
+  sc.curBegin = sc.pendBegin = ctx->g.slabBegin;
+  sc.curEnd = sc.pendEnd = ctx->g.slabEnd;
+  sc.minRows = (uint32_t)std::max(2 * ctx->g.slabHalo, 8);
   CK(cudaMemcpyAsync(ctx->dSlab, &sc, sizeof(sc), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
@@ -836,7 +843,7 @@ extern "C" int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
   if (!dev_low || !dev_high || quota == 0) return fail(ctx, WEED_E_INVALID, "exchange buffers missing");
   k_slab_pack<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, (SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab);
-  k_slab_headers<<<1, 32, 0, ctx->stream>>>((SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab);
+  k_slab_headers<<<1, 32, 0, ctx->stream>>>((SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab, ctx->dCtr);
   CK(cudaGetLastError());
   return WEED_OK;
 }
@@ -854,6 +861,16 @@ extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, const vo
   return WEED_OK;
 }
 
+extern "C" int weed_slab_balance(weed_ctx* ctx, uint32_t maxShiftRows, uint32_t hysteresisPercent) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (maxShiftRows > 8) return fail(ctx, WEED_E_INVALID, "maxShiftRows > 8 (the exchange quota is sized for the halo band)");
+  const uint32_t v[2] = {maxShiftRows, hysteresisPercent ? hysteresisPercent : 3u};
+  CK(cudaMemcpyAsync(&ctx->dSlab->maxShift, v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
 extern "C" int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out) {
   GUARD(ctx);
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
@@ -864,6 +881,7 @@ extern "C" int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out) {
   out->top = sc.top; out->owned = sc.lastOwned; out->sentLow = sc.lastLow; out->sentHigh = sc.lastHigh;
   out->receivedLow = sc.lastFromLow; out->receivedHigh = sc.lastFromHigh; out->overflow = sc.overflow;
   out->capacity = ctx->g.N;
+  out->rowBegin = sc.curBegin; out->rowEnd = sc.curEnd; out->cutMoves = sc.cutMoves; out->loadNs = sc.load;
   if (sc.overflow & 1u) return fail(ctx, WEED_E_OVERFLOW, "slab exchange quota exceeded: " + std::to_string(sc.lastLow) + " / " + std::to_string(sc.lastHigh) + " records");
   if (sc.overflow & 2u) return fail(ctx, WEED_E_OVERFLOW, "slab entity table full (capacity " + std::to_string(ctx->g.N) + ")");
   return WEED_OK;

@@ -91,10 +91,15 @@ __global__ void k_spatial_begin(Counters* ctr) {
     ctr->nCapped = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
+    ctr->tBegin = global_timer_ns();
   }
 }
 __global__ void k_physics_end(Counters* ctr) {
-  if (threadIdx.x == 0) { ctr->frame++; ctr->frames++; }
+  if (threadIdx.x == 0) {
+    ctr->frame++; ctr->frames++;
+    const unsigned long long dt = global_timer_ns() - ctr->tBegin;
+    ctr->frameNs = dt > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)dt;
+  }
 }
 
 // ---- K1: cell key + arrival rank (spatial_worker.js:146-169) ----------------------------
@@ -239,7 +244,8 @@ template <bool INTEGRATE>
 __global__ void __launch_bounds__(256)
 k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afterSpatial, ById d, BySlot s,
               const uint32_t* __restrict__ key, const uint32_t* __restrict__ cellStart,
-              const uint32_t* __restrict__ arrIds, uint32_t* __restrict__ slotOf) {
+              const uint32_t* __restrict__ arrIds, uint32_t* __restrict__ slotOf,
+              const int32_t* __restrict__ slabCuts) {     // {begin, end} of the slab in device memory, or nullptr
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.N) return;
   const uint32_t f = d.F[i];
@@ -304,7 +310,8 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   const uint32_t gid = d.GID ? d.GID[i] : i;
   const uint32_t slot = slotOf[i];                               // k_slot_rank
   const int32_t crow = (int32_t)(k / (uint32_t)g.cols);
-  const uint32_t owned = (crow >= g.slabBegin && crow < g.slabEnd) ? F_OWNED : 0u;
+  const int32_t sb = slabCuts ? slabCuts[0] : g.slabBegin, se = slabCuts ? slabCuts[1] : g.slabEnd;
+  const uint32_t owned = (crow >= sb && crow < se) ? F_OWNED : 0u;
   if (s.SLID) s.SLID[slot] = i;
   uint32_t keep = 0;
   if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
@@ -1008,7 +1015,13 @@ struct SlabCounters {
   uint32_t top;             // slots in use (persistent)
   uint32_t overflow;        // sticky: bit0 exchange quota exceeded, bit1 entity table full
   uint32_t lastOwned, lastLow, lastHigh, lastFromLow, lastFromHigh;   // previous exchange, for reporting
-  uint32_t _pad[25];
+  // cuts: `cur` decides ownership during a frame, `pend` (known to both sides of a cut before the
+  // frame's exchange) selects what is packed and becomes `cur` when the exchange is applied
+  int32_t curBegin, curEnd, pendBegin, pendEnd;
+  uint32_t maxShift, hysteresisPct, minRows;     // dynamic balancing: 0 rows = static cuts
+  uint32_t load;                                 // smoothed device time of this slab's frame kernels
+  uint32_t cutMoves;                             // how many times one of my cuts moved
+  uint32_t _pad[16];
 };
 static_assert(sizeof(SlabCounters) == 256, "two 128-byte lines");
 
@@ -1033,7 +1046,7 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
     const uint32_t k = key[i];
     if (k != KEY_INVALID) {
       const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
-      owned = row0 >= g.slabBegin && row0 < g.slabEnd;            // authoritative here during the frame
+      owned = row0 >= sc->curBegin && row0 < sc->curEnd;          // authoritative here during the frame
     }
   }
   // one counter update per BLOCK: same-address atomics serialise at ~2 ns each, and one per warp
@@ -1050,8 +1063,9 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
   bool toLow = false, toHigh = false;
   int32_t row;
   if (owned && present_row(g, d, i, row)) {
-    toLow = g.slabBegin > 0 && row < g.slabBegin + g.slabHalo;
-    toHigh = g.slabEnd < g.rows && row >= g.slabEnd - g.slabHalo;
+    // bands around the cuts of the NEXT frame (both sides of a cut know them already)
+    toLow = sc->pendBegin > 0 && row < sc->pendBegin + g.slabHalo;
+    toHigh = sc->pendEnd < g.rows && row >= sc->pendEnd - g.slabHalo;
   }
   // positions in the two exchange buffers: ballot inside the warp, shared memory across the
   // warps, ONE atomic per block and direction
@@ -1087,11 +1101,22 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
   }
 }
 
-__global__ void k_slab_headers(SlabRec* __restrict__ low, SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc) {
+// Header record (index 0) of a message: gid = record count, meta = the sender's smoothed frame time,
+// ax / ay = bit patterns of the sender's cuts for the next frame.
+__global__ void k_slab_headers(SlabRec* __restrict__ low, SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc,
+                               const Counters* __restrict__ ctr) {
   if (threadIdx.x != 0) return;
   if (sc->nLow > quota || sc->nHigh > quota) sc->overflow |= 1u;
-  low[0].gid = min(sc->nLow, quota);
-  high[0].gid = min(sc->nHigh, quota);
+  const uint32_t ns = ctr->frameNs;
+  sc->load = sc->load ? (uint32_t)((3ull * sc->load + ns) / 4) : ns;
+  SlabRec* hdr[2] = {low, high};
+  const uint32_t cnt[2] = {min(sc->nLow, quota), min(sc->nHigh, quota)};
+  for (int k = 0; k < 2; k++) {
+    hdr[k][0].gid = cnt[k];
+    hdr[k][0].meta = sc->load;
+    hdr[k][0].ax = __int_as_float(sc->pendBegin);
+    hdr[k][0].ay = __int_as_float(sc->pendEnd);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1104,7 +1129,7 @@ k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t* __re
     bool keep;
     if (k != KEY_INVALID) {
       const int32_t row0 = (int32_t)(k / (uint32_t)g.cols);
-      keep = row0 >= g.slabBegin && row0 < g.slabEnd;
+      keep = row0 >= sc->curBegin && row0 < sc->curEnd;
     } else {
       keep = (d.F[i] & F_T_ACTIVE) != 0;    // active but never in the grid (NaN position): stays where it is
     }
@@ -1143,6 +1168,20 @@ k_slab_unpack(ById d, const SlabRec* __restrict__ fromLow, const SlabRec* __rest
   d.DP[i] = r.dp; d.AT[i] = r.at; d.V[i] = r.v;
 }
 
+// One cut between a low slab (load l, rows hl) and a high slab (load h, rows hh): which way it
+// moves for the frame after next.  Both neighbours evaluate this on the SAME numbers (their own
+// and the other's header), so they always agree.
+__device__ __forceinline__ int32_t slab_cut_shift(const SlabCounters* sc, uint32_t l, uint32_t h, int32_t hl, int32_t hh) {
+  if (!sc->maxShift || !l || !h) return 0;
+  const unsigned long long L = l, H = h, pct = 100 + sc->hysteresisPct;
+  const int32_t room = (int32_t)sc->minRows + 2 * (int32_t)sc->maxShift;     // the other cut of a slab may move too
+  const bool far = (L > H ? (L - H) : (H - L)) * 100ull > (L + H) * (unsigned long long)(4 * sc->hysteresisPct) / 2;
+  const int32_t step = far ? (int32_t)sc->maxShift : 1;
+  if (L * 100 > H * pct && hl >= room) return -step;         // the low slab is slower: it shrinks
+  if (H * 100 > L * pct && hh >= room) return step;          // the high slab is slower: it shrinks
+  return 0;
+}
+
 __global__ void k_slab_finish(const SlabRec* __restrict__ fromLow, const SlabRec* __restrict__ fromHigh, uint32_t quota,
                               uint32_t capacity, SlabCounters* sc) {
   if (threadIdx.x != 0) return;
@@ -1156,6 +1195,16 @@ __global__ void k_slab_finish(const SlabRec* __restrict__ fromLow, const SlabRec
   sc->lastOwned = sc->owned; sc->lastLow = sc->nLow; sc->lastHigh = sc->nHigh;
   sc->lastFromLow = nL; sc->lastFromHigh = nH;
   sc->nLow = 0; sc->nHigh = 0; sc->nHoles = 0; sc->owned = 0;
+  // the cuts the exchange just served become the ownership of the next frame; the ones after
+  // that follow from the loads both sides of each cut now know
+  sc->curBegin = sc->pendBegin; sc->curEnd = sc->pendEnd;
+  const int32_t mine = sc->curEnd - sc->curBegin;
+  int32_t db = 0, de = 0;
+  if (fromLow) db = slab_cut_shift(sc, fromLow[0].meta, sc->load, __float_as_int(fromLow[0].ay) - __float_as_int(fromLow[0].ax), mine);
+  if (fromHigh) de = slab_cut_shift(sc, sc->load, fromHigh[0].meta, mine, __float_as_int(fromHigh[0].ay) - __float_as_int(fromHigh[0].ax));
+  sc->pendBegin = sc->curBegin + db;
+  sc->pendEnd = sc->curEnd + de;
+  sc->cutMoves += (db != 0) + (de != 0);
 }
 
 // ---- host <-> device column plumbing ---------------------------------------------------------

@@ -142,7 +142,7 @@ class SlabEngine:
     """One slab = one GameEngine over a LOCAL entity table + the exchange buffers."""
 
     def __init__(self, cfg, cols, rank, world, device=0, flags=0, stream=None, plan=None,
-                 capacity_factor=1.35, host_neighbor_rows=False):
+                 capacity_factor=1.35, host_neighbor_rows=False, balance_rows=0, balance_hysteresis=3):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
@@ -156,6 +156,8 @@ class SlabEngine:
             inside |= act & ~fin
         sel = np.nonzero(inside)[0].astype(np.uint32)
         self.capacity = int(len(sel) * capacity_factor) + 4096
+        if balance_rows:        # moving cuts even the slabs out: size every table for an even share (+ halo) as well
+            self.capacity = max(self.capacity, int((int(act.sum()) / world) * (capacity_factor + 0.25)) + 4096)
         lcfg = dict(cfg)
         lcfg["entityCount"] = self.capacity
         self.cfg = cfg
@@ -174,6 +176,8 @@ class SlabEngine:
         for (_, cut) in self.blocks[:-1]:
             band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
         self.quota = band + band // 2 + 8192
+        if balance_rows:        # cuts follow the measured load (weed_slab_balance)
+            B.check(self.eng.ctx, B.lib().weed_slab_balance(self.eng.ctx, int(balance_rows), int(balance_hysteresis)))
         dev = torch.device("cuda", device)
         mk = lambda: torch.zeros((self.quota + 1) * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
         self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
@@ -227,7 +231,9 @@ class SlabEngine:
         act = (c["T.active"][:top] != 0)
         row, _ = cell_rows(self.cfg, c["T.y"][:top])
         fin = np.isfinite(c["T.x"][:top]) & np.isfinite(c["T.y"][:top])
-        own = act & ((fin & (row >= self.rb) & (row < self.re)) | (~fin & (self.rank == 0)))
+        st = self.status()                      # the cuts may have moved (weed_slab_balance)
+        rb, re = st["rowBegin"], st["rowEnd"]
+        own = act & ((fin & (row >= rb) & (row < re)) | (~fin & (self.rank == 0)))
         idx = np.nonzero(own)[0]
         return g[idx], {k: c[k][idx].copy() for k in keys}, idx
 
@@ -240,8 +246,8 @@ class SlabGroup:
     device-to-device copy.  Used by the single-GPU tests; the multi-process path is
     SlabEngine.step_dist."""
 
-    def __init__(self, cfg, cols, world, devices=None, **kw):
-        plan = plan_slabs(cfg, cols, world)
+    def __init__(self, cfg, cols, world, devices=None, plan=None, **kw):
+        plan = plan or plan_slabs(cfg, cols, world)
         devices = devices or [0] * world
         self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, **kw) for r in range(world)]
 

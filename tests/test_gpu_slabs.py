@@ -14,12 +14,12 @@ pytestmark = pytest.mark.gpu
 KEYS = ("T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.speed", "RB.collisionCount")
 
 
-def run_case(cfg, cols, world, frames):
+def run_case(cfg, cols, world, frames, plan=None, **kw):
     from multithreadedgameengine_b200.engine import GameEngine
     N = cfg["entityCount"]
     ref = GameEngine(cfg, host_neighbor_rows=False)
     ref.load_columns(cols)
-    grp = SlabGroup(cfg, cols, world)
+    grp = SlabGroup(cfg, cols, world, plan=plan, **kw)
     for f in range(frames):
         ref.step(1.0, 0, B.COLS_INPUT_ALL | B.COL_COLLISIONS)
         grp.step(1.0)
@@ -30,13 +30,13 @@ def run_case(cfg, cols, world, frames):
             a, b = bits(ref.col[k][act]), bits(got[k][act])
             assert np.array_equal(a, b), f"frame {f} {k}: {int((a != b).sum())} mismatches"
     ref.close()
-    grp.close()
+    return grp
 
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_slabs_reproduce_single_context_balls(world):
     cfg, cols = scenes.scaled("config4", 60000)
-    run_case(cfg, cols, world, frames=6)
+    run_case(cfg, cols, world, frames=6).close()
 
 
 def test_slabs_with_fast_movers_migrate():
@@ -48,7 +48,7 @@ def test_slabs_with_fast_movers_migrate():
     cols["RB.py"] = (cols["T.y"].astype(np.float64) - v[1]).astype(np.float32)
     cfg["physics"]["gravity"] = dict(x=0.0, y=0.0)
     cfg["physics"]["verletDamping"] = 1.0
-    run_case(cfg, cols, 4, frames=8)
+    run_case(cfg, cols, 4, frames=8).close()
 
 
 def test_observer_on_a_cut_and_capped_rows():
@@ -59,7 +59,7 @@ def test_observer_on_a_cut_and_capped_rows():
     blocks, H = plan_slabs(cfg, cols, 2)
     cols["T.x"][0] = 800.0
     cols["T.y"][0] = blocks[0][1] * 16.0 + 1.0
-    run_case(cfg, cols, 2, frames=5)
+    run_case(cfg, cols, 2, frames=5).close()
 
 
 def test_plan_balances_entities():
@@ -67,3 +67,24 @@ def test_plan_balances_entities():
     blocks, H = plan_slabs(cfg, cols, 4)
     assert blocks[0][0] == 0 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
     assert H == 20         # max((S+1) * ceil(16/16), 2 * ceil(150/16)): the Mouse's range dominates
+
+
+def test_dynamic_cuts_follow_the_load_and_stay_bit_exact():
+    """weed_slab_balance: start from deliberately bad cuts (equal row counts over a scene whose
+    entities sit in the lower half), let the cuts move by up to 2 rows per frame.  Every frame
+    must still equal the unpartitioned world bit for bit; the cuts must stay contiguous, must
+    have moved, and must have moved toward the crowded half."""
+    cfg, cols = scenes.balls_synthetic(60000, (2048.0, 2048.0), 16.0, 24, 2, (2.0, 5.0), 16.0, seed=31)
+    cols["T.y"][1:] = (cols["T.y"][1:] * np.float32(0.5) + np.float32(1000.0)).astype(np.float32)   # rows 62..127 of 128
+    cols["RB.py"][1:] = cols["T.y"][1:]
+    cols["C.visualRange"][0] = 16.0         # a short-sighted Mouse: halo 3 rows, so 43-row slabs may shrink
+    rows = 128
+    _, H = plan_slabs(cfg, cols, 3)
+    plan = ([(0, 43), (43, 86), (86, rows)], H)
+    grp = run_case(cfg, cols, 3, frames=25, plan=plan, balance_rows=2, balance_hysteresis=3)
+    st = [s.status() for s in grp.slabs]
+    cuts = [(x["rowBegin"], x["rowEnd"]) for x in st]
+    assert cuts[0][0] == 0 and cuts[-1][1] == rows and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:])), cuts
+    assert sum(x["cutMoves"] for x in st) > 0, st
+    assert cuts[0][1] > 43, cuts            # slab 0 was almost empty: it has to grow
+    grp.close()
