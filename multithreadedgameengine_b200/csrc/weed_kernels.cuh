@@ -23,7 +23,7 @@ namespace weed {
 namespace cg = cooperative_groups;
 
 static constexpr int SCAN_THREADS = 512;
-static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_ITEMS = 16;   // per thread: the look-back chain is 1 / (512 * 16) of the cell count long
 static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 static constexpr int WB_THREADS = 256;
 
@@ -129,11 +129,19 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t epoch = ctr->epoch;
+  constexpr int V = SCAN_ITEMS / 4;
   const size_t i0 = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-  uint4 c = *reinterpret_cast<const uint4*>(cellCount + i0);   // arrays are padded to whole tiles
-  *reinterpret_cast<uint4*>(cellCount + i0) = make_uint4(0, 0, 0, 0);
-  const uint32_t tsum = c.x + c.y + c.z + c.w;
-  uint32_t tmax = max(max(c.x, c.y), max(c.z, c.w));
+  uint4 c[V];                                                  // arrays are padded to whole tiles
+#pragma unroll
+  for (int v = 0; v < V; v++) c[v] = reinterpret_cast<const uint4*>(cellCount + i0)[v];
+#pragma unroll
+  for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellCount + i0)[v] = make_uint4(0, 0, 0, 0);
+  uint32_t tsum = 0, tmax = 0;
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    tsum += c[v].x + c[v].y + c[v].z + c[v].w;
+    tmax = max(tmax, max(max(c[v].x, c[v].y), max(c[v].z, c[v].w)));
+  }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = tsum;
   for (int o = 1; o < 32; o <<= 1) {
@@ -167,9 +175,12 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
   }
   __syncthreads();
   uint32_t e = s_excl + s_warp[warp] + (inc - tsum);
-  uint4 o4;
-  o4.x = e; e += c.x; o4.y = e; e += c.y; o4.z = e; e += c.z; o4.w = e;
-  *reinterpret_cast<uint4*>(cellStart + i0) = o4;
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    uint4 o4;
+    o4.x = e; e += c[v].x; o4.y = e; e += c[v].y; o4.z = e; e += c[v].z; o4.w = e; e += c[v].w;
+    reinterpret_cast<uint4*>(cellStart + i0)[v] = o4;
+  }
 }
 
 // ---- K3a: ids into their cell segment, arrival order ------------------------------------

@@ -43,6 +43,23 @@ def test_struct_sizes_match_header(L):
             p.minSpeedForRotation, p.gravityX, p.gravityY) == (4, 0.8, 0.5, 0.995, 0.1, 0.0, 0.0)
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof of every public struct as a C compiler sees include/weedgpu.h == the ctypes mirror."""
+    import subprocess
+    pairs = [("weed_config", B.Config), ("weed_physics_config", B.PhysicsConfig), ("weed_stats", B.Stats),
+             ("weed_boids_params", B.BoidsParams), ("weed_flock_class", B.FlockClass), ("weed_flock_params", B.FlockParams),
+             ("weed_collision_event_counts", B.CollisionEventCounts), ("weed_camera", B.Camera),
+             ("weed_shadow_columns", B.ShadowColumns), ("weed_shadow_sprites", B.ShadowSprites),
+             ("weed_slab_stats", B.SlabStats)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "weedgpu.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n, _ in pairs) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(t) for _, t in pairs], list(zip([n for n, _ in pairs], got, [C.sizeof(t) for _, t in pairs]))
+
+
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 1001, 4099, 65537])
 def test_layout_rule_matches_component_js(L, N):
     for bid, cls, name in ((0, Transform, "Transform"), (1, RigidBody, "RigidBody"), (2, Collider, "Collider")):
