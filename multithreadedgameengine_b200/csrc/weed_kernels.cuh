@@ -449,7 +449,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
       const uint32_t m = min(4u, b - t);
       float4 cand[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) cand[u] = s.CXY[min(t + (uint32_t)u, b - 1)];
+      for (int u = 0; u < 4; u++) cand[u] = __ldg(s.CXY + min(t + (uint32_t)u, b - 1));
       uint32_t used = m;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -517,11 +517,11 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
         const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
         if (f == 0 && fin) {
           // whole row in this round: header + entries in one contiguous store
-          if (l == 0) { nd[rb] = (int32_t)c; dd[rb] = (float)c; }       // :274-275
-          else if (l <= c) { nd[rb + l] = (int32_t)sId[src * K4_STRIDE + l - 1]; dd[rb + l] = sD2[src * K4_STRIDE + l - 1]; }
+          if (l == 0) { __stcs(nd + rb, (int32_t)c); __stcs(dd + rb, (float)c); }       // :274-275
+          else if (l <= c) { __stcs(nd + rb + l, (int32_t)sId[src * K4_STRIDE + l - 1]); __stcs(dd + rb + l, sD2[src * K4_STRIDE + l - 1]); }
         } else {
-          if (l < c) { nd[rb + 1 + f + l] = (int32_t)sId[src * K4_STRIDE + l]; dd[rb + 1 + f + l] = sD2[src * K4_STRIDE + l]; }  // :259-260
-          if (fin && l == 15) { nd[rb] = (int32_t)(f + c); dd[rb] = (float)(f + c); }
+          if (l < c) { __stcs(nd + rb + 1 + f + l, (int32_t)sId[src * K4_STRIDE + l]); __stcs(dd + rb + 1 + f + l, sD2[src * K4_STRIDE + l]); }  // :259-260
+          if (fin && l == 15) { __stcs(nd + rb, (int32_t)(f + c)); __stcs(dd + rb, (float)(f + c)); }
         }
       }
     }
@@ -842,7 +842,7 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
 #pragma unroll
           for (int u = 0; u < 4; u++) wd[u] = s.NST[(size_t)min(k + (uint32_t)u, cnt - 1) * g.Npad + e];
 #pragma unroll
-          for (int u = 0; u < 4; u++) gt[u] = Gin[(size_t)(wd[u] & NS_SLOT_MASK) * gs];
+          for (int u = 0; u < 4; u++) gt[u] = __ldg(Gin + (size_t)(wd[u] & NS_SLOT_MASK) * gs);
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             if (k + (uint32_t)u >= cnt) break;
