@@ -173,9 +173,17 @@ class SlabEngine:
         # every frame moves exactly (quota + 1) records per neighbour and direction
         hist = np.bincount(row[act & fin], minlength=self.rows)
         band = 0
-        for (_, cut) in self.blocks[:-1]:
-            band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
-        self.quota = band + band // 2 + 8192
+        if balance_rows:
+            # cuts move: size the messages for the most crowded (halo + shift)-row window of the
+            # start scene wherever it lies (the mean band x 1.5 would overflow inside a cluster)
+            w = self.H + int(balance_rows)
+            csum = np.concatenate([[0], np.cumsum(hist)])
+            band = int((csum[w:] - csum[:-w]).max()) if len(hist) > w else int(hist.sum())
+            self.quota = band + band // 4 + 8192
+        else:
+            for (_, cut) in self.blocks[:-1]:
+                band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
+            self.quota = band + band // 2 + 8192
         if balance_rows:        # cuts follow the measured load (weed_slab_balance)
             B.check(self.eng.ctx, B.lib().weed_slab_balance(self.eng.ctx, int(balance_rows), int(balance_hysteresis)))
         dev = torch.device("cuda", device)
