@@ -814,6 +814,8 @@ extern "C" int weed_slab_set_gids(weed_ctx* ctx, const uint32_t* gids, uint32_t 
   GUARD(ctx);
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
   if (!gids || count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "bad gid list");
+  for (uint32_t k = 0; k < count; k++)      // bit 31 of an id word is the CX_EDGE flag of the candidate records
+    if (gids[k] & 0x80000000u) return fail(ctx, WEED_E_INVALID, "global entity ids must be below 2^31");
   CK(cudaMemsetAsync(ctx->d.GID, 0xFF, (size_t)ctx->g.N * 4, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d.GID, gids, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
   SlabCounters sc;
