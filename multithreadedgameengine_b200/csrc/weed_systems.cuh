@@ -213,7 +213,7 @@ struct ShadowIn {
 struct ShadowOut { uint8_t* active; float *radius, *x, *y, *rotation, *scaleX, *scaleY, *alpha; };
 
 __device__ __forceinline__ bool sh_is_light(const ShadowIn& in, const uint8_t* __restrict__ F, uint32_t i) {
-  return in.lightActive[i] && (F[i] & F_T_ACTIVE) && in.onScreen[i] && in.lightIntensity[i] > 0;   // :913-918
+  return in.lightActive[i] && (F[i] & F_T_ACTIVE) && in.onScreen[i] && !(in.lightIntensity[i] <= 0);   // :913-918 (`intensity <= 0` skips: NaN stays)
 }
 
 // pass 1: light flags per tile
