@@ -190,6 +190,7 @@ struct weed_ctx {
   std::vector<Pool> pools;
   void* poolStage = nullptr; size_t poolStageBytes = 0;   // device staging for a batch (records / indices)
   uint32_t* poolScalars = nullptr;
+  bool k4Wide = false;        // warp-per-entity neighbor scan (long rows); WEED_K4=wide|thread overrides at create
   // slabs
   bool slab = false;
   uint32_t* holes = nullptr;
@@ -355,6 +356,10 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
   g.Npad = ((g.N + 31) / 32) * 32;
   g.maxPairs = cfg->maxCollisionPairs;
+  {
+    const char* k4 = getenv("WEED_K4");   // diagnostic override, read once
+    ctx->k4Wide = k4 ? (strcmp(k4, "wide") == 0) : (cfg->maxNeighbors >= 256);
+  }
   g.slabBegin = 0; g.slabEnd = g.rows; g.slabHalo = 0;
   if (cfg->slabRowEnd > 0) {
     if (cfg->slabRowBegin >= cfg->slabRowEnd || (int32_t)cfg->slabRowEnd > g.rows) { ctx->err = "bad slab rows"; return bail(WEED_E_INVALID); }
@@ -524,8 +529,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   TIME_MARK(ctx, timing, 4);
   // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
   // short rows (the large synthetic worlds) -> one thread per entity with staged flush
-  const char* k4 = getenv("WEED_K4");   // diagnostic override: "wide" / "thread"
-  const bool wide = k4 ? (strcmp(k4, "wide") == 0) : (g.M >= 256);
+  const bool wide = ctx->k4Wide;
   if (wide) {
     const unsigned wb = blocks_for((size_t)g.N * 32, 256);
     if (ctx->nd) k_neighbors_wide<true><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
@@ -786,6 +790,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->collisionPairs = c.collisionPairs;
   out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 14 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
+  out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
   return WEED_OK;
 }
 
