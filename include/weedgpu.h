@@ -213,14 +213,18 @@ const char* weed_last_error(weed_ctx* ctx);   /* ctx may be NULL: last create() 
 /* device-resident access for in-process consumers (bench harness, multi-GPU plumbing):
  * raw device pointers of the API-visible mirrors.                                      */
 typedef enum weed_devptr_id {
-  WEED_DEV_NEIGHBOR  = 0,  /* int32  [N*(1+M)] */
-  WEED_DEV_DISTANCE  = 1,  /* float  [N*(1+M)] */
+  WEED_DEV_NEIGHBOR  = 0,  /* int32  [N*weed_row_pitch()] */
+  WEED_DEV_DISTANCE  = 1,  /* float  [N*weed_row_pitch()] */
   WEED_DEV_COLLISION = 2,  /* int32  [1+2*maxPairs] */
   WEED_DEV_STATE     = 3,  /* float4 [N] {x, y, px, py}, see DESIGN.md                  */
   WEED_DEV_ATTR      = 4,  /* float4 [N] {maxVel, radius, visualRange, velocityAngle}   */
   WEED_DEV_VEL       = 5   /* float4 [N] {vx, vy, speed, -}                             */
 } weed_devptr_id;
 int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
+/* Words between two rows of the DEVICE copies of neighborData / distanceData: 1 + maxNeighbors
+ * rounded up to 8, so that every row starts on a 32-byte sector (the host buffers keep the
+ * reference's stride of 1 + maxNeighbors, gameEngine.js:552-559; fetches are pitched copies). */
+uint32_t weed_row_pitch(weed_ctx* ctx);
 
 /* ---- device-side consumers of the neighbor rows ("systems") ----------------
  * The fixed-stride rows exist to feed GameObject.tick(); at >= 1M entities copying them to

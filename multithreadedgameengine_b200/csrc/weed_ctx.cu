@@ -383,7 +383,8 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
-  ctx->rowWords = N * (1 + (size_t)g.M);
+  g.rowPitch = (g.M + 1 + 7u) & ~7u;
+  ctx->rowWords = N * (size_t)g.rowPitch;
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
   A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
   A(ctx->dParams, 1); A(ctx->dCtr, 1);
@@ -447,6 +448,26 @@ static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = null
   return WEED_OK;
 }
 
+// API rows device -> host.  On the device a row starts on a 32-byte sector boundary (pitch =
+// 1 + maxNeighbors rounded up to 8 words); the host buffers keep the reference's stride of
+// 1 + maxNeighbors words (gameEngine.js:552-559), so the copy is a pitched one.  `absolute`:
+// the destination is the whole bound buffer (row `first` lands at its own offset), otherwise
+// the destination starts at row `first`.
+static int copy_rows(weed_ctx* ctx, void* nd_host, void* dd_host, uint32_t first, uint32_t count, bool absolute,
+                     cudaStream_t stream) {
+  if (!count) return WEED_OK;
+  const size_t hostStride = (1 + (size_t)ctx->g.M) * 4, devPitch = (size_t)ctx->g.rowPitch * 4;
+  const size_t hostOff = absolute ? (size_t)first * hostStride : 0;
+  const size_t devOff = (size_t)first * ctx->g.rowPitch;
+  if (nd_host)
+    CK(cudaMemcpy2DAsync((uint8_t*)nd_host + hostOff, hostStride, ctx->nd + devOff, devPitch, hostStride, count,
+                         cudaMemcpyDeviceToHost, stream));
+  if (dd_host)
+    CK(cudaMemcpy2DAsync((uint8_t*)dd_host + hostOff, hostStride, ctx->dd + devOff, devPitch, hostStride, count,
+                         cudaMemcpyDeviceToHost, stream));
+  return WEED_OK;
+}
+
 static int download_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr) {
   if (!stream) stream = ctx->stream;
   const uint32_t cols = mask & WEED_COLS_INPUT_ALL;
@@ -466,8 +487,8 @@ static int download_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nu
   if (mask & WEED_COL_NEIGHBORS) {
     if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
     if (!ctx->host[WEED_BUF_NEIGHBOR] || !ctx->host[WEED_BUF_DISTANCE]) return fail(ctx, WEED_E_NOT_BOUND, "neighbor/distance buffer not bound");
-    CK(cudaMemcpyAsync(ctx->host[WEED_BUF_NEIGHBOR], ctx->nd, ctx->rowWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->host[WEED_BUF_DISTANCE], ctx->dd, ctx->rowWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc2 = copy_rows(ctx, ctx->host[WEED_BUF_NEIGHBOR], ctx->host[WEED_BUF_DISTANCE], 0, (uint32_t)ctx->g.N, true, stream);
+    if (rc2) return rc2;
   }
   if (mask & WEED_COL_COLLISIONS) {
     if (!ctx->host[WEED_BUF_COLLISION]) return fail(ctx, WEED_E_NOT_BOUND, "collision buffer not bound");
@@ -750,10 +771,8 @@ extern "C" int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t coun
   if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
   if (!ctx->host[WEED_BUF_NEIGHBOR] || !ctx->host[WEED_BUF_DISTANCE]) return fail(ctx, WEED_E_NOT_BOUND, "neighbor/distance buffer not bound");
   if ((size_t)first + count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "row range out of bounds");
-  const size_t stride = 1 + (size_t)ctx->g.M;
-  const size_t off = (size_t)first * stride, len = (size_t)count * stride;
-  CK(cudaMemcpyAsync((int32_t*)ctx->host[WEED_BUF_NEIGHBOR] + off, ctx->nd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync((float*)ctx->host[WEED_BUF_DISTANCE] + off, ctx->dd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = copy_rows(ctx, ctx->host[WEED_BUF_NEIGHBOR], ctx->host[WEED_BUF_DISTANCE], first, count, true, ctx->stream);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
 }
@@ -762,10 +781,8 @@ extern "C" int weed_fetch_neighbors_to(weed_ctx* ctx, uint32_t first, uint32_t c
   GUARD(ctx);
   if (!ctx->nd) return fail(ctx, WEED_E_STATE, "neighbor rows disabled (WEED_FLAG_NO_NEIGHBOR_ROWS)");
   if ((size_t)first + count > ctx->g.N) return fail(ctx, WEED_E_INVALID, "row range out of bounds");
-  const size_t stride = 1 + (size_t)ctx->g.M;
-  const size_t off = (size_t)first * stride, len = (size_t)count * stride;
-  if (neighbor_out) CK(cudaMemcpyAsync(neighbor_out, ctx->nd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (distance_out) CK(cudaMemcpyAsync(distance_out, ctx->dd + off, len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = copy_rows(ctx, neighbor_out, distance_out, first, count, false, ctx->stream);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
 }
@@ -793,6 +810,8 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
   return WEED_OK;
 }
+
+extern "C" uint32_t weed_row_pitch(weed_ctx* ctx) { return ctx ? ctx->g.rowPitch : 0u; }
 
 extern "C" int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes) {
   if (!ctx || !out) return WEED_E_INVALID;
@@ -1068,7 +1087,7 @@ extern "C" int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLight
     ctx->shLightCap = maxShadowCastingLights;
   }
   int rc = sys_tiles(ctx, N); if (rc) return rc;
-  ShadowParams p{maxShadowCastingLights, maxShadowsPerLight, maxShadowSprites, (uint32_t)ctx->g.M};
+  ShadowParams p{maxShadowCastingLights, maxShadowsPerLight, maxShadowSprites, ctx->g.rowPitch};
   ShadowIn in{ctx->shLightActive, ctx->shIntensity, ctx->shCasterActive, ctx->shRadius, ctx->shHeight, ctx->onScreen};
   const size_t S = maxShadowSprites;
   ShadowOut o{ctx->shOutActive, ctx->shOut, ctx->shOut + S, ctx->shOut + 2 * S, ctx->shOut + 3 * S,

@@ -425,7 +425,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   const uint32_t vrBits = __float_as_uint(vr);
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
-  const size_t rowBase = (size_t)lid * (1 + (size_t)M);
+  const size_t rowBase = (size_t)lid * g.rowPitch;      // sector-aligned rows: one partial sector per row, not two
   uint32_t n = 0;
   int32_t row = win.x;
   uint32_t t = 0, b = 0;
@@ -562,7 +562,7 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
   const float vrSqF = vr * vr * 1.00001f;
   int32_t myCol, myRow;
   cell_of(g, q.x, q.y, myCol, myRow);
-  const size_t rowBase = (size_t)lid * (1 + (size_t)M);
+  const size_t rowBase = (size_t)lid * g.rowPitch;      // sector-aligned rows: one partial sector per row, not two
   uint32_t n = 0;
   for (int32_t row = win.x; row <= win.y && n < M && M > 0; row++) {
     const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
@@ -1360,7 +1360,7 @@ k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ n
   if (ci < 0) return;                               // not a boid: some other tick()
   const FlockClass& k = fp.cls[ci];
   const double dt = fp.dtRatio;
-  const size_t off = (size_t)i * (1 + (size_t)g.M);
+  const size_t off = (size_t)i * g.rowPitch;
   const int32_t cnt = nd[off];
   const float4 me = d.DP[i];
   const double myX = me.x, myY = me.y;

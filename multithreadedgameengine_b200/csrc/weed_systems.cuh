@@ -204,7 +204,7 @@ k_screen_visibility(uint32_t N, CameraParams c, const float4* __restrict__ DP, c
 // they cast anything), each walks its neighbor row in order and emits at most perLight shadows,
 // everything stops at maxSprites.  Parallel: light flag -> rank by id; shadow count per eligible
 // light -> prefix; ordered emit truncated at maxSprites (a prefix truncation, like the break).
-struct ShadowParams { uint32_t maxLights, perLight, maxSprites, M; };
+struct ShadowParams { uint32_t maxLights, perLight, maxSprites, rowPitch; };
 struct ShadowIn {
   const uint8_t* lightActive; const float* lightIntensity;
   const uint8_t* casterActive; const float* casterRadius; const float* casterHeight;
@@ -244,7 +244,7 @@ k_shadow_count(uint32_t N, ShadowParams p, ShadowIn in, const uint8_t* __restric
   uint32_t tot;
   const uint32_t rank = tilePrefix[blockIdx.x] + block_exclusive(isL, s_warp, tot);
   if (!isL || rank >= p.maxLights) return;                            // :911
-  const size_t o = (size_t)i * (1 + (size_t)p.M);
+  const size_t o = (size_t)i * p.rowPitch;
   const int32_t cnt = nd[o];
   uint32_t c = 0;
   for (int32_t k = 0; k < cnt && c < p.perLight; k++)                 // :930-931
@@ -268,7 +268,7 @@ k_shadow_emit(ShadowParams p, ShadowIn in, const uint8_t* __restrict__ F, const 
     const uint32_t i = lightId[l];
     const float4 lp = DP[i];
     const double intensity = (double)in.lightIntensity[i];
-    const size_t o = (size_t)i * (1 + (size_t)p.M);
+    const size_t o = (size_t)i * p.rowPitch;
     const int32_t cnt = nd[o];
     uint32_t c = 0;
     for (int32_t k = 0; k < cnt && c < p.perLight && base + c < p.maxSprites; k++) {
