@@ -38,7 +38,7 @@ UNIT = "entity-substeps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/), config4 16M on one B200; None = not captured for this kernel.
 TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r1_ncu_config4_16M_final_summary.md
-    "k_neighbors": 7.085e9, "k_substep": 2.539e9, "k_build_slots": 1.803e9, "k_writeback": 1.950e9,
+    "k_neighbors": 5.777e9, "k_substep": 2.539e9, "k_build_slots": 1.803e9, "k_writeback": 1.950e9,
 }
 
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
