@@ -3,12 +3,14 @@
 //   id order   k_cell_key      K1  cell key + arrival rank (one L2 atomic per entity)
 //   cells      k_cell_scan     K2  exclusive scan, single pass, decoupled look-back
 //   id order   k_scatter_ids   K3a ids into their cell segment (arrival order)
-//   id order   k_build_slots   K3b stable position inside the cell (ascending id), Verlet
-//                                  integration (K5) + derived speed/angle fused, one 32 B
+//   id order   k_slot_rank     K3b stable position inside the cell (ascending id)
+//   id order   k_build_slots   K3c Verlet integration (K5) + derived speed/angle fused, one 32 B
 //                                  slot record per entity (the only scattered write)
-//   slot order k_slot_prep     K3c query positions, scan windows, list heads, first bounds pass
+//   slot order k_slot_prep     K3d query positions, candidate records, scan windows, list heads,
+//                                  first bounds pass
 //   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
-//                                  warp-cooperative coalesced row flush
+//                                  warp-cooperative coalesced row flush (k_neighbors_wide: warp
+//                                  per entity for long rows); k_capped_rescan, k_sort_lists K4b/c
 //   slot order k_substep<LAST> K6  circle-circle correction, J-order (+ next sweep's bounds)
 //   id order   k_writeback     WB  gather results by id; per-tile outgoing pair counts
 //   tiles      k_pair_scan     K7a prefix of the tile counts, pair count
