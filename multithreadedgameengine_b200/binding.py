@@ -38,6 +38,8 @@ COL_COLLISIONS = 1 << 25
 FLAG_NO_GRAPH = 1 << 0
 FLAG_KERNEL_TIMING = 1 << 1
 FLAG_NO_NEIGHBOR_ROWS = 1 << 2
+FLAG_K4_V1 = 1 << 8
+FLAG_K6_V1 = 1 << 9
 
 DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL = range(6)
 

@@ -556,9 +556,15 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
     if (ctx->nd) k_neighbors_wide<true><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
     else         k_neighbors_wide<false><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   } else {
-    const unsigned kb = blocks_for(g.N, K4_THREADS);
-    if (ctx->nd) k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
-    else         k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+    if (ctx->cfg.flags & WEED_FLAG_K4_V1) {
+      const unsigned kb = blocks_for(g.N, K4_THREADS);
+      if (ctx->nd) k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+      else         k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+    } else {
+      const unsigned kb = blocks_for(g.N, K4V2_THREADS);
+      if (ctx->nd) k_neighbors2<true><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+      else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
+    }
   }
   TIME_MARK(ctx, timing, 5);
   k_capped_rescan<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
@@ -580,7 +586,14 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
   for (int step = 0; step < S; step++) {
     float4* out = bufs[step & 1];
     const bool first = step == 0, last = step == S - 1;
-    if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    if (!(ctx->cfg.flags & WEED_FLAG_K6_V1)) {
+      const unsigned sb = blocks_for(g.N, K6V2_THREADS);
+      if (first && last)       k_sweep<true, true><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else if (first)          k_sweep<true, false><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else if (last)           k_sweep<false, true><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else                     k_sweep<false, false><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    }
+    else if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
     else if (first)          k_substep<true, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
     else if (last)           k_substep<false, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
     else                     k_substep<false, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);

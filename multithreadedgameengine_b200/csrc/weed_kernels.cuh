@@ -384,6 +384,12 @@ k_slot_prep(GridDims g, const Params* __restrict__ pp, BySlot s, const uint32_t*
 // An explicit pair is a row entry of its owner (the lower id), so the owner's row position
 // (k * Npad + slot) is a unique pool index: incoming pairs of a target form a linked list
 // threaded through XNEXT, with no capacity limit and no allocation.
+// Pads the internal row of slot e (n entries) to a multiple of four with words that have no
+// membership bit and point at the entity itself: k_sweep walks rows four entries at a time.
+__device__ __forceinline__ void row_tail_fill(const GridDims& g, const BySlot& s, uint32_t e, uint32_t n) {
+  for (uint32_t k = n; k < ((n + 3u) & ~3u); k++) s.NST[k * g.Npad + e] = e;
+}
+
 __device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, uint32_t dstSlot, uint32_t ownerRowPos) {
   s.XNEXT[ownerRowPos] = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
   atomicAdd(&ctr->explicitPairs, 1u);
@@ -537,6 +543,167 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
   }
   s.NCNT[e] = n;
+  row_tail_fill(g, s, e, n);
+}
+
+// ---- K4, second form: survivor queue + converged exact pass ------------------------------------
+// Same rows, same bits as k_neighbors; the control flow differs.
+//   phase 1  streams the 8-byte query positions of the entity's own slot ranges (four in flight)
+//            through the float32 pre-filter and only PUSHES the slots that survive onto a per-thread
+//            shared-memory queue (a predicated store and an increment: nothing else runs under
+//            divergence).  It ends when the queue is full or the window is exhausted.
+//   phase 2  every lane drains its queue in step with the others: 16-byte candidate record, the
+//            binary64 predicate of spatial_worker.js:252-257, row word / id / float32 d2 staged in
+//            place (accepted <= drained), cap of :264.
+//   then     partners with another visualRange or on the rim (as in k_neighbors), warp flush.
+static constexpr int K4V2_THREADS = 128;
+static constexpr int K4V2_Q = 16;         // queue = stage entries per thread and round
+static constexpr int K4V2_STRIDE = 17;    // odd stride: conflict-free smem both ways
+
+template <bool WRITE_ROWS>
+__global__ void __launch_bounds__(K4V2_THREADS)
+k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
+             float* __restrict__ dd, Counters* ctr) {
+  constexpr uint32_t PLANE = (K4V2_THREADS / 32) * 32 * K4V2_STRIDE;
+  __shared__ uint32_t sStage[3 * PLANE];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* const myW = &sStage[warp * 32 * K4V2_STRIDE + lane * K4V2_STRIDE];
+  uint32_t* const sId = &sStage[PLANE + warp * 32 * K4V2_STRIDE];
+  const float* const sD2 = reinterpret_cast<const float*>(&sStage[2 * PLANE + warp * 32 * K4V2_STRIDE]);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t A = cellStart[g.cells];
+  const uint32_t M = g.M;
+  const bool live = e < A;
+  float2 q = make_float2(0.f, 0.f);
+  float vr = 0.f;
+  uint32_t id = 0, edge = CX_EDGE;
+  int4 win = make_int4(1, 0, 1, 0);
+  if (live) {
+    const float4 me = s.CXY[e];
+    q = make_float2(me.x, me.y);
+    vr = me.z; id = __float_as_uint(me.w) & ~CX_EDGE; edge = __float_as_uint(me.w) & CX_EDGE;
+    win = s.WIN[e];
+  }
+  const uint32_t lid = (live && s.SLID) ? s.SLID[e] : id;    // row address: local index
+  bool done = !(live && M > 0 && win.x <= win.y);
+  const double myX = q.x, myY = q.y;
+  const double vrSq = dmul((double)vr, (double)vr);
+  const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf compare false)
+  const uint32_t vrBits = __float_as_uint(vr);
+  int32_t myCol = 0, myRow = 0;
+  if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
+  const size_t rowBase = (size_t)lid * g.rowPitch;
+  const float2* __restrict__ QXY = s.QXY;
+  uint32_t n = 0;
+  int32_t row = win.x;
+  uint32_t t = 0, b = 0;
+  if (!done) {
+    t = cellStart[(uint32_t)row * g.cols + win.z];
+    b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+  }
+  bool hdr = live;                                   // row header (:274-275) still to be written
+  do {
+    // ---- phase 1: survivors of the float32 pre-filter -------------------------------------------
+    uint32_t qn = 0;
+    while (!done && qn + 4 <= (uint32_t)K4V2_Q) {
+      if (t >= b) {
+        if (++row > win.y) { done = true; break; }
+        t = cellStart[(uint32_t)row * g.cols + win.z];
+        b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+        continue;
+      }
+      const uint32_t last = b - 1;
+      float2 c[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) c[u] = __ldg(QXY + min(t + (uint32_t)u, last));
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float fx = c[u].x - q.x, fy = c[u].y - q.y;
+        const bool pass = (t + (uint32_t)u <= last) && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF);
+        if (pass) myW[qn] = t + (uint32_t)u;
+        qn += pass ? 1u : 0u;
+      }
+      t += 4;
+    }
+    // ---- phase 2: exact predicate, staged in place -------------------------------------------------
+    uint32_t cnt = 0;
+    bool anySlow = false;
+    for (uint32_t k = 0; k < qn; k++) {
+      const uint32_t tc = myW[k];
+      const float4 c = __ldg(s.CXY + tc);
+      const double dX = dsub((double)c.x, myX);           // :252-254
+      const double dY = dsub((double)c.y, myY);
+      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+      if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
+      const uint32_t jw = __float_as_uint(c.w);
+      const uint32_t jid = jw & ~CX_EDGE;
+      const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
+      myW[cnt] = tc | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
+      myW[PLANE + cnt] = sure ? jid : (jid | CX_EDGE);
+      myW[2 * PLANE + cnt] = __float_as_uint(fround(d2));
+      cnt++;
+      anySlow |= !sure;
+      if (n + cnt >= M) { done = true; break; }           // :264
+    }
+    const uint32_t first = n;                             // row position of my first staged entry
+    n += cnt;
+    // ---- staged entries whose partner differs in visualRange or sits on the rim ---------------------
+    if (anySlow) {
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t jraw = myW[PLANE + k];
+        if (!(jraw & CX_EDGE)) continue;
+        myW[PLANE + k] = jraw & ~CX_EDGE;
+        const uint32_t wd = myW[k];
+        const uint32_t tc = wd & NS_SLOT_MASK;
+        const float4 c = s.CXY[tc];
+        const int4 wt = s.WIN[tc];
+        bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+        if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
+          const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+          const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+          back = d2 < dmul((double)c.z, (double)c.z);
+        }
+        if (back) myW[k] = wd | NS_BACK;
+        else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
+      }
+    }
+    __syncwarp();
+    // ---- warp-cooperative flush ---------------------------------------------------------------------
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
+    for (uint32_t k = 0; k < kmax; k++)
+      if (k < cnt) s.NST[(size_t)(first + k) * g.Npad + e] = myW[k];
+    if (WRITE_ROWS) {
+      const uint32_t h = lane >> 4, l = lane & 15;
+      const uint32_t fin = (uint32_t)(done && hdr);    // the round in which this lane's scan ended
+      hdr = hdr && !done;
+      for (uint32_t s2 = 0; s2 < 16; s2++) {
+        const uint32_t src = s2 * 2 + h;
+        const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t f = __shfl_sync(0xffffffffu, first, src);
+        const uint32_t fn = __shfl_sync(0xffffffffu, fin, src);
+        const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
+        if (f == 0 && fn) {
+          // whole row in this round: header + entries in one contiguous store
+          if (l == 0) { __stcs(nd + rb, (int32_t)c); __stcs(dd + rb, (float)c); }       // :274-275
+          else if (l <= c) { __stcs(nd + rb + l, (int32_t)sId[src * K4V2_STRIDE + l - 1]); __stcs(dd + rb + l, sD2[src * K4V2_STRIDE + l - 1]); }
+          if (c == 16 && l == 15) { __stcs(nd + rb + 16, (int32_t)sId[src * K4V2_STRIDE + 15]); __stcs(dd + rb + 16, sD2[src * K4V2_STRIDE + 15]); }
+        } else {
+          if (l < c) { __stcs(nd + rb + 1 + f + l, (int32_t)sId[src * K4V2_STRIDE + l]); __stcs(dd + rb + 1 + f + l, sD2[src * K4V2_STRIDE + l]); }  // :259-260
+          if (fn && l == 15) { __stcs(nd + rb, (int32_t)(f + c)); __stcs(dd + rb, (float)(f + c)); }
+        }
+      }
+    }
+    __syncwarp();
+  } while (__any_sync(0xffffffffu, !done));
+  if (!live) return;
+  // capped row: my row may be missing partners; K4b finds the lower-id ones
+  if (n >= M && M > 0) {
+    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+    ctr->anyCapped = 1;
+    s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
+  }
+  s.NCNT[e] = n;
+  row_tail_fill(g, s, e, n);
 }
 
 // ---- K4 (wide variant): one WARP per entity -------------------------------------------------------
@@ -609,6 +776,7 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
       s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
     }
     s.NCNT[e] = n;
+    row_tail_fill(g, s, e, n);
   }
 }
 
@@ -880,6 +1048,135 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
     // boundary pass of the next sweep on my own result (:344-376)
     if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
       apply_bounds(g, p.boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
+    Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
+    s.PXY[e] = pxy;
+  }
+}
+
+// ---- K6, second form: mask walk + converged exact pass -----------------------------------------
+// Same arithmetic, same order, same results as k_substep; what changed is the control flow.
+//   phase 1  walks the row without a data-dependent branch: row word, 16-byte partner gather,
+//            membership bits, float32 "surely apart" test -> ONE bit per row entry in a 64-bit
+//            register mask (rows longer than 64 are walked 64 entries at a time).  Four entries in
+//            flight; the only divergence left is the row length.
+//   phase 2  visits the set bits in ascending row position and runs the binary64 pair code from the
+//            entity's own point of view: d = me - partner, so the displacement of BOTH endpoints of
+//            a pair is +d/dist * h on its own side (negation is exact, so this is bit for bit the
+//            reference's `x[i] += ux` / `x[j] -= ux`, physics_worker.js:519-547); the static /
+//            trigger bookkeeping collapses to "do I move" and "does my partner".
+// A lane whose partner's row is capped (F_CAPPED) still resolves membership with row_find, inside
+// phase 2 and only for entries that passed the float32 test.
+__device__ __noinline__ void sweep_pair_coincident(const Params& p, const BySlot& s, uint32_t frame, uint32_t substep,
+                                                   uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
+                                                   float4 gt, bool lower, SubstepAcc& acc) {
+  exact_pair(p, s, frame, substep, e, x, y, r, fw, t, gt.x, gt.y, gt.z, __float_as_uint(gt.w), lower, acc);
+}
+
+__device__ __forceinline__ void sweep_pair(const Params* __restrict__ pp, double strength, const BySlot& s,
+                                           const Counters* __restrict__ ctr, uint32_t substep, uint32_t e,
+                                           float x, float y, float r, uint32_t fw, uint32_t t, float4 gt, bool lower,
+                                           SubstepAcc& acc) {
+  const double dx = dsub((double)x, (double)gt.x);                   // :447-449, seen from this entity
+  const double dy = dsub((double)y, (double)gt.y);
+  const double dist2 = dadd(dmul(dx, dx), dmul(dy, dy));
+  const double minDist = dadd((double)r, (double)gt.z);              // :452
+  if (dist2 >= dmul(minDist, minDist)) return;                       // :455
+  const double dist = __dsqrt_rn(dist2);
+  if (dist == 0) { sweep_pair_coincident(*pp, s, ctr->frame, substep, e, x, y, r, fw, t, gt, lower, acc); return; }   // :460-507
+  const double depth = dsub(minDist, dist);                          // :510
+  if (!(depth > 0)) return;
+  acc.hits++;                                                        // :551-552
+  acc.outHits += lower ? 1u : 0u;
+  const uint32_t ft = __float_as_uint(gt.w);
+  if (((fw | ft) & F_TRIGGER) || (fw & F_STATIC)) return;            // logged, not moved (:512); a static side stays
+  double nx, ny;
+  ddiv2(dx, dy, dist, nx, ny);                                       // :519-520
+  const double corr = dmul(depth, strength);                         // :528
+  const double h = (ft & F_STATIC) ? corr : dmul(corr, 0.5);         // :532-546
+  acc.x = fround(dadd((double)acc.x, dmul(nx, h)));
+  acc.y = fround(dadd((double)acc.y, dmul(ny, h)));
+}
+
+static constexpr int K6V2_THREADS = 256;
+
+// record of slot t in an array of GS float4 per slot: one IMAD.WIDE (slots are below 2^30)
+template <uint32_t GS>
+__device__ __forceinline__ const float4* slot_rec(const float4* __restrict__ G, uint32_t t) {
+  return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(G) + (size_t)t * (16u * GS));
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(K6V2_THREADS, 4)
+k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
+        float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
+        uint32_t substep) {
+  constexpr uint32_t GS = FIRST ? 2u : 1u;        // the first sweep reads the 32-byte slot records
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cellStart[g.cells]) return;
+  const float4 gme = Gin[e * GS];
+  float2 pxy;
+  if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
+  else pxy = s.PXY[e];
+  const float x = gme.x, y = gme.y, r = gme.z;
+  const uint32_t fw = __float_as_uint(gme.w);
+  SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
+  if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
+    const uint32_t cnt = s.NCNT[e];
+    const uint32_t xhead = s.XHEAD[e];
+    if (xhead == 0) {
+      // row entry k lives at NST[k * Npad + e]; Npad * Mpad < 2^32 (weed_create), so 32-bit indices
+      const uint32_t* __restrict__ NST = s.NST;
+      const uint32_t Npad = g.Npad;
+      const double strength = pp->responseStrength;
+      for (uint32_t kb = 0; kb < cnt; kb += 64) {
+        const uint32_t ke = min(cnt, kb + 64u);
+        // ---- phase 1: one bit per row entry that may overlap --------------------------------------
+        unsigned long long mask = 0;
+        uint32_t idx = kb * Npad + e;
+        for (uint32_t k = kb; k < ke; k += 4, idx += 4 * Npad) {
+          uint32_t wd[4];
+          float4 gt[4];
+          // the spatial pass pads every row to a multiple of four entries with words that carry no
+          // membership bit (row_tail_fill), so a batch never needs a bounds test
+#pragma unroll
+          for (int u = 0; u < 4; u++) wd[u] = NST[idx + (uint32_t)u * Npad];
+#pragma unroll
+          for (int u = 0; u < 4; u++) gt[u] = __ldg(slot_rec<GS>(Gin, wd[u] & NS_SLOT_MASK));
+          uint32_t nib = 0;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const uint32_t ft = __float_as_uint(gt[u].w);
+            const bool apart = surely_apart(x, y, r, gt[u].x, gt[u].y, gt[u].z);
+            const bool cand = ((ft & F_COLLIDER) == F_COLLIDER) & (wd[u] >= NS_OUT) & !apart;   // :441; OUT or BACK set
+            nib |= cand ? (1u << u) : 0u;
+          }
+          mask |= (unsigned long long)nib << (k - kb);
+        }
+        // ---- phase 2: exact pair code on the marked entries, in row order --------------------------
+        while (mask) {
+          const uint32_t k = kb + (uint32_t)__ffsll((long long)mask) - 1u;
+          mask &= mask - 1;
+          const uint32_t wd = NST[k * Npad + e];
+          const uint32_t t = wd & NS_SLOT_MASK;
+          const float4 gt = __ldg(slot_rec<GS>(Gin, t));
+          const bool lower = (wd & NS_OUT) != 0;
+          if (!lower && (__float_as_uint(gt.w) & F_CAPPED) && row_find(g, s, t, e) < 0) continue;
+          sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
+        }
+      }
+    } else {
+      substep_slow(g, *pp, s, Gin, GS, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+    }
+  }
+  const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
+  if (LAST) {
+    float4* o = reinterpret_cast<float4*>(s.OUT + e);
+    o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
+    o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
+  } else {
+    // boundary pass of the next sweep on my own result (:344-376)
+    if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
+      apply_bounds(g, pp->boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
     Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
     s.PXY[e] = pxy;
   }
