@@ -313,7 +313,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return WEED_E_INVALID; }
   if (cfg->struct_size != sizeof(weed_config)) { g_create_error = "weed_config.struct_size mismatch (ABI)"; return WEED_E_INVALID; }
   if (cfg->entityCount == 0 || cfg->entityCount > 0x3FFFFFF0u) { g_create_error = "entityCount out of range"; return WEED_E_INVALID; }
-  if (((double)cfg->entityCount + 32.0) * (double)(((cfg->maxNeighbors + 7) / 8) * 8) >= 4294967295.0) {
+  if (((double)cfg->entityCount + 128.0) * (double)(((cfg->maxNeighbors + 7) / 8) * 8) >= 4294967295.0) {
     g_create_error = "entityCount * maxNeighbors must stay below 2^32 per context (partition the world into slabs)";
     return WEED_E_INVALID;
   }
@@ -354,7 +354,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.N = cfg->entityCount;
   g.M = cfg->maxNeighbors;
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
-  g.Npad = ((g.N + 31) / 32) * 32;
+  g.Npad = ((g.N + TILE - 1) / TILE) * TILE;   // whole tiles: a tile's row words are one aligned bulk copy
   g.maxPairs = cfg->maxCollisionPairs;
   {
     const char* k4 = getenv("WEED_K4");   // diagnostic override, read once
@@ -381,6 +381,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
+  if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
   g.rowPitch = (g.M + 1 + 7u) & ~7u;
@@ -546,7 +547,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   else
     k_build_slots<false><<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->phys.subStepCount, false, ctx->d, ctx->s, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf, slab_cuts(ctx));
   if (recordAfterBuild) CK(cudaEventRecord(recordAfterBuild, st));
-  k_slot_prep<<<nb, 256, 0, st>>>(g, ctx->dParams, ctx->s, ctx->cellStart);
+  k_slot_prep<<<blocks_for(g.N, PREP_THREADS), PREP_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, ctx->cellStart);
   TIME_MARK(ctx, timing, 4);
   // long rows (the reference's own demos: maxNeighbors 400-1500) -> one warp per entity;
   // short rows (the large synthetic worlds) -> one thread per entity with staged flush
@@ -579,25 +580,35 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
   cudaStream_t st = ctx->stream;
   const unsigned tb = blocks_for(g.N, K6_THREADS);
   const int S = ctx->phys.subStepCount;
-  // substep 0 reads the slot records (stride 2), later ones ping-pong GA/GB
-  const float4* in = ctx->s.SA;
-  uint32_t gs = 2;
-  float4* bufs[2] = {ctx->s.GA, ctx->s.GB};
+  // sweep 0 reads GA (written by k_slot_prep), then GB / GA alternate
+  const float4* in = ctx->s.GA;
+  const uint32_t gs = 1;
+  float4* bufs[2] = {ctx->s.GB, ctx->s.GA};
+  const uint32_t kflags = ctx->cfg.flags;
   for (int step = 0; step < S; step++) {
     float4* out = bufs[step & 1];
     const bool first = step == 0, last = step == S - 1;
-    if (!(ctx->cfg.flags & WEED_FLAG_K6_V1)) {
+#define SWEEP_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step
+    if (kflags & WEED_FLAG_K6_V1) {
+      if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else if (first)          k_substep<true, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else if (last)           k_substep<false, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      else                     k_substep<false, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+    } else if (kflags & WEED_FLAG_K6_TILE) {
+      const unsigned sb = blocks_for(g.N, TILE);
+      if (first && last)       k_sweep_tile<true, true><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
+      else if (first)          k_sweep_tile<true, false><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
+      else if (last)           k_sweep_tile<false, true><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
+      else                     k_sweep_tile<false, false><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
+    } else {
       const unsigned sb = blocks_for(g.N, K6V2_THREADS);
-      if (first && last)       k_sweep<true, true><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else if (first)          k_sweep<true, false><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else if (last)           k_sweep<false, true><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else                     k_sweep<false, false><<<sb, K6V2_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
+      if (first && last)       k_sweep<true, true><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
+      else if (first)          k_sweep<true, false><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
+      else if (last)           k_sweep<false, true><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
+      else                     k_sweep<false, false><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
     }
-    else if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    else if (first)          k_substep<true, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    else if (last)           k_substep<false, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    else                     k_substep<false, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    if (!last) { in = out; gs = 1; }
+#undef SWEEP_ARGS
+    if (!last) in = out;     // k_pair_emit re-derives the pairs on the LAST sweep's input
   }
   TIME_MARK(ctx, timing, 7);
   k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->d, ctx->s, ctx->slotOf, ctx->tileCount);
@@ -675,6 +686,7 @@ extern "C" int weed_physics(weed_ctx* ctx, double dtRatio) {
   const GridDims& g = ctx->g;
   k_build_slots<true><<<blocks_for(g.N, 256), 256, 0, ctx->stream>>>(g, ctx->dParams, ctx->phys.subStepCount, true, ctx->d, ctx->s,
                                                                       ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf, slab_cuts(ctx));
+  k_slots_to_sweep_input<<<blocks_for(g.N, 256), 256, 0, ctx->stream>>>(g, ctx->s, ctx->cellStart);
   rc = launch_constraints(ctx, false);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));

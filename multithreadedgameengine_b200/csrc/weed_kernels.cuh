@@ -17,6 +17,7 @@
 //   id order   k_pair_emit     K7b collisionData emission by the tiles below the cap
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 #include <math_constants.h>
 
 #include "weed_device.cuh"
@@ -233,6 +234,7 @@ struct BySlot {
   OutRec* OUT;       // last-substep result
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
   uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
+  TileDesc* TD;      // one descriptor per TILE slots (k_slot_prep), or nullptr when no tiled kernel runs
 };
 
 // stable position: number of ids in my cell smaller than mine (cell lists are ascending in the
@@ -336,36 +338,78 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   s.SA[2 * (size_t)slot + 1] = make_float4(dp.z, dp.w, at.z, __uint_as_float(gid));
 }
 
-// ---- K3c: coalesced slot-order pass: query positions, scan windows, list heads ----------------
-__global__ void __launch_bounds__(256)
+// ---- K3c: coalesced slot-order pass: query positions, scan windows, list heads, tile descriptors ----
+static constexpr int PREP_THREADS = 256;     // two tiles per block
+static_assert(PREP_THREADS % TILE == 0, "a prep block covers whole tiles");
+
+__global__ void __launch_bounds__(PREP_THREADS)
 k_slot_prep(GridDims g, const Params* __restrict__ pp, BySlot s, const uint32_t* __restrict__ cellStart) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cellStart[g.cells]) return;
-  float4 lo = s.SA[2 * (size_t)e], hi = s.SA[2 * (size_t)e + 1];
-  const bool moved = (__float_as_uint(lo.w) & F_MOVED) != 0;     // integrated: px,py hold the pre-move position
-  const float x0 = moved ? hi.x : lo.x, y0 = moved ? hi.y : lo.y;
-  s.QXY[e] = make_float2(x0, y0);
-  // The boundary pass of the FIRST sweep (physics_worker.js:344-376) is applied here, once the
-  // query position is safe in QXY: every sweep then reads positions that already had their
-  // pass, and k_substep applies the NEXT sweep's pass to its own result before storing it.
-  if (moved && !clear_of_walls(g, lo.x, lo.y, lo.z)) {
-    apply_bounds(g, pp->boundaryElasticity, lo.z, lo.x, lo.y, hi.x, hi.y);
-    s.SA[2 * (size_t)e] = lo;
-    s.SA[2 * (size_t)e + 1] = hi;
-  }
-  Window w;
+  const bool live = e < cellStart[g.cells];
   int4 wi = make_int4(1, 0, 1, 0);
-  if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
-  s.WIN[e] = wi;
-  s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
-                       (uint32_t)wi.z | ((uint32_t)wi.w << 16));
-  // CX_EDGE clear: my unclamped centre cell is my (clamped) grid cell and trunc == floor.  Two
-  // such entities with the same visualRange that pass 0 < d2 < vr^2 always lie in each other's
-  // window: |x_a - x_b| < vr  =>  |floor(x_a inv) - floor(x_b inv)| <= ceil(vr inv).
-  const int32_t ucol = js_toint32(dmul((double)x0, g.inv)), urow = js_toint32(dmul((double)y0, g.inv));
-  const bool inside = x0 >= 0.f && y0 >= 0.f && ucol >= 0 && ucol < g.cols && urow >= 0 && urow < g.rows;
-  s.CXY[e] = make_float4(x0, y0, hi.z, __uint_as_float(__float_as_uint(hi.w) | (inside ? 0u : CX_EDGE)));
-  s.XHEAD[e] = 0;
+  if (live) {
+    float4 lo = s.SA[2 * (size_t)e], hi = s.SA[2 * (size_t)e + 1];
+    const bool moved = (__float_as_uint(lo.w) & F_MOVED) != 0;     // integrated: px,py hold the pre-move position
+    const float x0 = moved ? hi.x : lo.x, y0 = moved ? hi.y : lo.y;
+    s.QXY[e] = make_float2(x0, y0);
+    // The boundary pass of the FIRST sweep (physics_worker.js:344-376) is applied here, once the
+    // query position is safe in QXY: every sweep then reads positions that already had their
+    // pass, and the sweep kernel applies the NEXT sweep's pass to its own result before storing it.
+    if (moved && !clear_of_walls(g, lo.x, lo.y, lo.z)) {
+      apply_bounds(g, pp->boundaryElasticity, lo.z, lo.x, lo.y, hi.x, hi.y);
+      s.SA[2 * (size_t)e] = lo;
+      s.SA[2 * (size_t)e + 1] = hi;
+    }
+    s.GA[e] = lo;                                                  // what the first sweep gathers: x, y, radius, flags (16 B, not the 32 B slot record)
+    Window w;
+    if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
+    s.WIN[e] = wi;
+    s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
+                         (uint32_t)wi.z | ((uint32_t)wi.w << 16));
+    // CX_EDGE clear: my unclamped centre cell is my (clamped) grid cell and trunc == floor.  Two
+    // such entities with the same visualRange that pass 0 < d2 < vr^2 always lie in each other's
+    // window: |x_a - x_b| < vr  =>  |floor(x_a inv) - floor(x_b inv)| <= ceil(vr inv).
+    const int32_t ucol = js_toint32(dmul((double)x0, g.inv)), urow = js_toint32(dmul((double)y0, g.inv));
+    const bool inside = x0 >= 0.f && y0 >= 0.f && ucol >= 0 && ucol < g.cols && urow >= 0 && urow < g.rows;
+    s.CXY[e] = make_float4(x0, y0, hi.z, __uint_as_float(__float_as_uint(hi.w) | (inside ? 0u : CX_EDGE)));
+    s.XHEAD[e] = 0;
+  }
+  if (!s.TD) return;                                               // uniform: no tiled kernel in this context
+  // ---- tile descriptor: union of the tile's windows, one slot range per grid row --------------------
+  __shared__ int32_t sWin[PREP_THREADS / 32][4];
+  const bool has = wi.x <= wi.y;                                   // an empty window contributes nothing
+  const int32_t r0 = __reduce_min_sync(0xffffffffu, has ? wi.x : 0x7fffffff);
+  const int32_t r1 = __reduce_max_sync(0xffffffffu, has ? wi.y : -1);
+  const int32_t c0 = __reduce_min_sync(0xffffffffu, has ? wi.z : 0x7fffffff);
+  const int32_t c1 = __reduce_max_sync(0xffffffffu, has ? wi.w : -1);
+  const uint32_t warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sWin[warp][0] = r0; sWin[warp][1] = r1; sWin[warp][2] = c0; sWin[warp][3] = c1; }
+  __syncthreads();
+  if (threadIdx.x % TILE == 0) {
+    int32_t R0 = 0x7fffffff, R1 = -1, C0 = 0x7fffffff, C1 = -1;
+    for (uint32_t w = warp; w < warp + TILE / 32; w++) {
+      R0 = min(R0, sWin[w][0]); R1 = max(R1, sWin[w][1]); C0 = min(C0, sWin[w][2]); C1 = max(C1, sWin[w][3]);
+    }
+    TileDesc d;
+    d.a[0] = d.a[1] = d.a[2] = 0; d.n[0] = d.n[1] = d.n[2] = 0; d.r0c0 = 0; d.shape = 0;
+    if (R1 >= R0 && R1 - R0 < 3) {
+      for (int32_t r = 0; r <= R1 - R0; r++) {
+        const uint32_t a = cellStart[(uint32_t)(R0 + r) * g.cols + C0];
+        d.a[r] = a;
+        d.n[r] = cellStart[(uint32_t)(R0 + r) * g.cols + C1 + 1] - a;
+      }
+      d.r0c0 = (uint32_t)R0 | ((uint32_t)C0 << 16);
+      d.shape = (uint32_t)min(C1 - C0 + 1, 0xFFFF) | ((uint32_t)(R1 - R0 + 1) << 16) | TD_OK;
+    }
+    s.TD[e / TILE] = d;
+  }
+}
+
+// first sweep input after a separate weed_spatial + weed_physics: the slot records were rewritten
+__global__ void __launch_bounds__(256)
+k_slots_to_sweep_input(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < cellStart[g.cells]) s.GA[e] = s.SA[2 * (size_t)e];
 }
 
 // ---- K4: capped, ordered neighbor gather (spatial_worker.js:195-277) ---------------------
@@ -539,6 +583,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   // capped row: my row may be missing partners; K4b finds the lower-id ones
   if (n >= M && M > 0) {
     reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
     ctr->anyCapped = 1;
     s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
   }
@@ -699,6 +744,7 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
   // capped row: my row may be missing partners; K4b finds the lower-id ones
   if (n >= M && M > 0) {
     reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
     ctr->anyCapped = 1;
     s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
   }
@@ -772,6 +818,7 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
     if (WRITE_ROWS) { nd[rowBase] = (int32_t)n; dd[rowBase] = (float)n; }   // :274-275
     if (n >= M && M > 0) {
       reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+      reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
       ctr->anyCapped = 1;
       s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
     }
@@ -1097,23 +1144,31 @@ __device__ __forceinline__ void sweep_pair(const Params* __restrict__ pp, double
   acc.y = fround(dadd((double)acc.y, dmul(ny, h)));
 }
 
-static constexpr int K6V2_THREADS = 256;
-
-// record of slot t in an array of GS float4 per slot: one IMAD.WIDE (slots are below 2^30)
-template <uint32_t GS>
+// record of slot t in an array of 16-byte records: one IMAD.WIDE (slots are below 2^30)
 __device__ __forceinline__ const float4* slot_rec(const float4* __restrict__ G, uint32_t t) {
-  return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(G) + (size_t)t * (16u * GS));
+  return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(G) + (size_t)t * 16u);
 }
 
+// Tuning (config 4, 16M entities, one B200, ms per sweep): 256 threads / 64 registers 1.81; 128 threads
+// 1.68; + next batch's row words prefetched 1.63; 48 registers (10 blocks/SM) 1.56; 40 registers
+// (12 blocks/SM) 1.50; 36 / 32 registers 1.62 / 1.63 (spills).  The walk is bound by the latency of
+// the partner gathers, so occupancy pays until the spills start.
+#ifndef WEED_K6V2_THREADS
+#define WEED_K6V2_THREADS 128
+#endif
+#ifndef WEED_K6V2_MINBLOCKS
+#define WEED_K6V2_MINBLOCKS 12
+#endif
+static constexpr int K6V2_THREADS = WEED_K6V2_THREADS;
+
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(K6V2_THREADS, 4)
+__global__ void __launch_bounds__(K6V2_THREADS, WEED_K6V2_MINBLOCKS)
 k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
         float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
         uint32_t substep) {
-  constexpr uint32_t GS = FIRST ? 2u : 1u;        // the first sweep reads the 32-byte slot records
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
-  const float4 gme = Gin[e * GS];
+  const float4 gme = Gin[e];
   float2 pxy;
   if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
   else pxy = s.PXY[e];
@@ -1133,15 +1188,22 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
         // ---- phase 1: one bit per row entry that may overlap --------------------------------------
         unsigned long long mask = 0;
         uint32_t idx = kb * Npad + e;
+        // the spatial pass pads every row to a multiple of four entries with words that carry no
+        // membership bit (row_tail_fill), so a batch never needs a bounds test
+        uint32_t nx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) nx[u] = NST[idx + (uint32_t)u * Npad];
         for (uint32_t k = kb; k < ke; k += 4, idx += 4 * Npad) {
           uint32_t wd[4];
           float4 gt[4];
-          // the spatial pass pads every row to a multiple of four entries with words that carry no
-          // membership bit (row_tail_fill), so a batch never needs a bounds test
 #pragma unroll
-          for (int u = 0; u < 4; u++) wd[u] = NST[idx + (uint32_t)u * Npad];
+          for (int u = 0; u < 4; u++) wd[u] = nx[u];
+          if (k + 4 < ke) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) gt[u] = __ldg(slot_rec<GS>(Gin, wd[u] & NS_SLOT_MASK));
+            for (int u = 0; u < 4; u++) nx[u] = NST[idx + (uint32_t)(4 + u) * Npad];     // the next batch's words, in flight behind the gathers
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) gt[u] = __ldg(slot_rec(Gin, wd[u] & NS_SLOT_MASK));
           uint32_t nib = 0;
 #pragma unroll
           for (int u = 0; u < 4; u++) {
@@ -1158,16 +1220,179 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
           mask &= mask - 1;
           const uint32_t wd = NST[k * Npad + e];
           const uint32_t t = wd & NS_SLOT_MASK;
-          const float4 gt = __ldg(slot_rec<GS>(Gin, t));
+          const float4 gt = __ldg(slot_rec(Gin, t));
           const bool lower = (wd & NS_OUT) != 0;
           if (!lower && (__float_as_uint(gt.w) & F_CAPPED) && row_find(g, s, t, e) < 0) continue;
           sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
         }
       }
     } else {
-      substep_slow(g, *pp, s, Gin, GS, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+      substep_slow(g, *pp, s, Gin, 1u, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
+  const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
+  if (LAST) {
+    float4* o = reinterpret_cast<float4*>(s.OUT + e);
+    o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
+    o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
+  } else {
+    // boundary pass of the next sweep on my own result (:344-376)
+    if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
+      apply_bounds(g, pp->boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
+    Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
+    s.PXY[e] = pxy;
+  }
+}
+
+// ---- K6, tiled form (measured alternative, WEED_FLAG_K6_TILE): TMA-staged partners and row words ------
+// One block per tile of TILE consecutive slots.  Thread 0 issues 1-D bulk copies (cp.async.bulk,
+// completion on an mbarrier): the tile's partner ranges of the sweep input (TileDesc: at most three
+// contiguous slot ranges hold every partner of every entity of the tile) and the tile's row words,
+// 8 rows x TILE words first, the rest of a 16-row group once the longest row of the tile is known.
+// The walk of k_sweep then runs out of shared memory.  Tiles whose ranges do not fit (a block that
+// straddles two grid rows, an observer with a huge visualRange, hundreds of entities per cell)
+// gather from global memory as k_sweep does.
+// Measured (config 4, 16M, one B200): 2.12 ms per sweep against 1.50 for k_sweep — the bulk copies
+// remove the gather stalls, but a block cannot overlap its own fill with its own walk, 24.6 KB of
+// shared memory hold occupancy at 8 blocks, and the slot -> tile position arithmetic adds 40 % to the
+// instruction count; a 32-row group (2.57 ms) is worse still.  Kept selectable for the cross-check tests.
+static constexpr int K6T_CAP = 1024;        // partner records per tile (16 KB)
+static constexpr int K6T_GROUP = 16;        // row entries walked per group: a wave of 8 rows, then the rest
+
+struct TileMap { uint32_t a1, a2, d0, d1, d2; };   // slot -> position in the staged ranges
+__device__ __forceinline__ uint32_t tile_pos(const TileMap& m, uint32_t t) {
+  return t + (t >= m.a2 ? m.d2 : (t >= m.a1 ? m.d1 : m.d0));
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(TILE, 8)
+k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
+             float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
+             uint32_t substep) {
+  __shared__ __align__(128) float4 tG[K6T_CAP];
+  __shared__ __align__(128) uint32_t tRow[K6T_GROUP][TILE];
+  __shared__ __align__(8) unsigned long long bars[3];       // 0: partner ranges, 1 / 2: row words, first wave / rest
+  __shared__ uint32_t sMax[TILE / 32];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t tile0 = blockIdx.x * TILE;
+  const uint32_t A = cellStart[g.cells];
+  if (tile0 >= A) return;                                    // whole block past the last slot
+  const uint32_t e = tile0 + tid;
+  const TileDesc td = s.TD[blockIdx.x];
+  const uint32_t total = td.n[0] + td.n[1] + td.n[2];
+  const bool tiled = (td.shape & TD_OK) && total <= (uint32_t)K6T_CAP;
+  const uint32_t* __restrict__ NST = s.NST;
+  const uint32_t Npad = g.Npad;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init_fence();
+    mbar_expect_tx(&bars[1], 8u * TILE * 4u);                // rows 0..7 of this tile: needed by every non-empty row
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++) bulk_g2s(&tRow[j][0], NST + j * Npad + tile0, TILE * 4u, &bars[1]);
+    if (tiled) {
+      mbar_expect_tx(&bars[0], total * 16u);
+      uint32_t off = 0;
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        if (td.n[r]) { bulk_g2s(tG + off, Gin + td.a[r], td.n[r] * 16u, &bars[0]); off += td.n[r]; }
+    }
+  }
+  TileMap tm;
+  tm.a1 = td.n[1] ? td.a[1] : 0xFFFFFFFFu;
+  tm.a2 = td.n[2] ? td.a[2] : 0xFFFFFFFFu;
+  tm.d0 = 0u - td.a[0];
+  tm.d1 = td.n[0] - td.a[1];
+  tm.d2 = td.n[0] + td.n[1] - td.a[2];
+  const bool live = e < A;
+  float4 gme = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 pxy = make_float2(0.f, 0.f);
+  if (live) {
+    gme = Gin[e];
+    if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
+    else pxy = s.PXY[e];
+  }
+  const float x = gme.x, y = gme.y, r = gme.z;
+  const uint32_t fw = __float_as_uint(gme.w);
+  SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
+  const bool collider = live && (fw & F_COLLIDER) == F_COLLIDER;     // :430
+  uint32_t cnt = 0, xhead = 0;
+  if (collider) { cnt = s.NCNT[e]; xhead = s.XHEAD[e]; }
+  const bool slow = xhead != 0;
+  const uint32_t walk = slow ? 0u : cnt;                     // rows walked here; explicit lists take substep_slow
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, walk);
+  if ((tid & 31) == 0) sMax[tid >> 5] = wmax;
+  __syncthreads();                                           // barrier inits and the warps' maxima visible to everyone
+  uint32_t blockMax = 0;
+#pragma unroll
+  for (int w = 0; w < TILE / 32; w++) blockMax = max(blockMax, sMax[w]);
+  if (tid == 0 && blockMax > 8) {
+    const uint32_t nr = min((uint32_t)K6T_GROUP - 8u, (blockMax - 8u + 3u) & ~3u);
+    mbar_expect_tx(&bars[2], nr * TILE * 4u);
+    for (uint32_t j = 0; j < nr; j++) bulk_g2s(&tRow[8 + j][0], NST + (8 + j) * Npad + tile0, TILE * 4u, &bars[2]);
+  }
+  const double strength = pp->responseStrength;
+  if (tiled) mbar_wait(&bars[0], 0);
+  auto walk_rows = [&](auto tiledTag) {
+    constexpr bool TILED = decltype(tiledTag)::value;
+    uint32_t par = 0;                                          // phase parity of bars[1], bars[2]
+    for (uint32_t k0 = 0;; k0 += K6T_GROUP) {
+      mbar_wait(&bars[1], par);                                // rows k0 .. k0+7 (always issued for k0 == 0)
+      const uint32_t ke = min(walk, k0 + (uint32_t)K6T_GROUP);
+      // ---- phase 1: one bit per row entry that may overlap ------------------------------------------
+      uint32_t mask = 0;
+      for (uint32_t k = k0; k < ke; k += 4) {
+        if (k == k0 + 8) mbar_wait(&bars[2], par);             // the rest of the group
+        uint32_t wd[4];
+        float4 gt[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) wd[u] = tRow[k - k0 + (uint32_t)u][tid];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t t = wd[u] & NS_SLOT_MASK;
+          if (TILED) gt[u] = tG[tile_pos(tm, t)]; else gt[u] = __ldg(Gin + t);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t ft = __float_as_uint(gt[u].w);
+          const bool apart = surely_apart(x, y, r, gt[u].x, gt[u].y, gt[u].z);
+          const bool cand = ((ft & F_COLLIDER) == F_COLLIDER) & (wd[u] >= NS_OUT) & !apart;   // :441; OUT or BACK set
+          mask |= cand ? (1u << (k - k0 + (uint32_t)u)) : 0u;
+        }
+      }
+      // ---- phase 2: exact pair code on the marked entries, in row order ------------------------------
+      while (mask) {
+        const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1;
+        const uint32_t wd = tRow[j][tid];
+        const uint32_t t = wd & NS_SLOT_MASK;
+        float4 gt;
+        if (TILED) gt = tG[tile_pos(tm, t)]; else gt = __ldg(Gin + t);
+        const bool lower = (wd & NS_OUT) != 0;
+        if (!lower && (__float_as_uint(gt.w) & F_CAPPED) && row_find(g, s, t, e) < 0) continue;
+        sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
+      }
+      if (k0 + K6T_GROUP >= blockMax) break;
+      // ---- next group of rows (dense tiles only) --------------------------------------------------------
+      // lanes that never waited on bars[2] in this group still observe its phase before it is re-armed
+      if (blockMax > k0 + 8) mbar_wait(&bars[2], par);
+      __syncthreads();                                         // everyone is done with tRow
+      par ^= 1;
+      if (tid == 0) {
+        const uint32_t left = blockMax - (k0 + K6T_GROUP);
+        const uint32_t n1 = min(8u, (left + 3u) & ~3u);
+        mbar_expect_tx(&bars[1], n1 * TILE * 4u);
+        for (uint32_t j = 0; j < n1; j++) bulk_g2s(&tRow[j][0], NST + (k0 + K6T_GROUP + j) * Npad + tile0, TILE * 4u, &bars[1]);
+        if (left > 8) {
+          const uint32_t n2 = min((uint32_t)K6T_GROUP - 8u, (left - 8u + 3u) & ~3u);
+          mbar_expect_tx(&bars[2], n2 * TILE * 4u);
+          for (uint32_t j = 0; j < n2; j++) bulk_g2s(&tRow[8 + j][0], NST + (k0 + K6T_GROUP + 8 + j) * Npad + tile0, TILE * 4u, &bars[2]);
+        }
+      }
+    }
+  };
+  if (tiled) walk_rows(std::true_type{}); else walk_rows(std::false_type{});
+  if (!live) return;
+  if (slow) substep_slow(g, *pp, s, Gin, 1u, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
   if (LAST) {
     float4* o = reinterpret_cast<float4*>(s.OUT + e);

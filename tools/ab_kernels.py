@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B measurement of kernel generations on one GPU (diagnostic; not part of bench.py).
 
-For every variant (a combination of WEED_FLAG_K4_V1 / WEED_FLAG_K6_V1) the same seeded scene is
+For every variant (a combination of WEED_FLAG_K4_V1 / WEED_FLAG_K6_V1 / WEED_FLAG_K6_TILE) the same seeded scene is
 run for --warmup + --frames frames with per-span CUDA-event timing (WEED_FLAG_KERNEL_TIMING);
 the mean span times over the timed frames are printed, together with a hash of the final state,
 of collisionData and of a sample of API rows, so that a variant that is faster but different is
@@ -31,14 +31,17 @@ def main():
     ap.add_argument("--entities", type=int, default=None)
     ap.add_argument("--frames", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--variants", default="22,11", help="comma list of <K4 generation><K6 generation>, e.g. 22,12,21,11")
+    ap.add_argument("--variants", default="22,11", help="comma list of <K4 form><K6 form>: 1 = round 1, 2 = current, T = TMA tiles (K6 only), e.g. 22,2T,11")
     ap.add_argument("--rows", type=int, default=200_000, help="API rows hashed per sample block (3 blocks)")
+    ap.add_argument("--lib", default=None, help="tag of an experimental build (tools/build_variant.sh) to load instead of the product library")
     args = ap.parse_args()
 
+    from multithreadedgameengine_b200 import binding as B
+    if args.lib:          # before anything loads the library
+        B.LIB_PATH = os.path.join(os.path.dirname(B.LIB_PATH), "exp", f"libweedgpu_{args.lib}.so")
     import __graft_entry__ as entry
     entry.build()
     from bench import workload
-    from multithreadedgameengine_b200 import binding as B
     from multithreadedgameengine_b200.engine import GameEngine
 
     cfg, cols = workload(args.workload, args.entities)
@@ -47,10 +50,8 @@ def main():
     results = []
     for v in args.variants.split(","):
         flags = B.FLAG_KERNEL_TIMING
-        if v[0] == "1":
-            flags |= B.FLAG_K4_V1
-        if v[1] == "1":
-            flags |= B.FLAG_K6_V1
+        flags |= {"1": B.FLAG_K4_V1, "2": 0}[v[0]]
+        flags |= {"1": B.FLAG_K6_V1, "2": 0, "T": B.FLAG_K6_TILE}[v[1]]
         eng = GameEngine(cfg, flags=flags, host_neighbor_rows=False)
         eng.load_columns(cols)
         eng.run(args.warmup)
@@ -87,7 +88,7 @@ def main():
             hr.update(nd[keep].tobytes())
             hr.update(dd[keep].tobytes())
         st = eng.stats()
-        res = {"variant": f"K4 v{v[0]} / K6 v{v[1]}", "entities": N, "frames": f"{args.warmup}..{args.warmup + args.frames}",
+        res = {"lib": args.lib or "product", "variant": f"K4 v{v[0]} / K6 v{v[1]}", "entities": N, "frames": f"{args.warmup}..{args.warmup + args.frames}",
                "span_ms": {n: round(float(x), 4) for n, x in zip(SPANS, ms)},
                "K6_ms_per_sweep": round(float(ms[6]) / S, 4), "sum_ms": round(float(ms.sum()), 4),
                "device_frame_ms": round(dev / args.frames, 4),
