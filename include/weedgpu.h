@@ -215,20 +215,30 @@ int weed_sync(weed_ctx* ctx);
 int weed_get_stats(weed_ctx* ctx, weed_stats* out);
 const char* weed_last_error(weed_ctx* ctx);   /* ctx may be NULL: last create() failure */
 
-/* device-resident access for in-process consumers (bench harness, multi-GPU plumbing):
- * raw device pointers of the API-visible mirrors.                                      */
+/* device-resident access for in-process consumers (bench harness, multi-GPU plumbing,
+ * device-side systems): raw device pointers.
+ *
+ * On the device the rows of neighborData / distanceData are stored as slot-major planes, not
+ * in the reference's row layout: entry k of the entity in grid slot s is word
+ * k * weed_row_pitch() + s of WEED_DEV_NEIGHBOR / WEED_DEV_DISTANCE, its count is
+ * WEED_DEV_NEIGHBOR_COUNT[s], and the slot of entity i this frame is WEED_DEV_SLOT_OF[i]
+ * (0xFFFFFFFF: inactive or NaN position, i.e. not in the grid; the reference leaves such a
+ * row stale).  Consecutive slots are consecutive grid cells, so the scan kernel's stores are
+ * whole cache lines; the row layout of gameEngine.js:552-559 exists in the host buffers,
+ * which weed_fetch_neighbors / weed_download(WEED_COL_NEIGHBORS) fill through a gather.   */
 typedef enum weed_devptr_id {
-  WEED_DEV_NEIGHBOR  = 0,  /* int32  [N*weed_row_pitch()] */
-  WEED_DEV_DISTANCE  = 1,  /* float  [N*weed_row_pitch()] */
+  WEED_DEV_NEIGHBOR  = 0,  /* int32  [maxNeighbors rounded up to 8][weed_row_pitch()]   */
+  WEED_DEV_DISTANCE  = 1,  /* float  [same]                                              */
   WEED_DEV_COLLISION = 2,  /* int32  [1+2*maxPairs] */
   WEED_DEV_STATE     = 3,  /* float4 [N] {x, y, px, py}, see DESIGN.md                  */
   WEED_DEV_ATTR      = 4,  /* float4 [N] {maxVel, radius, visualRange, velocityAngle}   */
-  WEED_DEV_VEL       = 5   /* float4 [N] {vx, vy, speed, -}                             */
+  WEED_DEV_VEL       = 5,  /* float4 [N] {vx, vy, speed, -}                             */
+  WEED_DEV_NEIGHBOR_COUNT = 6, /* uint32 [N] by grid slot                               */
+  WEED_DEV_SLOT_OF   = 7   /* uint32 [N] by entity index                                */
 } weed_devptr_id;
 int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes);
-/* Words between two rows of the DEVICE copies of neighborData / distanceData: 1 + maxNeighbors
- * rounded up to 8, so that every row starts on a 32-byte sector (the host buffers keep the
- * reference's stride of 1 + maxNeighbors, gameEngine.js:552-559; fetches are pitched copies). */
+/* Words between two planes of the DEVICE copies of neighborData / distanceData (the entity
+ * count rounded up to 128).                                                               */
 uint32_t weed_row_pitch(weed_ctx* ctx);
 
 /* ---- device-side consumers of the neighbor rows ("systems") ----------------

@@ -42,7 +42,7 @@ FLAG_K4_V1 = 1 << 8
 FLAG_K6_V1 = 1 << 9
 FLAG_K6_TILE = 1 << 10
 
-DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL = range(6)
+DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL, DEV_NEIGHBOR_COUNT, DEV_SLOT_OF = range(8)
 
 
 class PhysicsConfig(C.Structure):

@@ -155,8 +155,9 @@ struct weed_ctx {
   // by slot
   BySlot s{};
   // outputs
-  int32_t* nd = nullptr; float* dd = nullptr; int32_t* coll = nullptr;
+  int32_t* nd = nullptr; float* dd = nullptr; int32_t* coll = nullptr;   // API rows as slot-major planes (RowView)
   size_t rowWords = 0;
+  int32_t* mnd = nullptr; float* mdd = nullptr;   // the rows in the reference's layout, filled on demand (k_rows_gather)
   // control
   Params* dParams = nullptr;
   Counters* dCtr = nullptr;
@@ -379,13 +380,12 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
-  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N); A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
+  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
-  g.rowPitch = (g.M + 1 + 7u) & ~7u;
-  ctx->rowWords = N * (size_t)g.rowPitch;
+  ctx->rowWords = (size_t)g.Npad * g.Mpad;
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
   A(ctx->coll, 1 + 2 * (size_t)g.maxPairs);
   A(ctx->dParams, 1); A(ctx->dCtr, 1);
@@ -449,23 +449,35 @@ static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = null
   return WEED_OK;
 }
 
-// API rows device -> host.  On the device a row starts on a 32-byte sector boundary (pitch =
-// 1 + maxNeighbors rounded up to 8 words); the host buffers keep the reference's stride of
-// 1 + maxNeighbors words (gameEngine.js:552-559), so the copy is a pitched one.  `absolute`:
-// the destination is the whole bound buffer (row `first` lands at its own offset), otherwise
-// the destination starts at row `first`.
+// API rows device -> host.  The scan kernels keep the rows as slot-major planes (RowView); the
+// reference's layout (row i at i * (1 + maxNeighbors), gameEngine.js:552-559) is produced on demand:
+// k_rows_gather writes header + entries of the requested rows into a device mirror that has the host
+// stride and persists (so the words past 1 + count and the rows of entities that are not in the grid
+// keep their old contents, as in the reference), then the mirror rows go to the host in one copy.
+// `absolute`: the destination is the whole bound buffer (row `first` lands at its own offset),
+// otherwise the destination starts at row `first`.
+static RowView row_view(weed_ctx* ctx) {
+  return RowView{ctx->nd, ctx->dd, ctx->s.NCNT, ctx->slotOf, ctx->g.Npad};
+}
+
 static int copy_rows(weed_ctx* ctx, void* nd_host, void* dd_host, uint32_t first, uint32_t count, bool absolute,
                      cudaStream_t stream) {
   if (!count) return WEED_OK;
-  const size_t hostStride = (1 + (size_t)ctx->g.M) * 4, devPitch = (size_t)ctx->g.rowPitch * 4;
-  const size_t hostOff = absolute ? (size_t)first * hostStride : 0;
-  const size_t devOff = (size_t)first * ctx->g.rowPitch;
-  if (nd_host)
-    CK(cudaMemcpy2DAsync((uint8_t*)nd_host + hostOff, hostStride, ctx->nd + devOff, devPitch, hostStride, count,
-                         cudaMemcpyDeviceToHost, stream));
-  if (dd_host)
-    CK(cudaMemcpy2DAsync((uint8_t*)dd_host + hostOff, hostStride, ctx->dd + devOff, devPitch, hostStride, count,
-                         cudaMemcpyDeviceToHost, stream));
+  const size_t hostWords = 1 + (size_t)ctx->g.M;
+  if (!ctx->mnd) {
+    int rc = dalloc(ctx, &ctx->mnd, (size_t)ctx->g.N * hostWords);
+    if (rc) return rc;
+    rc = dalloc(ctx, &ctx->mdd, (size_t)ctx->g.N * hostWords);
+    if (rc) return rc;
+    if (stream != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));     // the zero fill ran on the context's stream
+  }
+  k_rows_gather<<<(unsigned)(((size_t)count * 32 + 255) / 256), 256, 0, stream>>>(row_view(ctx), first, count, (uint32_t)hostWords,
+                                                                                 ctx->mnd, ctx->mdd);
+  CK(cudaGetLastError());
+  const size_t off = (size_t)first * hostWords, bytes = (size_t)count * hostWords * 4;
+  const size_t hostOff = absolute ? off * 4 : 0;
+  if (nd_host) CK(cudaMemcpyAsync((uint8_t*)nd_host + hostOff, ctx->mnd + off, bytes, cudaMemcpyDeviceToHost, stream));
+  if (dd_host) CK(cudaMemcpyAsync((uint8_t*)dd_host + hostOff, ctx->mdd + off, bytes, cudaMemcpyDeviceToHost, stream));
   return WEED_OK;
 }
 
@@ -836,7 +848,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   return WEED_OK;
 }
 
-extern "C" uint32_t weed_row_pitch(weed_ctx* ctx) { return ctx ? ctx->g.rowPitch : 0u; }
+extern "C" uint32_t weed_row_pitch(weed_ctx* ctx) { return ctx ? ctx->g.Npad : 0u; }
 
 extern "C" int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, size_t* bytes) {
   if (!ctx || !out) return WEED_E_INVALID;
@@ -849,6 +861,8 @@ extern "C" int weed_device_ptr(weed_ctx* ctx, weed_devptr_id which, void** out, 
     case WEED_DEV_STATE: p = ctx->d.DP; b = N * 16; break;
     case WEED_DEV_ATTR: p = ctx->d.AT; b = N * 16; break;
     case WEED_DEV_VEL: p = ctx->d.V; b = N * 16; break;
+    case WEED_DEV_NEIGHBOR_COUNT: p = ctx->s.NCNT; b = N * 4; break;
+    case WEED_DEV_SLOT_OF: p = ctx->slotOf; b = N * 4; break;
     default: return fail(ctx, WEED_E_INVALID, "bad devptr id");
   }
   *out = p;
@@ -949,7 +963,7 @@ static int run_flock(weed_ctx* ctx, const FlockParams& fp, const float* protecte
     if (!ctx->protRange) { int rc = dalloc(ctx, &ctx->protRange, N); if (rc) return rc; }
     CK(cudaMemcpyAsync(ctx->protRange, protectedRange, N * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
-  k_system_flock<<<blocks_for(N, 128), 128, 0, ctx->stream>>>(ctx->g, fp, ctx->d, ctx->nd, ctx->dd,
+  k_system_flock<<<blocks_for(N, 128), 128, 0, ctx->stream>>>(ctx->g, fp, ctx->d, row_view(ctx),
                                                               protectedRange ? ctx->protRange : nullptr);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1112,7 +1126,7 @@ extern "C" int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLight
     ctx->shLightCap = maxShadowCastingLights;
   }
   int rc = sys_tiles(ctx, N); if (rc) return rc;
-  ShadowParams p{maxShadowCastingLights, maxShadowsPerLight, maxShadowSprites, ctx->g.rowPitch};
+  ShadowParams p{maxShadowCastingLights, maxShadowsPerLight, maxShadowSprites, 0u};
   ShadowIn in{ctx->shLightActive, ctx->shIntensity, ctx->shCasterActive, ctx->shRadius, ctx->shHeight, ctx->onScreen};
   const size_t S = maxShadowSprites;
   ShadowOut o{ctx->shOutActive, ctx->shOut, ctx->shOut + S, ctx->shOut + 2 * S, ctx->shOut + 3 * S,
@@ -1120,9 +1134,9 @@ extern "C" int weed_system_shadows(weed_ctx* ctx, uint32_t maxShadowCastingLight
   const unsigned blocks = (unsigned)((N + SYS_TILE - 1) / SYS_TILE);
   k_shadow_lights<<<blocks, SYS_TILE, 0, st>>>((uint32_t)N, in, ctx->d.F, ctx->sysTileCount);
   k_tile_scan<<<1, 1024, 0, st>>>(ctx->sysTileCount, ctx->sysTilePrefix, blocks, ctx->shScalars);
-  k_shadow_count<<<blocks, SYS_TILE, 0, st>>>((uint32_t)N, p, in, ctx->d.F, ctx->sysTilePrefix, ctx->nd, ctx->dd,
+  k_shadow_count<<<blocks, SYS_TILE, 0, st>>>((uint32_t)N, p, in, ctx->d.F, ctx->sysTilePrefix, row_view(ctx),
                                               ctx->shLightId, ctx->shLightCount);
-  k_shadow_emit<<<1, 256, 0, st>>>(p, in, ctx->d.F, ctx->d.DP, ctx->shScalars, ctx->nd, ctx->dd, ctx->shLightId,
+  k_shadow_emit<<<1, 256, 0, st>>>(p, in, ctx->d.F, ctx->d.DP, ctx->shScalars, row_view(ctx), ctx->shLightId,
                                    ctx->shLightCount, o, ctx->shScalars + 1);
   CK(cudaGetLastError());
   uint32_t n = 0;

@@ -469,7 +469,6 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     vr = me.z; id = __float_as_uint(me.w) & ~CX_EDGE; edge = __float_as_uint(me.w) & CX_EDGE;
     win = s.WIN[e];
   }
-  const uint32_t lid = (live && s.SLID) ? s.SLID[e] : id;    // row address: local index
   bool done = !(live && M > 0 && win.x <= win.y);
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
@@ -477,7 +476,6 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
   const uint32_t vrBits = __float_as_uint(vr);
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
-  const size_t rowBase = (size_t)lid * g.rowPitch;      // sector-aligned rows: one partial sector per row, not two
   uint32_t n = 0;
   int32_t row = win.x;
   uint32_t t = 0, b = 0;
@@ -558,25 +556,11 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
     // ---- warp-cooperative flush -------------------------------------------------------------
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
     for (uint32_t k = 0; k < kmax; k++)
-      if (k < cnt) s.NST[(size_t)(first + k) * g.Npad + e] = myW[k];
-    if (WRITE_ROWS) {
-      const uint32_t h = lane >> 4, l = lane & 15;
-      for (uint32_t s2 = 0; s2 < 16; s2++) {
-        const uint32_t src = s2 * 2 + h;
-        const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t f = __shfl_sync(0xffffffffu, first, src);
-        const uint32_t fin = __shfl_sync(0xffffffffu, (uint32_t)(done && live), src);
-        const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
-        if (f == 0 && fin) {
-          // whole row in this round: header + entries in one contiguous store
-          if (l == 0) { __stcs(nd + rb, (int32_t)c); __stcs(dd + rb, (float)c); }       // :274-275
-          else if (l <= c) { __stcs(nd + rb + l, (int32_t)sId[src * K4_STRIDE + l - 1]); __stcs(dd + rb + l, sD2[src * K4_STRIDE + l - 1]); }
-        } else {
-          if (l < c) { __stcs(nd + rb + 1 + f + l, (int32_t)sId[src * K4_STRIDE + l]); __stcs(dd + rb + 1 + f + l, sD2[src * K4_STRIDE + l]); }  // :259-260
-          if (fin && l == 15) { __stcs(nd + rb, (int32_t)(f + c)); __stcs(dd + rb, (float)(f + c)); }
-        }
+      if (k < cnt) {
+        const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
+        s.NST[ix] = myW[k];
+        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)sId[lane * K4_STRIDE + k]); __stcs(dd + ix, sD2[lane * K4_STRIDE + k]); }   // :259-260
       }
-    }
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (!live) return;
@@ -601,20 +585,25 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
 //            binary64 predicate of spatial_worker.js:252-257, row word / id / float32 d2 staged in
 //            place (accepted <= drained), cap of :264.
 //   then     partners with another visualRange or on the rim (as in k_neighbors), warp flush.
+#ifndef WEED_K4V2_Q
+#define WEED_K4V2_Q 16
+#endif
+#ifndef WEED_K4V2_MINBLOCKS
+#define WEED_K4V2_MINBLOCKS 1
+#endif
 static constexpr int K4V2_THREADS = 128;
-static constexpr int K4V2_Q = 16;         // queue = stage entries per thread and round
-static constexpr int K4V2_STRIDE = 17;    // odd stride: conflict-free smem both ways
+static constexpr int K4V2_Q = WEED_K4V2_Q;                    // queue = stage entries per thread and round (at most 16)
+static constexpr int K4V2_STRIDE = K4V2_Q | 1;                // odd stride: conflict-free smem both ways
+static_assert(K4V2_Q >= 4 && K4V2_Q <= 16, "the flush writes at most 16 words of a row per round");
 
 template <bool WRITE_ROWS>
-__global__ void __launch_bounds__(K4V2_THREADS)
+__global__ void __launch_bounds__(K4V2_THREADS, WEED_K4V2_MINBLOCKS)
 k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
              float* __restrict__ dd, Counters* ctr) {
   constexpr uint32_t PLANE = (K4V2_THREADS / 32) * 32 * K4V2_STRIDE;
   __shared__ uint32_t sStage[3 * PLANE];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* const myW = &sStage[warp * 32 * K4V2_STRIDE + lane * K4V2_STRIDE];
-  uint32_t* const sId = &sStage[PLANE + warp * 32 * K4V2_STRIDE];
-  const float* const sD2 = reinterpret_cast<const float*>(&sStage[2 * PLANE + warp * 32 * K4V2_STRIDE]);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t A = cellStart[g.cells];
   const uint32_t M = g.M;
@@ -629,7 +618,6 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
     vr = me.z; id = __float_as_uint(me.w) & ~CX_EDGE; edge = __float_as_uint(me.w) & CX_EDGE;
     win = s.WIN[e];
   }
-  const uint32_t lid = (live && s.SLID) ? s.SLID[e] : id;    // row address: local index
   bool done = !(live && M > 0 && win.x <= win.y);
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
@@ -637,7 +625,6 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
   const uint32_t vrBits = __float_as_uint(vr);
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
-  const size_t rowBase = (size_t)lid * g.rowPitch;
   const float2* __restrict__ QXY = s.QXY;
   uint32_t n = 0;
   int32_t row = win.x;
@@ -646,30 +633,33 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
     t = cellStart[(uint32_t)row * g.cols + win.z];
     b = cellStart[(uint32_t)row * g.cols + win.w + 1];
   }
-  bool hdr = live;                                   // row header (:274-275) still to be written
   do {
     // ---- phase 1: survivors of the float32 pre-filter -------------------------------------------
-    uint32_t qn = 0;
-    while (!done && qn + 4 <= (uint32_t)K4V2_Q) {
+    uint32_t* wp = myW;                                     // next free queue entry
+    uint32_t* const wfull = myW + (K4V2_Q - 3);             // room for four more below this
+    while (!done && wp < wfull) {
       if (t >= b) {
         if (++row > win.y) { done = true; break; }
         t = cellStart[(uint32_t)row * g.cols + win.z];
         b = cellStart[(uint32_t)row * g.cols + win.w + 1];
         continue;
       }
-      const uint32_t last = b - 1;
+      // four positions off one pointer; reads past the end of the range stay inside the (padded)
+      // array and are masked by the range test
+      const float2* cp = QXY + t;
       float2 c[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) c[u] = __ldg(QXY + min(t + (uint32_t)u, last));
+      for (int u = 0; u < 4; u++) c[u] = __ldg(cp + u);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const float fx = c[u].x - q.x, fy = c[u].y - q.y;
-        const bool pass = (t + (uint32_t)u <= last) && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF);
-        if (pass) myW[qn] = t + (uint32_t)u;
-        qn += pass ? 1u : 0u;
+        const bool pass = (t + (uint32_t)u < b) && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF);
+        if (pass) *wp = t + (uint32_t)u;
+        wp += pass ? 1 : 0;
       }
       t += 4;
     }
+    const uint32_t qn = (uint32_t)(wp - myW);
     // ---- phase 2: exact predicate, staged in place -------------------------------------------------
     uint32_t cnt = 0;
     bool anySlow = false;
@@ -716,28 +706,11 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
     // ---- warp-cooperative flush ---------------------------------------------------------------------
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
     for (uint32_t k = 0; k < kmax; k++)
-      if (k < cnt) s.NST[(size_t)(first + k) * g.Npad + e] = myW[k];
-    if (WRITE_ROWS) {
-      const uint32_t h = lane >> 4, l = lane & 15;
-      const uint32_t fin = (uint32_t)(done && hdr);    // the round in which this lane's scan ended
-      hdr = hdr && !done;
-      for (uint32_t s2 = 0; s2 < 16; s2++) {
-        const uint32_t src = s2 * 2 + h;
-        const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t f = __shfl_sync(0xffffffffu, first, src);
-        const uint32_t fn = __shfl_sync(0xffffffffu, fin, src);
-        const unsigned long long rb = __shfl_sync(0xffffffffu, (unsigned long long)rowBase, src);
-        if (f == 0 && fn) {
-          // whole row in this round: header + entries in one contiguous store
-          if (l == 0) { __stcs(nd + rb, (int32_t)c); __stcs(dd + rb, (float)c); }       // :274-275
-          else if (l <= c) { __stcs(nd + rb + l, (int32_t)sId[src * K4V2_STRIDE + l - 1]); __stcs(dd + rb + l, sD2[src * K4V2_STRIDE + l - 1]); }
-          if (c == 16 && l == 15) { __stcs(nd + rb + 16, (int32_t)sId[src * K4V2_STRIDE + 15]); __stcs(dd + rb + 16, sD2[src * K4V2_STRIDE + 15]); }
-        } else {
-          if (l < c) { __stcs(nd + rb + 1 + f + l, (int32_t)sId[src * K4V2_STRIDE + l]); __stcs(dd + rb + 1 + f + l, sD2[src * K4V2_STRIDE + l]); }  // :259-260
-          if (fn && l == 15) { __stcs(nd + rb, (int32_t)(f + c)); __stcs(dd + rb, (float)(f + c)); }
-        }
+      if (k < cnt) {
+        const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
+        s.NST[ix] = myW[k];
+        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
       }
-    }
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (!live) return;
@@ -771,13 +744,11 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
   const float vr = hi.z;
   const uint32_t id = __float_as_uint(hi.w);
   const int4 win = s.WIN[e];
-  const uint32_t lid = s.SLID ? s.SLID[e] : id;
   const double myX = q.x, myY = q.y;
   const double vrSq = dmul((double)vr, (double)vr);
   const float vrSqF = vr * vr * 1.00001f;
   int32_t myCol, myRow;
   cell_of(g, q.x, q.y, myCol, myRow);
-  const size_t rowBase = (size_t)lid * g.rowPitch;      // sector-aligned rows: one partial sector per row, not two
   uint32_t n = 0;
   for (int32_t row = win.x; row <= win.y && n < M && M > 0; row++) {
     const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
@@ -806,8 +777,8 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
         const bool out = pw.y > id;
         s.NST[(size_t)pos * g.Npad + e] = t | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
         if (WRITE_ROWS) {
-          nd[rowBase + 1 + pos] = (int32_t)pw.y;        // :259
-          dd[rowBase + 1 + pos] = fround(d2);           // :260
+          nd[(size_t)pos * g.Npad + e] = (int32_t)pw.y;  // :259
+          dd[(size_t)pos * g.Npad + e] = fround(d2);     // :260
         }
         if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
       }
@@ -815,7 +786,6 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
     }
   }
   if (lane == 0) {
-    if (WRITE_ROWS) { nd[rowBase] = (int32_t)n; dd[rowBase] = (float)n; }   // :274-275
     if (n >= M && M > 0) {
       reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
       reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
@@ -1872,7 +1842,7 @@ struct FlockParams {
 };
 
 __global__ void __launch_bounds__(128)
-k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ nd, const float* __restrict__ dd,
+k_system_flock(GridDims g, FlockParams fp, ById d, RowView rows,
                const float* __restrict__ protectedRange) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.N || i == 0) return;                   // index 0 is the Mouse: its tick() is empty
@@ -1884,8 +1854,8 @@ k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ n
   if (ci < 0) return;                               // not a boid: some other tick()
   const FlockClass& k = fp.cls[ci];
   const double dt = fp.dtRatio;
-  const size_t off = (size_t)i * g.rowPitch;
-  const int32_t cnt = nd[off];
+  uint32_t slot;
+  const int32_t cnt = rows.count(i, slot);
   const float4 me = d.DP[i];
   const double myX = me.x, myY = me.y;
   float2 acc = d.ACC[i];
@@ -1897,10 +1867,10 @@ k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ n
     uint32_t same = 0, predators = 0;
     int32_t closest = -1;
     for (int32_t n = 0; n < cnt; n++) {
-      const int32_t j = nd[off + 1 + n];
+      const int32_t j = rows.id(slot, n);
       const uint32_t nt = d.ET[j];
       if (nt == fp.mouseType) continue;                                          // :179-180
-      const double d2 = (double)dd[off + 1 + n];
+      const double d2 = (double)rows.d2(slot, n);
       const float4 pj = d.DP[j];
       const double dx = dsub((double)pj.x, myX), dy = dsub((double)pj.y, myY);
       if (d2 < pr2 && d2 > 0) {                                                  // :192-196
@@ -1952,8 +1922,8 @@ k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ n
   }
   if (fp.mouseDown) {                                                            // boid.js:281-316
     for (int32_t n = 0; n < cnt; n++) {
-      if (nd[off + 1 + n] != 0) continue;                                        // the Mouse is entity 0
-      const double d2 = (double)dd[off + 1 + n];
+      if (rows.id(slot, n) != 0) continue;                                        // the Mouse is entity 0
+      const double d2 = (double)rows.d2(slot, n);
       if (d2 != d2 || d2 == 0) break;                                            // `!dist2`
       const float4 pm = d.DP[0];
       const double dx = dsub((double)pm.x, myX), dy = dsub((double)pm.y, myY);
@@ -1968,6 +1938,24 @@ k_system_flock(GridDims g, FlockParams fp, ById d, const int32_t* __restrict__ n
   if (myY < k.margin) acc.y = fround(dadd((double)acc.y, turn));
   if (myY > dsub(g.worldH, k.margin)) acc.y = fround(dsub((double)acc.y, turn));
   d.ACC[i] = acc;
+}
+
+// ---- API rows for the host: slot-major planes -> the reference's rows (gameEngine.js:552-559) ------
+// One warp per entity of [first, first + count): header and the `count` entries of its row go to the
+// mirror in host layout (stride 1 + maxNeighbors).  Entities that are not in the grid keep whatever
+// their row held (spatial_worker.js:148,153 never rewrites it), and so do the words past 1 + count.
+__global__ void __launch_bounds__(256)
+k_rows_gather(RowView rows, uint32_t first, uint32_t count, uint32_t hostStride, int32_t* __restrict__ mnd,
+              float* __restrict__ mdd) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const uint32_t i = first + w;
+  const uint32_t slot = rows.slotOf[i];
+  if (slot == SLOT_NONE) return;
+  const int32_t cnt = (int32_t)rows.ncnt[slot];
+  const size_t o = (size_t)i * hostStride;
+  if (lane == 0) { mnd[o] = cnt; mdd[o] = (float)cnt; }                         // :274-275
+  for (int32_t k = (int32_t)lane; k < cnt; k += 32) { mnd[o + 1 + k] = rows.id(slot, k); mdd[o + 1 + k] = rows.d2(slot, k); }
 }
 
 // ---- statistics (only when the host asks) -------------------------------------------------

@@ -204,7 +204,7 @@ k_screen_visibility(uint32_t N, CameraParams c, const float4* __restrict__ DP, c
 // they cast anything), each walks its neighbor row in order and emits at most perLight shadows,
 // everything stops at maxSprites.  Parallel: light flag -> rank by id; shadow count per eligible
 // light -> prefix; ordered emit truncated at maxSprites (a prefix truncation, like the break).
-struct ShadowParams { uint32_t maxLights, perLight, maxSprites, rowPitch; };
+struct ShadowParams { uint32_t maxLights, perLight, maxSprites, _pad; };
 struct ShadowIn {
   const uint8_t* lightActive; const float* lightIntensity;
   const uint8_t* casterActive; const float* casterRadius; const float* casterHeight;
@@ -236,7 +236,7 @@ __device__ __forceinline__ bool sh_casts(const ShadowIn& in, const uint8_t* __re
 // pass 2: the first maxLights lights (by id) list themselves and count their shadows
 __global__ void __launch_bounds__(SYS_TILE)
 k_shadow_count(uint32_t N, ShadowParams p, ShadowIn in, const uint8_t* __restrict__ F,
-               const uint32_t* __restrict__ tilePrefix, const int32_t* __restrict__ nd, const float* __restrict__ dd,
+               const uint32_t* __restrict__ tilePrefix, RowView rows,
                uint32_t* __restrict__ lightId, uint32_t* __restrict__ lightCount) {
   __shared__ uint32_t s_warp[SYS_TILE / 32];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,11 +244,11 @@ k_shadow_count(uint32_t N, ShadowParams p, ShadowIn in, const uint8_t* __restric
   uint32_t tot;
   const uint32_t rank = tilePrefix[blockIdx.x] + block_exclusive(isL, s_warp, tot);
   if (!isL || rank >= p.maxLights) return;                            // :911
-  const size_t o = (size_t)i * p.rowPitch;
-  const int32_t cnt = nd[o];
+  uint32_t slot;
+  const int32_t cnt = rows.count(i, slot);
   uint32_t c = 0;
   for (int32_t k = 0; k < cnt && c < p.perLight; k++)                 // :930-931
-    if (sh_casts(in, F, nd[o + 1 + k], dd[o + 1 + k])) c++;
+    if (sh_casts(in, F, rows.id(slot, k), rows.d2(slot, k))) c++;
   lightId[rank] = i;
   lightCount[rank] = c;
 }
@@ -256,7 +256,7 @@ k_shadow_count(uint32_t N, ShadowParams p, ShadowIn in, const uint8_t* __restric
 // pass 3 (one block): prefix over the <= maxLights counts, ordered emit, clear the unused tail
 __global__ void __launch_bounds__(256)
 k_shadow_emit(ShadowParams p, ShadowIn in, const uint8_t* __restrict__ F, const float4* __restrict__ DP,
-              const uint32_t* __restrict__ nLightsTotal, const int32_t* __restrict__ nd, const float* __restrict__ dd,
+              const uint32_t* __restrict__ nLightsTotal, RowView rows,
               const uint32_t* __restrict__ lightId, const uint32_t* __restrict__ lightCount, ShadowOut out,
               uint32_t* __restrict__ nSprites) {
   __shared__ uint32_t s_total;
@@ -268,12 +268,12 @@ k_shadow_emit(ShadowParams p, ShadowIn in, const uint8_t* __restrict__ F, const 
     const uint32_t i = lightId[l];
     const float4 lp = DP[i];
     const double intensity = (double)in.lightIntensity[i];
-    const size_t o = (size_t)i * p.rowPitch;
-    const int32_t cnt = nd[o];
+    uint32_t slot;
+    const int32_t cnt = rows.count(i, slot);
     uint32_t c = 0;
     for (int32_t k = 0; k < cnt && c < p.perLight && base + c < p.maxSprites; k++) {
-      const int32_t j = nd[o + 1 + k];
-      const float distSqF = dd[o + 1 + k];
+      const int32_t j = rows.id(slot, k);
+      const float distSqF = rows.d2(slot, k);
       if (!sh_casts(in, F, j, distSqF)) continue;
       const double distSq = (double)distSqF;
       const float4 cp = DP[j];

@@ -448,8 +448,11 @@ def test_no_neighbor_rows_flag_and_device_pointers():
     assert n == int(b.collisionData[0]) and np.array_equal(a.collisionData[:1 + 2 * n], b.collisionData[:1 + 2 * n])
     assert B.lib().weed_fetch_neighbors(b.ctx, 0, 1) == B.WEED_E_STATE
     ptr, nbytes = a.device_ptr(B.DEV_NEIGHBOR)
-    pitch = B.lib().weed_row_pitch(a.ctx)                  # device rows are sector-aligned: 65 -> 72 words
-    assert pitch == (1 + a.maxNeighbors + 7) // 8 * 8 and ptr and nbytes == cfg["entityCount"] * pitch * 4
+    pitch = B.lib().weed_row_pitch(a.ctx)                  # device rows are slot-major planes of `pitch` words
+    assert pitch == (cfg["entityCount"] + 127) // 128 * 128 and ptr and nbytes == (a.maxNeighbors + 7) // 8 * 8 * pitch * 4
+    for which in (B.DEV_NEIGHBOR_COUNT, B.DEV_SLOT_OF):
+        ptr, nbytes = a.device_ptr(which)
+        assert ptr and nbytes == cfg["entityCount"] * 4
     ptr, nbytes = a.device_ptr(B.DEV_STATE)
     assert ptr and nbytes == cfg["entityCount"] * 16
     assert b.device_ptr(B.DEV_NEIGHBOR)[0] is None

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--variants", default="22,11", help="comma list of <K4 form><K6 form>: 1 = round 1, 2 = current, T = TMA tiles (K6 only), e.g. 22,2T,11")
     ap.add_argument("--rows", type=int, default=200_000, help="API rows hashed per sample block (3 blocks)")
+    ap.add_argument("--no-rows", action="store_true", help="WEED_FLAG_NO_NEIGHBOR_ROWS: what the scan costs without the API rows")
     ap.add_argument("--lib", default=None, help="tag of an experimental build (tools/build_variant.sh) to load instead of the product library")
     args = ap.parse_args()
 
@@ -52,6 +53,8 @@ def main():
         flags = B.FLAG_KERNEL_TIMING
         flags |= {"1": B.FLAG_K4_V1, "2": 0}[v[0]]
         flags |= {"1": B.FLAG_K6_V1, "2": 0, "T": B.FLAG_K6_TILE}[v[1]]
+        if args.no_rows:
+            flags |= B.FLAG_NO_NEIGHBOR_ROWS
         eng = GameEngine(cfg, flags=flags, host_neighbor_rows=False)
         eng.load_columns(cols)
         eng.run(args.warmup)
@@ -75,7 +78,7 @@ def main():
         hr = hashlib.sha256()
         nrows = min(args.rows, N)
         act = eng.col["T.active"]
-        for first in sorted({0, max(0, N // 2 - nrows // 2), max(0, N - nrows)}):
+        for first in ([] if args.no_rows else sorted({0, max(0, N // 2 - nrows // 2), max(0, N - nrows)})):
             nd = np.empty(nrows * stride, np.int32)
             dd = np.empty(nrows * stride, np.float32)
             B.check(eng.ctx, B.lib().weed_fetch_neighbors_to(eng.ctx, first, nrows, nd.ctypes.data, dd.ctypes.data))

@@ -1,5 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/ab_kernels.py --frames 6 --variants 22,2T,11 > gpurun_out/ab_prod.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python tools/ab_kernels.py --frames 6 --variants 22,11 > gpurun_out/ab_prod.log 2>&1
 grep -h K6_ms gpurun_out/ab_*.log | python -c "
 import sys, json
 for l in sys.stdin:
