@@ -150,11 +150,11 @@ def oracle_for(cfg, cols):
     return o
 
 
-def cpu_reference(name, steps, warmup, sample_entities):
+def cpu_reference(name, steps, warmup, sample_entities, lockstep_frames=None):
     """The reference's CPU structure: ONE spatial worker thread + ONE physics worker thread,
     free-running on shared buffers (gameEngine.js:978-996, AbstractWorker.js:114-146),
-    restated in C (oracle/weed_oracle.c).  Bounded sample of the same workload at the same
-    entity density."""
+    restated in C (oracle/weed_oracle.c).  sample_entities=None runs the workload at its full
+    size; a number runs a scaled instance at the same entity density (and says so)."""
     cfg, cols = workload(name, sample_entities)
     o = oracle_for(cfg, cols)
     S = cfg["physics"]["subStepCount"]
@@ -163,13 +163,20 @@ def cpu_reference(name, steps, warmup, sample_entities):
         o.bench(warmup, 1.0, freerun=True)
     ts, tp = o.bench(steps, 1.0, freerun=True)
     t = max(ts, tp)
-    ls, lp = o.bench(max(1, steps // 2), 1.0, freerun=False)
-    lock = (ls + lp) / max(1, steps // 2)
+    nl = max(1, steps // 2) if lockstep_frames is None else lockstep_frames
+    lock_note = ""
+    if nl:
+        ls, lp = o.bench(nl, 1.0, freerun=False)
+        lock = (ls + lp) / nl
+        lock_note = f"; single-thread lockstep {lock * 1e3:.1f} ms/frame = {active * S / lock:.3e} {UNIT}"
+    sampled = sample_entities is not None and full_config(name, sample_entities) is None
+    what = (f"{name} at the same density scaled to {cfg['entityCount'] - 1} entities" if sampled
+            else f"{name} at full size ({cfg['entityCount'] - 1} entities)")
     return {
         "value": active * S * steps / t, "unit": UNIT, "cores": 2, "kind": "port",
-        "sample": f"{name} at the same density scaled to {cfg['entityCount'] - 1} entities, {steps} frames, "
-                  f"2 free-running threads (spatial {ts / steps * 1e3:.1f} ms/frame, physics {tp / steps * 1e3:.1f} ms/frame); "
-                  f"single-thread lockstep {lock * 1e3:.1f} ms/frame = {active * S / lock:.3e} {UNIT}",
+        "sample": f"{what}, {steps} frames after {warmup} warm-up frames, "
+                  f"2 free-running threads (spatial {ts / steps * 1e3:.1f} ms/frame, physics {tp / steps * 1e3:.1f} ms/frame)" + lock_note,
+        "sampled": sampled, "sample_entities": cfg["entityCount"],
         "host_cores_available": len(os.sched_getaffinity(0)),
     }, cfg, t / steps
 
@@ -179,11 +186,17 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.time()
-    base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, args.cpu_sample)
+    # the reference arm runs the SAME workload as the GPU arm (config4 at 16M: ~6 s per frame on two host
+    # threads); --cpu-sample N runs a scaled instance instead and is then labelled as such
+    sample = args.cpu_sample if args.cpu_sample else args.entities
+    base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, sample, lockstep_frames=0)
+    conf = describe(args.workload, cfg)
+    if base["sampled"]:
+        conf["workload"] += " [scaled sample of the workload: --cpu-sample]"
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": describe(args.workload, full_config(args.workload, args.entities) or cfg),
+            "config": conf,
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -393,7 +406,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            cpu, _, _ = cpu_reference(name, args.cpu_steps, 1, args.cpu_sample)
+            cpu, _, _ = cpu_reference(name, args.cpu_steps, 1, args.cpu_sample or 400_000)
         conf = describe(name, cfg)
         conf.update({"parallelism": "1 GPU" if world == 1 else
                      f"{world} row slabs (1 per GPU), halo {plan[1]} rows recomputed redundantly, 1 fixed-size NCCL neighbour exchange per frame, no host sync inside a frame",
@@ -423,7 +436,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config4")
     ap.add_argument("--entities", type=int, default=None, help="override the entity count (same density)")
-    ap.add_argument("--cpu-sample", type=int, default=400_000, help="entities of the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="entities of a scaled CPU sample (default: 400000 for the cpu_baseline leg of the GPU arm; "
+                         "--impl reference runs the full workload unless this is given)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")

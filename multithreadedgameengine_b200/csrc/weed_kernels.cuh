@@ -589,7 +589,7 @@ k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_
 #define WEED_K4V2_Q 16
 #endif
 #ifndef WEED_K4V2_MINBLOCKS
-#define WEED_K4V2_MINBLOCKS 1
+#define WEED_K4V2_MINBLOCKS 8
 #endif
 static constexpr int K4V2_THREADS = 128;
 static constexpr int K4V2_Q = WEED_K4V2_Q;                    // queue = stage entries per thread and round (at most 16)

@@ -56,14 +56,30 @@ def assert_cols_equal(a, b, keys=None, what=""):
 
 
 def active_rows_equal(nd_a, dd_a, nd_b, dd_b, N, M, rows):
-    """Compare count + the first count entries of each listed row (ids and float32 d² bits)."""
+    """Compare count + the first count entries of each listed row (ids and float32 d² bits).
+    Vectorised (benchmark-scale scenes have millions of rows); the first mismatch is reported by
+    row."""
     stride = 1 + M
-    for i in rows:
-        o = int(i) * stride
-        ca, cb = int(nd_a[o]), int(nd_b[o])
-        assert ca == cb, f"row {i}: count {ca} vs {cb}"
-        assert np.array_equal(nd_a[o + 1:o + 1 + ca], nd_b[o + 1:o + 1 + ca]), f"row {i}: ids differ"
-        assert np.array_equal(bits(dd_a[o:o + 1 + ca]), bits(dd_b[o:o + 1 + ca])), f"row {i}: d2 differ"
+    rows = np.asarray(rows, dtype=np.int64)
+    if rows.size == 0:
+        return
+    A = np.asarray(nd_a).reshape(-1, stride)
+    Bn = np.asarray(nd_b).reshape(-1, stride)
+    DA = bits(np.asarray(dd_a)).reshape(-1, stride)
+    DB = bits(np.asarray(dd_b)).reshape(-1, stride)
+    for lo in range(0, rows.size, 1 << 18):                      # bounded temporaries
+        r = rows[lo:lo + (1 << 18)]
+        a, b, da, db = A[r], Bn[r], DA[r], DB[r]
+        ca, cb = a[:, 0], b[:, 0]
+        if not np.array_equal(ca, cb):
+            k = int(np.nonzero(ca != cb)[0][0])
+            raise AssertionError(f"row {int(r[k])}: count {int(ca[k])} vs {int(cb[k])}")
+        valid = np.arange(stride)[None, :] <= ca[:, None]        # header + count entries
+        bad = ((a != b) | (da != db)) & valid
+        if bad.any():
+            k, w = (int(v[0]) for v in np.nonzero(bad))
+            what = "ids" if a[k, w] != b[k, w] else "d2"
+            raise AssertionError(f"row {int(r[k])}: {what} differ at word {w}: {a[k, w]} / {da[k, w]:#x} vs {b[k, w]} / {db[k, w]:#x}")
 
 
 def random_scene(rng, N=300, W=1000.0, H=600.0, cellSize=50.0, M=16, S=2, weird=True):

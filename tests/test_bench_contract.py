@@ -26,9 +26,13 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "entity_substep_updates_per_sec" and d["unit"] == "entity-substeps/s"
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
-    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "16000000 entities" in d["config"]["workload"]
+    assert d["vs_baseline"] is None and d["data"] == "synthetic"
+    # the line names what actually ran: a scaled sample is labelled as one (round 1 printed the 16M label here)
+    assert "20000 entities" in d["config"]["workload"] and "scaled sample" in d["config"]["workload"]
+    assert d["config"]["entities"] == 20001
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 2 and cb["value"] == d["value"] and "20000 entities" in cb["sample"]
+    assert cb["sampled"] is True and cb["sample_entities"] == 20001
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
