@@ -37,12 +37,16 @@ UNIT = "entity-substeps/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/), config4 16M on one B200; None = not captured for this kernel.
-TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r1_ncu_config4_16M_final_summary.md
-    "k_neighbors": 5.777e9, "k_substep": 2.539e9, "k_build_slots": 1.803e9, "k_writeback": 1.950e9,
+TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r2_ncu_config4_16M_summary.md
+    "k_neighbors2": None, "k_sweep": None, "k_build_slots+k_slot_prep": None,
 }
 
-KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids", "k_build_slots", "k_neighbors",
-                "k_capped_rescan+k_sort_lists", "k_substep", "k_writeback+k_pair_scan+k_pair_emit"]
+KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids+k_slot_rank", "k_build_slots+k_slot_prep", "k_neighbors2",
+                "k_capped_rescan+k_sort_lists", "k_sweep", "k_writeback+k_pair_scan+k_pair_emit"]
+# algorithmic bytes per active entity of each timed span (SURVEY 8 d); spans without compulsory
+# traffic of their own (the cap path, the pair log) can never be the "dominant kernel" of the roofline line
+def span_bytes(kbar):
+    return [13.0, 0.0, 8.0, 82.0, 24.0 + 8.0 * (1.0 + kbar), 0.0, 34.0 + 4.0 * (1.0 + kbar), 0.0]
 
 
 def workload(name, n_override=None):
@@ -94,6 +98,19 @@ def algorithmic_bytes(kbar, S):
         "k_substep": S * (34.0 + 4.0 * (1.0 + kbar)),
     }
     return 127.0 + 8.0 * (1.0 + kbar) + S * (34.0 + 4.0 * (1.0 + kbar)), per_kernel
+
+
+def state_checksum(gids, vals):
+    """Order-independent 64-bit checksum of (gid, x, y, px, py, collisionCount) over a set of entities."""
+    M = np.uint64
+    with np.errstate(over="ignore"):
+        h = gids.astype(M) * M(0x9E3779B97F4A7C15)
+        for k, c in zip(("T.x", "T.y", "RB.px", "RB.py"), (0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5, 0x85EBCA77C2B2AE63)):
+            h = (h ^ (np.ascontiguousarray(vals[k]).view(np.uint32).astype(M) * M(c))) * M(0xFF51AFD7ED558CCD)
+            h ^= h >> M(33)
+        h = (h ^ vals["RB.collisionCount"].astype(M)) * M(0xC4CEB9FE1A85EC53)
+        h ^= h >> M(29)
+        return int(h.sum(dtype=M))
 
 
 class ClockSampler:
@@ -241,7 +258,7 @@ def run_ours(args):
         row_weight = row_costs(cfg, cols)[0]
         for it in range(args.autobalance):
             with torch.cuda.stream(stream):
-                sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan)
+                sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan, transport=args.transport)
                 for _ in range(args.warmup + args.steps // 2):     # the scene evolves: balance for the frames that get timed
                     sl.step_dist()
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,7 +288,7 @@ def run_ours(args):
             e.load_columns(cols)
             return e, e
         sl = SlabEngine(cfg, cols, rank, world, device=local, flags=flags, stream=stream.cuda_stream, plan=plan,
-                        balance_rows=args.balance_rows)
+                        balance_rows=args.balance_rows, transport=args.transport)
         return sl, sl.eng
 
     def frames(obj, k):
@@ -329,7 +346,7 @@ def run_ours(args):
             local_active, kbar_t = st["activeInGrid"], st["neighborsTotal"] / max(1, st["activeInGrid"])
         else:
             obj_t, eng_t = make(B.FLAG_KERNEL_TIMING)
-            frames(obj_t, args.warmup + args.steps)
+            frames(obj_t, args.warmup)         # the SAME frame window as the headline: frames warmup .. warmup + steps of the scene
             acc = np.zeros(8)
             for _ in range(args.steps):
                 frames(obj_t, 1)
@@ -354,10 +371,11 @@ def run_ours(args):
             allk = [torch.zeros_like(t) for _ in range(world)]
             dist.all_gather(allk, t)
             kernel_ms_per_rank = [round(float(x.item()), 3) for x in allk]
-        top = 4 if args.quick else int(np.argmax(kms))
         F, per_kernel = algorithmic_bytes(kbar_t, S)
-        alg = {0: 13.0, 1: 8.0 * 0.5, 2: 8.0 * 0.5, 3: 82.0, 4: 24.0 + 8.0 * (1.0 + kbar_t), 5: 0.0,
-               6: 34.0 + 4.0 * (1.0 + kbar_t), 7: 0.0}[top]
+        sb = span_bytes(kbar_t)
+        # dominant kernel = the longest launch among the spans that move compulsory bytes
+        top = 4 if args.quick else int(np.argmax(np.where(np.array(sb) > 0, np.nan_to_num(kms), -1.0)))
+        alg = sb[top]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -394,14 +412,62 @@ def run_ours(args):
             e2e_frame()
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t_wall) * 1e3)
-        n_host = eng.totalEntityCount
+        n_host = eng.totalEntityCount if world == 1 else obj.status()["top"]     # a slab's weed_step moves its table up to `top`
         e2e = {"value": owned_total * S * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(sum_over_ranks(8 * n_host)), "d2h_bytes_per_step": int(sum_over_ranks(24 * n_host)),
                "ms_per_step": ms_e2e / e2e_steps,
                "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"
                       + ("; + SlabEngine.exchange_dist per frame" if world > 1 else "")}
-        launches = st["kernelLaunchesPerStep"] * args.steps + (3 * args.steps if world > 1 else 0)
+        launches = st["kernelLaunchesPerStep"] * args.steps + (6 * args.steps if world > 1 else 0)
         (obj.close if world > 1 else eng.close)()
+
+        # ---- steady state: the same measurement far into the scene (settled beds, not the opening explosion) ----
+        steady = None
+        if args.steady_frame and not args.quick:
+            obj_s, eng_s = make()
+            frames(obj_s, args.steady_frame)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            frames(obj_s, args.steps)
+            s1.record(stream)
+            barrier()
+            ms_s = max_over_ranks(s0.elapsed_time(s1))
+            st_s = eng_s.stats()
+            steady = {"frame_window": [args.steady_frame, args.steady_frame + args.steps], "ms_per_step": ms_s / args.steps,
+                      "value": owned_total * S * args.steps / (ms_s * 1e-3),
+                      "kbar": sum_over_ranks(st_s["neighborsTotal"]) / max(1.0, sum_over_ranks(st_s["activeInGrid"])),
+                      "capped_rows": int(sum_over_ranks(st_s["cappedRows"])),
+                      "collision_pairs_last_substep": int(sum_over_ranks(st_s["collisionPairs"]))}
+            (obj_s.close if world > 1 else eng_s.close)()
+
+        # ---- verification of the partitioned run against ONE context (N > 1) ---------------------------------
+        verified = None
+        if world > 1 and args.verify:
+            vf = args.verify
+            obj_v, eng_v = make()
+            frames(obj_v, vf)
+            g, vals, _ = obj_v.owned_state(("T.x", "T.y", "RB.px", "RB.py", "RB.collisionCount"))
+            obj_v.status()
+            cs_mine = state_checksum(g, vals)
+            t = torch.tensor([len(g), cs_mine & 0xFFFFFFFF, cs_mine >> 32], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            obj_v.close()
+            n_all = int(t[0].item())
+            cs_all = (int(t[1].item()) + (int(t[2].item()) << 32)) & 0xFFFFFFFFFFFFFFFF
+            if rank == 0:
+                ref = GameEngine(cfg, device=local, stream=stream.cuda_stream, host_neighbor_rows=False)
+                ref.load_columns(cols)
+                ref.run(vf)
+                ref.download(B.COLS_INPUT_ALL)
+                act = np.nonzero(ref.col["T.active"] != 0)[0].astype(np.uint32)
+                cs_ref = state_checksum(act, {k: ref.col[k][act] for k in ("T.x", "T.y", "RB.px", "RB.py", "RB.collisionCount")})
+                ref.close()
+                verified = {"ok": bool(n_all == len(act) and cs_all == cs_ref), "frames": vf, "entities_owned_once": n_all == len(act),
+                            "checksum_slabs": f"{cs_all:016x}", "checksum_single_context": f"{cs_ref:016x}",
+                            "what": "order-independent 64-bit checksum of (gid, x, y, px, py, collisionCount) bits over the owned entities "
+                                    "of all slabs, all-reduced, against one context that ran the same frames on rank 0"}
+            dist.barrier()
 
     if rank == 0:
         cpu = None
@@ -409,7 +475,11 @@ def run_ours(args):
             cpu, _, _ = cpu_reference(name, args.cpu_steps, 1, args.cpu_sample or 400_000)
         conf = describe(name, cfg)
         conf.update({"parallelism": "1 GPU" if world == 1 else
-                     f"{world} row slabs (1 per GPU), halo {plan[1]} rows recomputed redundantly, 1 fixed-size NCCL neighbour exchange per frame, no host sync inside a frame",
+                     f"{world} row slabs (1 per GPU, one process each), halo {plan[1]} rows recomputed redundantly, one neighbour exchange per frame: "
+                     + ("pack kernels write straight into the neighbours' receive buffers over NVLink (CUDA IPC peer mappings), device-side arrival flags; "
+                        "no host work and no library call inside a frame (NCCL: setup, barriers, reductions of the timings)" if args.transport == "p2p"
+                        else "one fixed-size NCCL send/recv per neighbour (torch.distributed)"),
+                     "frame_window": [args.warmup, args.warmup + args.steps], "steady_state": steady, "verified": verified,
                      "kbar": kbar, "active": active, "l2_policy": "working set >> 126 MB L2 (inputs larger than L2)"
                      if N / world > 2_000_000 else "per-GPU working set comparable to L2; frames run back-to-back on evolving state",
                      "kernel_ms_rank0_per_launch": None if args.quick else {n: float(v) for n, v in zip(KERNEL_NAMES, kms)},
@@ -420,7 +490,8 @@ def run_ours(args):
                      "slab_balance": balance_note if world > 1 else None})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "scaling": "weak" if name == "config5" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "verified": None if verified is None else verified["ok"],
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk.summary()}
         print(json.dumps(line))
@@ -444,7 +515,14 @@ def main():
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
     ap.add_argument("--balance-rows", type=int, default=2, help="N>1: rows a cut may move per frame toward the slower slab (weed_slab_balance; 0 = static cuts)")
     ap.add_argument("--autobalance", type=int, default=3, help="measured-feedback slab re-plans before timing (N>1)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 neighbour exchange: peer-to-peer writes over NVLink (default) or the NCCL send/recv fallback")
+    ap.add_argument("--verify", type=int, default=8, help="N>1: frames of the checksum comparison against one context (0 = skip)")
+    ap.add_argument("--steady-frame", type=int, default=None,
+                    help="also time --steps frames starting this far into the scene (default: 300 for config3/config4 on one GPU, else off)")
     args = ap.parse_args()
+    if args.steady_frame is None:
+        args.steady_frame = 300 if (args.workload in ("config3", "config4") and args.gpus == 1 and not args.entities) else 0
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -34,7 +34,7 @@ enum {
   WEED_E_CUDA        = -2,  /* CUDA runtime failure (context becomes sticky-failed)    */
   WEED_E_NOT_BOUND   = -3,  /* a required host buffer was not bound                    */
   WEED_E_SIZE        = -4,  /* bound buffer smaller than the layout requires           */
-  WEED_E_OVERFLOW    = -5,  /* reserved                                                */
+  WEED_E_OVERFLOW    = -5,  /* a capacity was exceeded (slab quota / table / halo reach, pool free list) */
   WEED_E_STATE       = -6,  /* call order violated (e.g. weed_physics before spatial)  */
   WEED_E_NOMEM       = -7
 };
@@ -392,6 +392,52 @@ int weed_slab_get_gids(weed_ctx* ctx, uint32_t* gids_out, uint32_t* top_out);
 int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint32_t quota);
 /* drop this frame's replicas, then insert the neighbours' records (either may be NULL)     */
 int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, const void* dev_from_high, uint32_t quota);
+
+/* Peer-to-peer exchange: no host and no library call inside a frame.  Every slab owns two receive
+ * buffers per side (frame parity) of quota + 1 records; the neighbour's pack kernel writes its
+ * records STRAIGHT into them over NVLink (a peer mapping), then the header and, after a system
+ * fence, an arrival flag; this slab's apply waits for the flag on the device.  Setup, once:
+ *   weed_slab_exchange_create(ctx, quota)             the same quota on every slab
+ *   weed_slab_exchange_export(ctx, &handle, &base)    handle: for a neighbour in ANOTHER process
+ *                                                     (a cudaIpcMemHandle_t, ship it any way you
+ *                                                     like); base: for one in THIS process
+ *   weed_slab_exchange_connect(ctx, side, handle|NULL, base|NULL)   side 0: the low neighbour
+ *                                                     (rows below mine), 1: the high one
+ * then, per frame, weed_slab_frame (frame kernels + pack + wait + apply, all asynchronous on the
+ * context's stream) or weed_step followed by weed_slab_exchange.  weed_slab_frame_begin / _end split
+ * the frame at the wait: one host thread that drives several slabs calls begin on all of them, then
+ * end on all of them, so that no slab waits for a message that has not been queued yet.
+ * The halo is sized for the entities near the cuts when the slabs were planned; if an entity whose
+ * reach exceeds it (an observer with a large visualRange) later comes near a cut, weed_slab_status
+ * returns WEED_E_OVERFLOW instead of letting the partition diverge from the single-context result. */
+typedef struct weed_ipc_handle { unsigned char bytes[64]; } weed_ipc_handle;
+int weed_slab_exchange_create(weed_ctx* ctx, uint32_t quota);
+int weed_slab_exchange_export(weed_ctx* ctx, weed_ipc_handle* handle_out, void** base_out);
+int weed_slab_exchange_connect(weed_ctx* ctx, int side, const weed_ipc_handle* peer_handle, void* peer_base);
+int weed_slab_frame(weed_ctx* ctx, double dtRatio);
+int weed_slab_frame_begin(weed_ctx* ctx, double dtRatio);
+int weed_slab_frame_end(weed_ctx* ctx);
+int weed_slab_exchange(weed_ctx* ctx);
+/* unmaps the neighbours' buffers (call it on every slab, then synchronise the processes, before any
+ * of them destroys its context: memory a peer still has mapped must not be freed)              */
+int weed_slab_exchange_disconnect(weed_ctx* ctx);
+
+/* One world on several GPUs of ONE process (what a single Node engine uses; call site
+ * src/core/gameEngine.js:972-1009 creates one spatial and one physics worker — here: one group).
+ * weed_group_create makes one slab context per entry of devices[] (capacity = its local entity
+ * table), creates their exchange buffers and connects neighbours (peer access over NVLink).  The
+ * host fills every slab's local table through weed_group_slab(g, k): weed_bind / weed_upload /
+ * weed_slab_set_gids as for any slab context.  weed_group_step queues one frame on every slab and
+ * returns at once; weed_group_sync waits and reports the first slab error (WEED_E_OVERFLOW ...).  */
+typedef struct weed_group weed_group;
+int weed_group_create(const weed_config* cfg_template, uint32_t nSlabs, const int32_t* devices, const uint32_t* rowCuts,
+                      uint32_t haloRows, const uint32_t* capacities, uint32_t quota, weed_group** out);
+uint32_t weed_group_size(weed_group* g);
+weed_ctx* weed_group_slab(weed_group* g, uint32_t k);
+int weed_group_step(weed_group* g, double dtRatio);
+int weed_group_sync(weed_group* g);
+void weed_group_destroy(weed_group* g);
+const char* weed_group_last_error(weed_group* g);   /* g may be NULL: last create() failure */
 typedef struct weed_slab_stats {
   uint32_t top, capacity;          /* local slots in use / available                         */
   uint32_t owned;                  /* entities owned during the last packed frame            */

@@ -149,6 +149,21 @@ SYMBOLS = {
     "weed_slab_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "weed_slab_balance": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "weed_slab_status": (C.c_int, [C.c_void_p, C.POINTER(SlabStats)]),
+    "weed_slab_exchange_create": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "weed_slab_exchange_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "weed_slab_exchange_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "weed_slab_frame": (C.c_int, [C.c_void_p, C.c_double]),
+    "weed_slab_frame_begin": (C.c_int, [C.c_void_p, C.c_double]),
+    "weed_slab_frame_end": (C.c_int, [C.c_void_p]),
+    "weed_slab_exchange": (C.c_int, [C.c_void_p]),
+    "weed_slab_exchange_disconnect": (C.c_int, [C.c_void_p]),
+    "weed_group_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "weed_group_size": (C.c_uint32, [C.c_void_p]),
+    "weed_group_slab": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "weed_group_step": (C.c_int, [C.c_void_p, C.c_double]),
+    "weed_group_sync": (C.c_int, [C.c_void_p]),
+    "weed_group_destroy": (None, [C.c_void_p]),
+    "weed_group_last_error": (C.c_char_p, [C.c_void_p]),
 }
 SLAB_RECORD_BYTES = 64
 FLOCK_BOID, FLOCK_PREY, FLOCK_PREDATOR, FLOCK_ANY_TYPE = 0, 1, 2, 0xFFFFFFFF

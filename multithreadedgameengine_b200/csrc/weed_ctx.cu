@@ -196,6 +196,13 @@ struct weed_ctx {
   bool slab = false;
   uint32_t* holes = nullptr;
   SlabCounters* dSlab = nullptr;
+  // peer-to-peer exchange (weed_slab_exchange_*): my receive buffers, the neighbours' mapped ones
+  SlabRec* xRecv = nullptr;            // 4 buffers of xQuota + 1 records: [side][parity]
+  uint32_t xQuota = 0;
+  SlabXfer hXfer{};
+  SlabXfer* dXfer = nullptr;
+  void* xPeerIpc[2] = {};              // bases opened with cudaIpcOpenMemHandle (closed in weed_destroy)
+  size_t copyCount = 0;                // entities weed_step moves per column: the table top of a slab, else N
 };
 
 #define CK(call)                                                                              \
@@ -302,6 +309,8 @@ extern "C" void weed_destroy(weed_ctx* ctx) {
   if (ctx->frameGraph) cudaGraphExecDestroy(ctx->frameGraph);
   for (int b = 0; b < WEED_BUF_COUNT; b++)
     if (ctx->registered[b]) cudaHostUnregister(ctx->host[b]);
+  for (void* p : ctx->xPeerIpc)
+    if (p) cudaIpcCloseMemHandle(p);
   for (void* p : ctx->allocs) cudaFree(p);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
@@ -430,13 +439,13 @@ static int check_bound(weed_ctx* ctx, uint32_t mask) {
   return WEED_OK;
 }
 
-static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr) {
+static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr, size_t count = 0) {
   if (!stream) stream = ctx->stream;
   mask &= WEED_COLS_INPUT_ALL;
   if (!mask) return WEED_OK;
   int rc = check_bound(ctx, mask);
   if (rc) return rc;
-  const size_t N = ctx->g.N;
+  const size_t N = count ? count : ctx->g.N;
   for (int c = 0; c < 20; c++)
     if ((mask >> c) & 1u)
       CK(cudaMemcpyAsync(ctx->stage[c], host_col(ctx, c), N * kHot[c].bytes, cudaMemcpyHostToDevice, stream));
@@ -445,7 +454,10 @@ static int upload_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = null
   for (int c = 0; c < 20; c++) sp[c] = ctx->stage[c];
   k_pack<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((uint32_t)N, mask, st, ctx->d);
   CK(cudaGetLastError());
-  ctx->spatialValid = false;
+  // The grid and the rows of a preceding weed_spatial depend on Transform.active, x, y and
+  // Collider.visualRange only: a tick() that read the rows and now uploads ax / ay (or any other column)
+  // leaves them valid, so weed_spatial -> upload -> weed_physics works (one worker swapped at a time).
+  if (mask & (WEED_COL_T_ACTIVE | WEED_COL_T_X | WEED_COL_T_Y | WEED_COL_C_VISRANGE)) ctx->spatialValid = false;
   return WEED_OK;
 }
 
@@ -481,10 +493,10 @@ static int copy_rows(weed_ctx* ctx, void* nd_host, void* dd_host, uint32_t first
   return WEED_OK;
 }
 
-static int download_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr) {
+static int download_async(weed_ctx* ctx, uint32_t mask, cudaStream_t stream = nullptr, size_t count = 0) {
   if (!stream) stream = ctx->stream;
   const uint32_t cols = mask & WEED_COLS_INPUT_ALL;
-  const size_t N = ctx->g.N;
+  const size_t N = count ? count : ctx->g.N;
   if (cols) {
     int rc = check_bound(ctx, cols);
     if (rc) return rc;
@@ -735,12 +747,12 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
   if (upCols && !(upCols & ~kAccCols)) {
     CK(cudaEventRecord(ctx->evUp, ctx->stream));                 // order after everything already queued
     CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evUp, 0));
-    rc = upload_async(ctx, upCols, ctx->copyStream);
+    rc = upload_async(ctx, upCols, ctx->copyStream, ctx->copyCount);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->evUp, ctx->copyStream));
     waitUp = ctx->evUp;
   } else {
-    rc = upload_async(ctx, upload_mask);
+    rc = upload_async(ctx, upload_mask, nullptr, ctx->copyCount);
     if (rc) return rc;
   }
   const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
@@ -749,14 +761,14 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
   if (rc) return rc;
   if (early) {
     CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evBuilt, 0));
-    rc = download_async(ctx, early, ctx->copyStream);
+    rc = download_async(ctx, early, ctx->copyStream, ctx->copyCount);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->evCopied, ctx->copyStream));
   }
   rc = launch_constraints(ctx, false);
   if (rc) return rc;
   ctx->spatialValid = false;
-  rc = download_async(ctx, download_mask & ~early);
+  rc = download_async(ctx, download_mask & ~early, nullptr, ctx->copyCount);
   if (rc) return rc;
   if (early) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied, 0));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -767,12 +779,21 @@ extern "C" int weed_step(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, ui
   GUARD(ctx);
   const bool direct = (ctx->cfg.flags & (WEED_FLAG_KERNEL_TIMING | WEED_FLAG_NO_GRAPH)) != 0;
   const bool hasCopies = ((upload_mask | download_mask) & WEED_COLS_INPUT_ALL) != 0;
+  ctx->copyCount = 0;
+  if (ctx->slab && hasCopies) {
+    // a slab's table is used up to `top`: the columns beyond it hold nothing (weed_upload / weed_download move
+    // the whole table; the per-frame call moves what exists).  One 4-byte read per step.
+    uint32_t top = 0;
+    CK(cudaMemcpyAsync(&top, &ctx->dSlab->top, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->copyCount = std::max<size_t>(1, std::min<size_t>(top, ctx->g.N));
+  }
   if (!direct && hasCopies && ctx->g.N >= kPipelineMinEntities) return step_pipelined(ctx, dtRatio, upload_mask, download_mask);
-  int rc = upload_async(ctx, upload_mask);
+  int rc = upload_async(ctx, upload_mask, nullptr, ctx->copyCount);
   if (rc) return rc;
   rc = run_frames(ctx, dtRatio, 1);
   if (rc) return rc;
-  rc = download_async(ctx, download_mask);
+  rc = download_async(ctx, download_mask, nullptr, ctx->copyCount);
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   return WEED_OK;
@@ -907,8 +928,9 @@ extern "C" int weed_slab_pack(weed_ctx* ctx, void* dev_low, void* dev_high, uint
   GUARD(ctx);
   if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
   if (!dev_low || !dev_high || quota == 0) return fail(ctx, WEED_E_INVALID, "exchange buffers missing");
-  k_slab_pack<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, (SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab);
-  k_slab_headers<<<1, 32, 0, ctx->stream>>>((SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab, ctx->dCtr);
+  k_slab_pack<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, (SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab,
+                                                                  nullptr, ctx->phys.subStepCount);
+  k_slab_headers<<<1, 32, 0, ctx->stream>>>((SlabRec*)dev_low, (SlabRec*)dev_high, quota, ctx->dSlab, ctx->dCtr, nullptr);
   CK(cudaGetLastError());
   return WEED_OK;
 }
@@ -919,11 +941,137 @@ extern "C" int weed_slab_apply(weed_ctx* ctx, const void* dev_from_low, const vo
   if (quota == 0) return fail(ctx, WEED_E_INVALID, "quota must be positive");
   k_slab_drop<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, ctx->holes, ctx->dSlab);
   k_slab_unpack<<<blocks_for(2 * (size_t)quota, 256), 256, 0, ctx->stream>>>(ctx->d, (const SlabRec*)dev_from_low, (const SlabRec*)dev_from_high,
-                                                                           quota, ctx->holes, ctx->g.N, ctx->dSlab);
-  k_slab_finish<<<1, 32, 0, ctx->stream>>>((const SlabRec*)dev_from_low, (const SlabRec*)dev_from_high, quota, ctx->g.N, ctx->dSlab);
+                                                                           quota, ctx->holes, ctx->g.N, ctx->dSlab, nullptr);
+  k_slab_finish<<<1, 32, 0, ctx->stream>>>((const SlabRec*)dev_from_low, (const SlabRec*)dev_from_high, quota, ctx->g.N, ctx->dSlab, nullptr);
   CK(cudaGetLastError());
   ctx->spatialValid = false;
   return WEED_OK;
+}
+
+// ---- peer-to-peer exchange: no host, no library call inside a frame -------------------------------------
+static size_t xfer_offset(uint32_t quota, int side, int parity) { return (size_t)(side * 2 + parity) * ((size_t)quota + 1); }
+
+extern "C" int weed_slab_exchange_create(weed_ctx* ctx, uint32_t quota) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  if (quota == 0) return fail(ctx, WEED_E_INVALID, "quota must be positive");
+  if (ctx->xRecv) return fail(ctx, WEED_E_STATE, "exchange buffers already exist");
+  int rc = dalloc(ctx, &ctx->xRecv, 4 * ((size_t)quota + 1));          // zeroed: no arrival flag is set
+  if (rc) return rc;
+  rc = dalloc(ctx, &ctx->dXfer, 1);
+  if (rc) return rc;
+  ctx->xQuota = quota;
+  memset(&ctx->hXfer, 0, sizeof(ctx->hXfer));
+  ctx->hXfer.quota = quota;
+  for (int side = 0; side < 2; side++)
+    for (int par = 0; par < 2; par++) ctx->hXfer.recv[side][par] = ctx->xRecv + xfer_offset(quota, side, par);
+  CK(cudaMemcpyAsync(ctx->dXfer, &ctx->hXfer, sizeof(SlabXfer), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_exchange_export(weed_ctx* ctx, weed_ipc_handle* handle_out, void** base_out) {
+  GUARD(ctx);
+  if (!ctx->xRecv) return fail(ctx, WEED_E_STATE, "weed_slab_exchange_create has not been called");
+  static_assert(sizeof(weed_ipc_handle) == sizeof(cudaIpcMemHandle_t), "weed_ipc_handle carries a cudaIpcMemHandle_t");
+  if (handle_out) CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out), ctx->xRecv));
+  if (base_out) *base_out = ctx->xRecv;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_exchange_connect(weed_ctx* ctx, int side, const weed_ipc_handle* peer_handle, void* peer_base) {
+  GUARD(ctx);
+  if (!ctx->xRecv) return fail(ctx, WEED_E_STATE, "weed_slab_exchange_create has not been called");
+  if (side < 0 || side > 1 || (!peer_handle && !peer_base)) return fail(ctx, WEED_E_INVALID, "bad side / no peer buffer");
+  SlabRec* base = (SlabRec*)peer_base;
+  if (peer_handle) {             // another process: map its allocation (peer access over NVLink is enabled lazily)
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, *reinterpret_cast<const cudaIpcMemHandle_t*>(peer_handle), cudaIpcMemLazyEnablePeerAccess));
+    ctx->xPeerIpc[side] = p;
+    base = (SlabRec*)p;
+  } else {                       // same process: a context on this or another device
+    cudaPointerAttributes at;
+    CK(cudaPointerGetAttributes(&at, peer_base));
+    if (at.device != ctx->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, ctx->device, at.device));
+      if (!can) return fail(ctx, WEED_E_CUDA, "no peer access between devices " + std::to_string(ctx->device) + " and " + std::to_string(at.device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+      cudaGetLastError();
+    }
+  }
+  // what I send to my LOW neighbour arrives in ITS "from high" buffers, and the other way round
+  for (int par = 0; par < 2; par++) ctx->hXfer.send[side][par] = base + xfer_offset(ctx->xQuota, 1 - side, par);
+  CK(cudaMemcpyAsync(ctx->dXfer, &ctx->hXfer, sizeof(SlabXfer), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_exchange_disconnect(weed_ctx* ctx) {
+  GUARD(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int side = 0; side < 2; side++) {
+    if (ctx->xPeerIpc[side]) { cudaIpcCloseMemHandle(ctx->xPeerIpc[side]); ctx->xPeerIpc[side] = nullptr; }
+    ctx->hXfer.send[side][0] = ctx->hXfer.send[side][1] = nullptr;
+  }
+  if (ctx->dXfer) {
+    CK(cudaMemcpyAsync(ctx->dXfer, &ctx->hXfer, sizeof(SlabXfer), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return WEED_OK;
+}
+
+static int slab_frame_begin(weed_ctx* ctx, double dtRatio, bool runFrame) {
+  if (!ctx->xRecv) return fail(ctx, WEED_E_STATE, "weed_slab_exchange_create has not been called");
+  if (runFrame) {
+    int rc = run_frames(ctx, dtRatio, 1);
+    if (rc) return rc;
+  }
+  k_slab_pack<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, nullptr, nullptr, 0, ctx->dSlab, ctx->dXfer,
+                                                                  ctx->phys.subStepCount);
+  k_slab_headers<<<1, 32, 0, ctx->stream>>>(nullptr, nullptr, 0, ctx->dSlab, ctx->dCtr, ctx->dXfer);
+  CK(cudaGetLastError());
+  return WEED_OK;
+}
+
+static int slab_frame_end(weed_ctx* ctx) {
+  const uint32_t quota = ctx->xQuota;
+  k_slab_wait<<<1, 32, 0, ctx->stream>>>(ctx->dXfer, ctx->dSlab);
+  k_slab_drop<<<blocks_for(ctx->g.N, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->d, ctx->key, ctx->holes, ctx->dSlab);
+  k_slab_unpack<<<blocks_for(2 * (size_t)quota, 256), 256, 0, ctx->stream>>>(ctx->d, nullptr, nullptr, quota, ctx->holes, ctx->g.N, ctx->dSlab, ctx->dXfer);
+  k_slab_finish<<<1, 32, 0, ctx->stream>>>(nullptr, nullptr, quota, ctx->g.N, ctx->dSlab, ctx->dXfer);
+  CK(cudaGetLastError());
+  ctx->spatialValid = false;
+  return WEED_OK;
+}
+
+extern "C" int weed_slab_frame(weed_ctx* ctx, double dtRatio) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  int rc = slab_frame_begin(ctx, dtRatio, true);
+  if (rc) return rc;
+  return slab_frame_end(ctx);
+}
+
+extern "C" int weed_slab_exchange(weed_ctx* ctx) {          // the exchange alone (after a weed_step of the slab)
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  int rc = slab_frame_begin(ctx, 1.0, false);
+  if (rc) return rc;
+  return slab_frame_end(ctx);
+}
+
+extern "C" int weed_slab_frame_begin(weed_ctx* ctx, double dtRatio) {
+  GUARD(ctx);
+  if (!ctx->slab) return fail(ctx, WEED_E_STATE, "not a slab context (slabRowEnd == 0)");
+  return slab_frame_begin(ctx, dtRatio, true);
+}
+
+extern "C" int weed_slab_frame_end(weed_ctx* ctx) {
+  GUARD(ctx);
+  if (!ctx->slab || !ctx->xRecv) return fail(ctx, WEED_E_STATE, "no peer-to-peer exchange on this context");
+  return slab_frame_end(ctx);
 }
 
 extern "C" int weed_slab_balance(weed_ctx* ctx, uint32_t maxShiftRows, uint32_t hysteresisPercent) {
@@ -949,6 +1097,82 @@ extern "C" int weed_slab_status(weed_ctx* ctx, weed_slab_stats* out) {
   out->rowBegin = sc.curBegin; out->rowEnd = sc.curEnd; out->cutMoves = sc.cutMoves; out->loadNs = sc.load;
   if (sc.overflow & 1u) return fail(ctx, WEED_E_OVERFLOW, "slab exchange quota exceeded: " + std::to_string(sc.lastLow) + " / " + std::to_string(sc.lastHigh) + " records");
   if (sc.overflow & 2u) return fail(ctx, WEED_E_OVERFLOW, "slab entity table full (capacity " + std::to_string(ctx->g.N) + ")");
+  if (sc.overflow & SLAB_OVF_REACH) return fail(ctx, WEED_E_OVERFLOW, "an entity whose reach exceeds the halo (" + std::to_string(ctx->g.slabHalo) + " rows) came near a cut: recreate the slabs with a deeper halo");
+  if (sc.overflow & SLAB_OVF_TIMEOUT) return fail(ctx, WEED_E_OVERFLOW, "a neighbour's message did not arrive within two seconds");
+  return WEED_OK;
+}
+
+// ---- a whole world on several GPUs of ONE process (the Node host of INTEGRATION.md) -----------------------
+struct weed_group {
+  std::vector<weed_ctx*> slabs;
+  std::string err;
+};
+thread_local std::string g_group_error;
+
+extern "C" const char* weed_group_last_error(weed_group* g) { return g ? g->err.c_str() : g_group_error.c_str(); }
+
+extern "C" void weed_group_destroy(weed_group* g) {
+  if (!g) return;
+  for (weed_ctx* c : g->slabs) weed_destroy(c);
+  delete g;
+}
+
+extern "C" int weed_group_create(const weed_config* tmpl, uint32_t nSlabs, const int32_t* devices, const uint32_t* rowCuts,
+                                 uint32_t haloRows, const uint32_t* capacities, uint32_t quota, weed_group** out) {
+  if (out) *out = nullptr;
+  if (!tmpl || !out || nSlabs == 0 || !rowCuts || !capacities || quota == 0) { g_group_error = "null / empty argument"; return WEED_E_INVALID; }
+  weed_group* g = new weed_group();
+  auto bail = [&](int code, const std::string& why) { g_group_error = why; weed_group_destroy(g); return code; };
+  for (uint32_t k = 0; k < nSlabs; k++) {
+    weed_config c = *tmpl;
+    c.entityCount = capacities[k];
+    c.device = devices ? devices[k] : tmpl->device;
+    c.stream = nullptr;                                  // every slab runs on a stream of its own
+    c.slabRowBegin = rowCuts[k]; c.slabRowEnd = rowCuts[k + 1]; c.slabHaloRows = haloRows;
+    weed_ctx* ctx = nullptr;
+    int rc = weed_create(&c, &ctx);
+    if (rc) return bail(rc, "slab " + std::to_string(k) + ": " + weed_last_error(nullptr));
+    g->slabs.push_back(ctx);
+    rc = weed_slab_exchange_create(ctx, quota);
+    if (rc) return bail(rc, "slab " + std::to_string(k) + ": " + weed_last_error(ctx));
+  }
+  for (uint32_t k = 0; k < nSlabs; k++) {                // neighbours write straight into each other's buffers
+    if (k > 0) {
+      int rc = weed_slab_exchange_connect(g->slabs[k], 0, nullptr, g->slabs[k - 1]->xRecv);
+      if (rc) return bail(rc, "slab " + std::to_string(k) + ": " + weed_last_error(g->slabs[k]));
+    }
+    if (k + 1 < nSlabs) {
+      int rc = weed_slab_exchange_connect(g->slabs[k], 1, nullptr, g->slabs[k + 1]->xRecv);
+      if (rc) return bail(rc, "slab " + std::to_string(k) + ": " + weed_last_error(g->slabs[k]));
+    }
+  }
+  *out = g;
+  return WEED_OK;
+}
+
+extern "C" uint32_t weed_group_size(weed_group* g) { return g ? (uint32_t)g->slabs.size() : 0u; }
+extern "C" weed_ctx* weed_group_slab(weed_group* g, uint32_t k) { return (g && k < g->slabs.size()) ? g->slabs[k] : nullptr; }
+
+extern "C" int weed_group_step(weed_group* g, double dtRatio) {
+  if (!g) return WEED_E_INVALID;
+  for (size_t k = 0; k < g->slabs.size(); k++) {          // queue every slab's frame + pack first ...
+    int rc = weed_slab_frame_begin(g->slabs[k], dtRatio);
+    if (rc) { g->err = "slab " + std::to_string(k) + ": " + weed_last_error(g->slabs[k]); return rc; }
+  }
+  for (size_t k = 0; k < g->slabs.size(); k++) {          // ... then the waits: every message they wait for is queued
+    int rc = weed_slab_frame_end(g->slabs[k]);
+    if (rc) { g->err = "slab " + std::to_string(k) + ": " + weed_last_error(g->slabs[k]); return rc; }
+  }
+  return WEED_OK;
+}
+
+extern "C" int weed_group_sync(weed_group* g) {
+  if (!g) return WEED_E_INVALID;
+  for (size_t k = 0; k < g->slabs.size(); k++) {
+    weed_slab_stats st;
+    int rc = weed_slab_status(g->slabs[k], &st);         // synchronises; reports quota / table / reach / timeout
+    if (rc) { g->err = "slab " + std::to_string(k) + ": " + weed_last_error(g->slabs[k]); return rc; }
+  }
   return WEED_OK;
 }
 

@@ -1526,7 +1526,8 @@ struct SlabCounters {
   uint32_t maxShift, hysteresisPct, minRows;     // dynamic balancing: 0 rows = static cuts
   uint32_t load;                                 // smoothed device time of this slab's frame kernels
   uint32_t cutMoves;                             // how many times one of my cuts moved
-  uint32_t _pad[16];
+  uint32_t seq;                                  // exchanges completed (peer-to-peer transport: frame parity and arrival flag)
+  uint32_t _pad[15];
 };
 static_assert(sizeof(SlabCounters) == 256, "two 128-byte lines");
 
@@ -1539,13 +1540,31 @@ __device__ __forceinline__ bool present_row(const GridDims& g, const ById& d, ui
   return true;
 }
 
+// Peer-to-peer transport (weed_slab_exchange_*): the pack kernel writes its records STRAIGHT into the
+// neighbour's receive buffer over NVLink (a peer mapping: cudaIpcOpenMemHandle across processes,
+// cudaDeviceEnablePeerAccess inside one), k_slab_publish then stores the header and, after a system
+// fence, the arrival flag; the neighbour's k_slab_wait spins on that flag before its unpack.  Two
+// buffers per side alternate by frame parity: a sender can only be one exchange ahead of its
+// neighbour (it needs the neighbour's previous message to get there), so the buffer it writes was
+// consumed two exchanges ago.  The table lives in device memory so that captured launches see it.
+struct SlabXfer {
+  SlabRec* send[2][2];     // [side: 0 low neighbour, 1 high][parity]: that neighbour's receive buffer (peer memory), or null
+  SlabRec* recv[2][2];     // [side][parity]: my receive buffers
+  uint32_t quota, _pad;
+};
+static constexpr uint32_t SLAB_OVF_QUOTA = 1u, SLAB_OVF_TABLE = 2u, SLAB_OVF_REACH = 4u, SLAB_OVF_TIMEOUT = 8u;
+
 // Exchange buffers hold quota + 1 records; record 0 is a header whose `gid` word is the count.
 // key[] still holds the cell of the frame-START position (ownership during the frame).
 __global__ void __launch_bounds__(256)
 k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __restrict__ low,
-            SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc) {
+            SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc, const SlabXfer* __restrict__ xf, int subSteps) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
+  if (xf) {                                     // peer-to-peer: my records go straight into the neighbours' buffers
+    const uint32_t par = sc->seq & 1u;
+    low = xf->send[0][par]; high = xf->send[1][par]; quota = xf->quota;
+  }
   bool owned = false;
   if (i < sc->top) {
     const uint32_t k = key[i];
@@ -1571,6 +1590,20 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
     // bands around the cuts of the NEXT frame (both sides of a cut know them already)
     toLow = sc->pendBegin > 0 && row < sc->pendBegin + g.slabHalo;
     toHigh = sc->pendEnd < g.rows && row >= sc->pendEnd - g.slabHalo;
+    // Guard of the halo depth: the halo is sized for the entities that were near a cut when the slabs
+    // were planned.  An entity whose reach (rows of neighbours that must be replicated for it: S + 1
+    // visual ranges for one that collides, two for an observer — trigger or no collider — whose capped
+    // row must be complete) exceeds the halo must stay clear of the cuts; if one gets there the
+    // partition would no longer reproduce the single-context result, so the slab says so.
+    const uint32_t f = d.F[i];
+    const double crd = ceil(dmul((double)d.AT[i].z, g.inv));
+    const int32_t cr = crd > 0 ? (crd < (double)g.rows ? (int32_t)crd : g.rows) : 0;      // NaN: empty window
+    const bool observer = (f & (F_C_ACTIVE | F_TRIGGER)) != F_C_ACTIVE;
+    const int32_t need = observer ? 2 * cr : (subSteps + 1) * cr;
+    const int32_t near = observer ? cr : need;
+    if (need > g.slabHalo &&
+        ((sc->pendBegin > 0 && row < sc->pendBegin + near) || (sc->pendEnd < g.rows && row >= sc->pendEnd - near)))
+      atomicOr(&sc->overflow, SLAB_OVF_REACH);
   }
   // positions in the two exchange buffers: ballot inside the warp, shared memory across the
   // warps, ONE atomic per block and direction
@@ -1596,11 +1629,11 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
   r.ax = a.x; r.ay = a.y;
   r.dp = d.DP[i]; r.at = d.AT[i]; r.v = d.V[i];
   const uint32_t below = (1u << lane) - 1u;
-  if (toLow) {
+  if (toLow && low) {
     const uint32_t p = baseLow + (uint32_t)__popc(mLow & below);
     if (p < quota) low[1 + p] = r;
   }
-  if (toHigh) {
+  if (toHigh && high) {
     const uint32_t p = baseHigh + (uint32_t)__popc(mHigh & below);
     if (p < quota) high[1 + p] = r;
   }
@@ -1609,19 +1642,50 @@ k_slab_pack(GridDims g, ById d, const uint32_t* __restrict__ key, SlabRec* __res
 // Header record (index 0) of a message: gid = record count, meta = the sender's smoothed frame time,
 // ax / ay = bit patterns of the sender's cuts for the next frame.
 __global__ void k_slab_headers(SlabRec* __restrict__ low, SlabRec* __restrict__ high, uint32_t quota, SlabCounters* sc,
-                               const Counters* __restrict__ ctr) {
+                               const Counters* __restrict__ ctr, const SlabXfer* __restrict__ xf) {
   if (threadIdx.x != 0) return;
-  if (sc->nLow > quota || sc->nHigh > quota) sc->overflow |= 1u;
+  if (xf) {
+    const uint32_t par = sc->seq & 1u;
+    low = xf->send[0][par]; high = xf->send[1][par]; quota = xf->quota;
+  }
+  if (sc->nLow > quota || sc->nHigh > quota) sc->overflow |= SLAB_OVF_QUOTA;
   const uint32_t ns = ctr->frameNs;
   sc->load = sc->load ? (uint32_t)((3ull * sc->load + ns) / 4) : ns;
   SlabRec* hdr[2] = {low, high};
   const uint32_t cnt[2] = {min(sc->nLow, quota), min(sc->nHigh, quota)};
   for (int k = 0; k < 2; k++) {
+    if (!hdr[k]) continue;
     hdr[k][0].gid = cnt[k];
     hdr[k][0].meta = sc->load;
     hdr[k][0].ax = __int_as_float(sc->pendBegin);
     hdr[k][0].ay = __int_as_float(sc->pendEnd);
   }
+  if (xf) {
+    // the records were written by the previous kernel, the header just now: make all of it visible to
+    // the peer before the arrival flag (the exchange number, never 0) appears
+    __threadfence_system();
+    for (int k = 0; k < 2; k++)
+      if (hdr[k]) *reinterpret_cast<volatile uint32_t*>(&hdr[k][0].dp.x) = sc->seq + 1u;
+    __threadfence_system();
+  }
+}
+
+// Spins until both neighbours' messages of this exchange have arrived (their flag shows the exchange
+// number).  Bounded: about two seconds of %globaltimer, then the slab reports SLAB_OVF_TIMEOUT
+// instead of hanging the device.
+__global__ void k_slab_wait(const SlabXfer* __restrict__ xf, SlabCounters* sc) {
+  if (threadIdx.x != 0) return;
+  const uint32_t par = sc->seq & 1u, want = sc->seq + 1u;
+  const unsigned long long t0 = global_timer_ns();
+  for (int side = 0; side < 2; side++) {
+    if (!xf->send[side][par]) continue;                        // no neighbour on that side
+    const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(&xf->recv[side][par][0].dp.x);
+    while (*flag != want) {
+      if (global_timer_ns() - t0 > 2000000000ull) { sc->overflow |= SLAB_OVF_TIMEOUT; return; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256)
@@ -1654,8 +1718,14 @@ k_slab_drop(GridDims g, ById d, const uint32_t* __restrict__ key, uint32_t* __re
 // first `quota` threads: records from the low neighbour, next `quota`: from the high one
 __global__ void __launch_bounds__(256)
 k_slab_unpack(ById d, const SlabRec* __restrict__ fromLow, const SlabRec* __restrict__ fromHigh, uint32_t quota,
-              const uint32_t* __restrict__ holes, uint32_t capacity, SlabCounters* sc) {
+              const uint32_t* __restrict__ holes, uint32_t capacity, SlabCounters* sc, const SlabXfer* __restrict__ xf) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xf) {
+    const uint32_t par = sc->seq & 1u;
+    fromLow = xf->send[0][par] ? xf->recv[0][par] : nullptr;
+    fromHigh = xf->send[1][par] ? xf->recv[1][par] : nullptr;
+    quota = xf->quota;
+  }
   const uint32_t nL = fromLow ? min(fromLow[0].gid, quota) : 0u;
   const uint32_t nH = fromHigh ? min(fromHigh[0].gid, quota) : 0u;
   const SlabRec* src;
@@ -1688,14 +1758,21 @@ __device__ __forceinline__ int32_t slab_cut_shift(const SlabCounters* sc, uint32
 }
 
 __global__ void k_slab_finish(const SlabRec* __restrict__ fromLow, const SlabRec* __restrict__ fromHigh, uint32_t quota,
-                              uint32_t capacity, SlabCounters* sc) {
+                              uint32_t capacity, SlabCounters* sc, const SlabXfer* __restrict__ xf) {
   if (threadIdx.x != 0) return;
+  if (xf) {
+    const uint32_t par = sc->seq & 1u;
+    fromLow = xf->send[0][par] ? xf->recv[0][par] : nullptr;
+    fromHigh = xf->send[1][par] ? xf->recv[1][par] : nullptr;
+    quota = xf->quota;
+  }
+  sc->seq++;
   const uint32_t nL = fromLow ? min(fromLow[0].gid, quota) : 0u;
   const uint32_t nH = fromHigh ? min(fromHigh[0].gid, quota) : 0u;
   const unsigned long long total = (unsigned long long)nL + nH;
   unsigned long long nt = sc->top;
   if (total > sc->nHoles) nt += total - sc->nHoles;
-  if (nt > capacity) { sc->overflow |= 2u; nt = capacity; }
+  if (nt > capacity) { sc->overflow |= SLAB_OVF_TABLE; nt = capacity; }
   sc->top = (uint32_t)nt;
   sc->lastOwned = sc->owned; sc->lastLow = sc->nLow; sc->lastHigh = sc->nHigh;
   sc->lastFromLow = nL; sc->lastFromHigh = nH;

@@ -55,7 +55,7 @@ class PhysicsWorker(_Worker):
 
 
 class GameEngine:
-    def __init__(self, config, device=0, flags=0, stream=None, host_neighbor_rows=True, slab=None):
+    def __init__(self, config, device=0, flags=0, stream=None, host_neighbor_rows=True, slab=None, adopt_ctx=None):
         L = B.lib()
         self.config = dict(config)
         # gameEngine.js:34-49 default merge
@@ -84,18 +84,46 @@ class GameEngine:
         cfg.device = device
         cfg.flags = flags
         cfg.stream = stream
+        self._cfg_struct = cfg
         if slab is not None:      # (rowBegin, rowEnd, haloRows): this context is one slab of the world
             cfg.slabRowBegin, cfg.slabRowEnd, cfg.slabHaloRows = (int(v) for v in slab)
         self.slab = slab
-        self.ctx = C.c_void_p()
-        rc = L.weed_create(C.byref(cfg), C.byref(self.ctx))
-        if rc != B.WEED_OK:
-            msg = L.weed_last_error(None)
-            raise B.WeedError(rc, msg.decode() if msg else "")
+        self._owns_ctx = adopt_ctx is None
+        if adopt_ctx is not None:      # a context somebody else created and will destroy (a slab of a weed_group)
+            self.ctx = C.c_void_p(adopt_ctx)
+        else:
+            self.ctx = C.c_void_p()
+            rc = L.weed_create(C.byref(cfg), C.byref(self.ctx))
+            if rc != B.WEED_OK:
+                msg = L.weed_last_error(None)
+                raise B.WeedError(rc, msg.decode() if msg else "")
         self.spatial = SpatialWorker(self)
         self.physics_worker = PhysicsWorker(self)
         self.buffers = {}
         self.createSharedBuffers(host_neighbor_rows)
+
+    @staticmethod
+    def config_struct(config, device=0, flags=0):
+        """weed_config for `config` with the engine's defaults applied (gameEngine.js:34-49), without creating
+        a context: the template weed_group_create takes."""
+        L = B.lib()
+        phys = dict(PHYSICS_DEFAULTS)
+        phys.update({k: v for k, v in (config.get("physics") or {}).items() if k not in ("gravity", "noLimitFPS")})
+        phys["gravity"] = dict((config.get("physics") or {}).get("gravity") or config.get("gravity") or {"x": 0, "y": 0})
+        spatial = config.get("spatial") or {}
+        cfg = B.Config()
+        L.weed_default_config(C.byref(cfg))
+        cfg.entityCount = int(config["entityCount"])
+        cfg.worldWidth = float(config["worldWidth"])
+        cfg.worldHeight = float(config["worldHeight"])
+        cfg.cellSize = float(spatial.get("cellSize") or config.get("cellSize"))
+        cfg.maxNeighbors = int(spatial.get("maxNeighbors") or config.get("maxNeighbors") or 100)
+        cfg.maxCollisionPairs = int(phys.get("maxCollisionPairs") or config.get("maxCollisionPairs") or 10000)
+        cfg.seed = float(config.get("seed") or 1.0)
+        cfg.physics = GameEngine._physics_struct(phys)
+        cfg.device = device
+        cfg.flags = flags
+        return cfg
 
     @staticmethod
     def _physics_struct(phys):
@@ -362,7 +390,8 @@ class GameEngine:
 
     def close(self):
         if getattr(self, "ctx", None):
-            B.lib().weed_destroy(self.ctx)
+            if self._owns_ctx:
+                B.lib().weed_destroy(self.ctx)
             self.ctx = None
 
     def __del__(self):

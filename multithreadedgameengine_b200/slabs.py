@@ -36,23 +36,45 @@ def cell_rows(cfg, y):
     return np.clip(r, 0, rows - 1).astype(np.int64), rows
 
 
-def halo_rows(cfg, cols):
+GUARD_ROWS = 8      # an observer this close to its reach of a cut counts as "near" when the slabs are planned
+
+
+def halo_rows(cfg, cols, blocks=None):
     """Replicated rows beyond each cut.
 
     Entities that can move or push (non-trigger colliders) propagate position dependencies one
     visual range per substep, and the pair-membership inference looks one more range out (a
-    partner's row must be complete): (S+1) * h_dyn.  Observers (triggers such as the Mouse,
-    src/core/Mouse.js:139-145, and non-colliders) never move anybody, so they do not extend the
-    chain; but an owned entity's collisionCount needs the observer's row to be complete when it
-    is capped: 2 * h_obs."""
+    partner's row must be complete): reach (S+1) * h, wherever they are — they move.
+    Observers (triggers such as the Mouse, src/core/Mouse.js:139-145, and non-colliders) never move
+    anybody, so they do not extend the chain; but when one lies within h rows of a cut, the slabs
+    on both sides need its capped row complete: reach 2 * h.  The Mouse of the large scenes
+    (visualRange 150, ten cells) parked in a corner therefore costs nothing: with `blocks` (the
+    planned cuts) only the observers near a cut count.  The library checks the same rule on the
+    device every frame (k_slab_pack): an entity whose reach exceeds the halo and that comes near a
+    cut makes weed_slab_status fail instead of letting the partition diverge."""
     act = cols["T.active"] != 0
-    vr = np.where(np.isfinite(cols["C.visualRange"]), cols["C.visualRange"], 0).astype(np.float64)
-    observer = (cols["C.isTrigger"] != 0) | (cols["C.active"] == 0)
+    vr = cols["C.visualRange"].astype(np.float64)
     cs = float(cfg["spatial"]["cellSize"])
+    rows = math.ceil(cfg["worldHeight"] / cs)
+    with np.errstate(invalid="ignore"):
+        cr = np.ceil(vr * (1.0 / cs))
+    cr = np.where(np.isnan(cr), 0.0, np.clip(cr, 0, rows))
+    observer = (cols["C.isTrigger"] != 0) | (cols["C.active"] == 0)
     S = int(cfg["physics"].get("subStepCount", 4))
-    h_dyn = math.ceil(float(vr[act & ~observer].max(initial=0.0)) / cs)
-    h_obs = math.ceil(float(vr[act & observer].max(initial=0.0)) / cs)
-    return max(1, (S + 1) * h_dyn, 2 * h_obs)
+    need = np.where(observer, 2 * cr, (S + 1) * cr)
+    H = int(need[act & ~observer].max(initial=1.0))
+    obs = act & observer
+    if obs.any():
+        if blocks is None:
+            H = max(H, int(need[obs].max()))
+        else:
+            row, _ = cell_rows(cfg, cols["T.y"])
+            cuts = np.array([b for (_, b) in blocks[:-1]], dtype=np.int64)
+            if len(cuts):
+                dist = np.abs(row[obs][:, None] - cuts[None, :]).min(axis=1)
+                near = dist <= cr[obs] + GUARD_ROWS
+                H = max(H, int(need[obs][near].max(initial=0)))
+    return max(1, H)
 
 
 def row_costs(cfg, cols):
@@ -88,7 +110,8 @@ def plan_slabs(cfg, cols, world, balance="cost"):
         r = int(np.searchsorted(cum, target)) + 1
         cuts.append(min(max(r, cuts[-1] + 1), rows - (world - k)))
     cuts.append(rows)
-    return [(cuts[k], cuts[k + 1]) for k in range(world)], halo_rows(cfg, cols)
+    blocks = [(cuts[k], cuts[k + 1]) for k in range(world)]
+    return blocks, halo_rows(cfg, cols, blocks)
 
 
 def replan_from_times(blocks, times_ms, row_weight=None):
@@ -139,56 +162,123 @@ def header_count(buf):
 
 
 class SlabEngine:
-    """One slab = one GameEngine over a LOCAL entity table + the exchange buffers."""
+    """One slab = one GameEngine over a LOCAL entity table + its share of the exchange.
+
+    transport "p2p" (default): the library's peer-to-peer exchange (weed_slab_exchange_*): the pack
+    kernel writes into the neighbour's receive buffer over NVLink and the frame needs no host work at
+    all — `step_dist` is ONE call, weed_slab_frame.  Between processes the buffers are shared through
+    CUDA IPC handles that travel once, at setup, over torch.distributed; inside one process
+    (SlabGroup) through plain device pointers.  transport "nccl": the round-1 path, one fixed-size
+    send/recv per neighbour through torch.distributed, kept as the fallback for boxes without peer
+    access."""
 
     def __init__(self, cfg, cols, rank, world, device=0, flags=0, stream=None, plan=None,
-                 capacity_factor=1.35, host_neighbor_rows=False, balance_rows=0, balance_hysteresis=3):
+                 capacity_factor=1.35, host_neighbor_rows=False, balance_rows=0, balance_hysteresis=3,
+                 transport="p2p", connect=True, adopt_ctx=None, capacity=None, quota=None):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
         self.blocks, self.H = plan if plan is not None else plan_slabs(cfg, cols, world)
         self.rb, self.re = self.blocks[rank]
-        row, self.rows = cell_rows(cfg, cols["T.y"])
-        act = cols["T.active"] != 0
-        fin = np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"])
-        inside = act & fin & (row >= self.rb - self.H) & (row < self.re + self.H)
-        if rank == 0:   # active entities that never enter the grid (NaN position) live on slab 0
-            inside |= act & ~fin
-        sel = np.nonzero(inside)[0].astype(np.uint32)
-        self.capacity = int(len(sel) * capacity_factor) + 4096
-        if balance_rows:        # moving cuts even the slabs out: size every table for an even share (+ halo) as well
-            self.capacity = max(self.capacity, int((int(act.sum()) / world) * (capacity_factor + 0.25)) + 4096)
-        lcfg = dict(cfg)
-        lcfg["entityCount"] = self.capacity
         self.cfg = cfg
         self.S = int(cfg["physics"].get("subStepCount", 4))
+        sel = self.select(cfg, cols, rank, self.blocks, self.H)
+        self.capacity = capacity or self.plan_capacity(cfg, cols, world, len(sel), capacity_factor, balance_rows)
+        self.quota = quota or self.plan_quota(cfg, cols, self.blocks, self.H, balance_rows)
+        lcfg = dict(cfg)
+        lcfg["entityCount"] = self.capacity
+        if transport == "nccl" and stream is None:
+            # the NCCL calls of torch.distributed are ordered against torch's CURRENT stream only: the
+            # context must run on a stream torch knows, and the exchange under `with torch.cuda.stream`
+            self._tstream = torch.cuda.Stream(device=device)
+            stream = self._tstream.cuda_stream
+        else:
+            self._tstream = None
+        self._ext_stream = stream
         self.eng = GameEngine(lcfg, device=device, flags=flags, stream=stream, host_neighbor_rows=host_neighbor_rows,
-                              slab=(self.rb, self.re, self.H))
+                              slab=(self.rb, self.re, self.H), adopt_ctx=adopt_ctx)
         for k, v in cols.items():
             self.eng.column(k)[:len(sel)] = v[sel]
         self.eng.upload(B.COLS_INPUT_ALL)
         B.check(self.eng.ctx, B.lib().weed_slab_set_gids(self.eng.ctx, sel.ctypes.data, len(sel)))
-        # exchange quota: 1.5x the start population of the widest boundary band of ANY cut (+ slack),
-        # the same on every rank, because the two sides of a cut must agree on the message size;
-        # every frame moves exactly (quota + 1) records per neighbour and direction
-        hist = np.bincount(row[act & fin], minlength=self.rows)
-        band = 0
-        if balance_rows:
-            # cuts move: size the messages for the most crowded (halo + shift)-row window of the
-            # start scene wherever it lies (the mean band x 1.5 would overflow inside a cluster)
-            w = self.H + int(balance_rows)
-            csum = np.concatenate([[0], np.cumsum(hist)])
-            band = int((csum[w:] - csum[:-w]).max()) if len(hist) > w else int(hist.sum())
-            self.quota = band + band // 4 + 8192
-        else:
-            for (_, cut) in self.blocks[:-1]:
-                band = max(band, int(hist[max(0, cut - self.H):cut].sum()), int(hist[cut:cut + self.H].sum()))
-            self.quota = band + band // 2 + 8192
         if balance_rows:        # cuts follow the measured load (weed_slab_balance)
             B.check(self.eng.ctx, B.lib().weed_slab_balance(self.eng.ctx, int(balance_rows), int(balance_hysteresis)))
-        dev = torch.device("cuda", device)
-        mk = lambda: torch.zeros((self.quota + 1) * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
-        self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
+        self.transport = transport
+        self.device = device
+        if transport == "p2p":
+            if adopt_ctx is None:
+                B.check(self.eng.ctx, B.lib().weed_slab_exchange_create(self.eng.ctx, self.quota))
+                if connect and world > 1:
+                    self.connect_dist()
+        else:
+            dev = torch.device("cuda", device)
+            mk = lambda: torch.zeros((self.quota + 1) * B.SLAB_RECORD_BYTES, dtype=torch.uint8, device=dev)
+            self.send_low, self.send_high, self.recv_low, self.recv_high = mk(), mk(), mk(), mk()
+
+    # ---- planning helpers (identical on every rank: the two sides of a cut must agree) --------------
+    @staticmethod
+    def select(cfg, cols, rank, blocks, H):
+        rb, re = blocks[rank]
+        row, _ = cell_rows(cfg, cols["T.y"])
+        act = cols["T.active"] != 0
+        fin = np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"])
+        inside = act & fin & (row >= rb - H) & (row < re + H)
+        if rank == 0:   # active entities that never enter the grid (NaN position) live on slab 0
+            inside |= act & ~fin
+        return np.nonzero(inside)[0].astype(np.uint32)
+
+    @staticmethod
+    def plan_capacity(cfg, cols, world, n_local, capacity_factor=1.35, balance_rows=0):
+        cap = int(n_local * capacity_factor) + 4096
+        if balance_rows:        # moving cuts even the slabs out: size every table for an even share (+ halo) as well
+            act = int((cols["T.active"] != 0).sum())
+            cap = max(cap, int((act / world) * (capacity_factor + 0.25)) + 4096)
+        return cap
+
+    @staticmethod
+    def plan_quota(cfg, cols, blocks, H, balance_rows=0):
+        """Records one message can hold: the same on every rank.  The peer-to-peer transport only
+        moves the records that exist (the quota is the size of the receive buffers: memory, not
+        traffic); the NCCL fallback sends whole buffers."""
+        row, rows = cell_rows(cfg, cols["T.y"])
+        act = cols["T.active"] != 0
+        fin = np.isfinite(cols["T.x"]) & np.isfinite(cols["T.y"])
+        hist = np.bincount(row[act & fin], minlength=rows)
+        if balance_rows:
+            # cuts move: size for the most crowded (halo + shift)-row window of the start scene wherever it lies
+            w = H + int(balance_rows)
+            csum = np.concatenate([[0], np.cumsum(hist)])
+            band = int((csum[w:] - csum[:-w]).max()) if len(hist) > w else int(hist.sum())
+            return band + band // 4 + 8192
+        band = 0
+        for (_, cut) in blocks[:-1]:
+            band = max(band, int(hist[max(0, cut - H):cut].sum()), int(hist[cut:cut + H].sum()))
+        return band + band // 2 + 8192
+
+    # ---- peer-to-peer setup -----------------------------------------------------------------------
+    def export(self):
+        """(64-byte IPC handle, device pointer) of this slab's receive buffers."""
+        h = (C.c_ubyte * 64)()
+        base = C.c_void_p()
+        B.check(self.eng.ctx, B.lib().weed_slab_exchange_export(self.eng.ctx, h, C.byref(base)))
+        return bytes(h), base.value
+
+    def connect(self, side, handle=None, base=None):
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        B.check(self.eng.ctx, B.lib().weed_slab_exchange_connect(self.eng.ctx, side, hb, base))
+
+    def connect_dist(self):
+        """One process per GPU: the IPC handles travel once over torch.distributed."""
+        dist = self.torch.distributed
+        handle, _ = self.export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        if self.rank > 0:
+            self.connect(0, handle=handles[self.rank - 1])
+        if self.rank + 1 < self.world:
+            self.connect(1, handle=handles[self.rank + 1])
+        self._connected_dist = True
+        dist.barrier()
 
     # ---- one frame of this slab: everything below is asynchronous on the context's stream ---------
     def run(self, dtRatio=1.0):
@@ -202,25 +292,49 @@ class SlabEngine:
         hi = self.recv_high.data_ptr() if self.rank + 1 < self.world else None
         B.check(self.eng.ctx, B.lib().weed_slab_apply(self.eng.ctx, lo, hi, self.quota))
 
+    def _nccl_stream(self):
+        t = self.torch
+        if self._tstream is not None:
+            return t.cuda.stream(self._tstream)
+        return t.cuda.stream(t.cuda.ExternalStream(self._ext_stream, device=self.device))
+
     def exchange_dist(self):
-        """pack -> one fixed-size NCCL send/recv per adjacent rank -> apply; no host synchronisation."""
-        self.pack()
-        exchange_fixed(self.torch, self.rank, self.world, self.send_low, self.send_high, self.recv_low, self.recv_high)
-        self.apply()
+        """The exchange alone (after a frame run by `run` or `eng.step`)."""
+        if self.transport == "p2p":
+            B.check(self.eng.ctx, B.lib().weed_slab_exchange(self.eng.ctx))
+            return
+        with self._nccl_stream():        # pack -> one fixed-size send/recv per adjacent rank -> apply, all on ONE stream
+            self.pack()
+            exchange_fixed(self.torch, self.rank, self.world, self.send_low, self.send_high, self.recv_low, self.recv_high)
+            self.apply()
 
     def step_dist(self, dtRatio=1.0):
+        if self.transport == "p2p":      # frame kernels + pack into the neighbours' buffers + wait + apply: one call, no host work
+            B.check(self.eng.ctx, B.lib().weed_slab_frame(self.eng.ctx, float(dtRatio)))
+            return
         self.run(dtRatio)
         self.exchange_dist()
 
+    def frame_begin(self, dtRatio=1.0):
+        B.check(self.eng.ctx, B.lib().weed_slab_frame_begin(self.eng.ctx, float(dtRatio)))
+
+    def frame_end(self):
+        B.check(self.eng.ctx, B.lib().weed_slab_frame_end(self.eng.ctx))
+
     def status(self):
-        """Synchronises; raises if a quota or the entity table overflowed at any time."""
+        """Synchronises; raises if a quota, the entity table or the halo reach was exceeded at any time."""
         st = B.SlabStats()
         B.check(self.eng.ctx, B.lib().weed_slab_status(self.eng.ctx, C.byref(st)))
         return {n: getattr(st, n) for n, _ in st._fields_}
 
     @property
     def exchange_bytes_per_frame(self):
+        """Bytes this slab sent in its last exchange (synchronises).  p2p: the records that exist plus
+        one header per neighbour; nccl: whole buffers."""
         n = (self.rank > 0) + (self.rank + 1 < self.world)
+        if self.transport == "p2p":
+            st = self.status()
+            return (st["sentLow"] + st["sentHigh"] + n) * B.SLAB_RECORD_BYTES
         return n * (self.quota + 1) * B.SLAB_RECORD_BYTES
 
     # ---- results -----------------------------------------------------------------------------------
@@ -246,35 +360,90 @@ class SlabEngine:
         return g[idx], {k: c[k][idx].copy() for k in keys}, idx
 
     def close(self):
+        if getattr(self, "_connected_dist", False) and self.eng.ctx:
+            # unmap the neighbours' buffers, wait for everybody, only then free mine
+            B.lib().weed_slab_exchange_disconnect(self.eng.ctx)
+            self.torch.distributed.barrier()
+            self._connected_dist = False
         self.eng.close()
 
 
 class SlabGroup:
-    """All slabs of a world inside ONE process (contexts may share a device): the exchange is a
-    device-to-device copy.  Used by the single-GPU tests; the multi-process path is
-    SlabEngine.step_dist."""
+    """All slabs of a world inside ONE process (contexts may share a device).
 
-    def __init__(self, cfg, cols, world, devices=None, plan=None, **kw):
+    mode "c" (default): the library's weed_group_* entry points — what a single Node engine would call
+    — create the contexts and step them; mode "py": SlabEngines created here and connected through
+    device pointers (weed_slab_exchange_connect); mode "nccl-buffers": the round-1 staging path
+    (weed_slab_pack / weed_slab_apply with a device-to-device copy in between)."""
+
+    def __init__(self, cfg, cols, world, devices=None, plan=None, mode="c", **kw):
         plan = plan or plan_slabs(cfg, cols, world)
         devices = devices or [0] * world
-        self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, **kw) for r in range(world)]
+        self.mode = mode
+        self.group = None
+        balance_rows = kw.get("balance_rows", 0)
+        if mode == "c":
+            blocks, H = plan
+            sels = [SlabEngine.select(cfg, cols, r, blocks, H) for r in range(world)]
+            caps = [SlabEngine.plan_capacity(cfg, cols, world, len(s), kw.get("capacity_factor", 1.35), balance_rows) for s in sels]
+            quota = SlabEngine.plan_quota(cfg, cols, blocks, H, balance_rows)
+            probe = GameEngine.config_struct(cfg, flags=kw.get("flags", 0))
+            cuts = (C.c_uint32 * (world + 1))(*([b[0] for b in blocks] + [blocks[-1][1]]))
+            devs = (C.c_int32 * world)(*devices)
+            capa = (C.c_uint32 * world)(*caps)
+            g = C.c_void_p()
+            rc = B.lib().weed_group_create(C.byref(probe), world, devs, cuts, H, capa, quota, C.byref(g))
+            if rc != B.WEED_OK:
+                msg = B.lib().weed_group_last_error(None)
+                raise B.WeedError(rc, msg.decode() if msg else "")
+            self.group = g
+            self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, transport="p2p",
+                                     adopt_ctx=B.lib().weed_group_slab(g, r), capacity=caps[r], quota=quota, **kw)
+                          for r in range(world)]
+        elif mode == "py":
+            self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, transport="p2p", connect=False, **kw)
+                          for r in range(world)]
+            bases = [s.export()[1] for s in self.slabs]
+            for r, s in enumerate(self.slabs):
+                if r > 0:
+                    s.connect(0, base=bases[r - 1])
+                if r + 1 < world:
+                    s.connect(1, base=bases[r + 1])
+        else:
+            self.slabs = [SlabEngine(cfg, cols, r, world, device=devices[r], plan=plan, transport="nccl", **kw) for r in range(world)]
 
-    def step(self, dtRatio=1.0):
-        for s in self.slabs:
-            s.run(dtRatio)
-        for s in self.slabs:
-            s.pack()
-        self.slabs[0].torch.cuda.synchronize()
-        for r, s in enumerate(self.slabs):
-            if r > 0:
-                s.recv_low.copy_(self.slabs[r - 1].send_high)
-            if r + 1 < len(self.slabs):
-                s.recv_high.copy_(self.slabs[r + 1].send_low)
-        self.slabs[0].torch.cuda.synchronize()
-        for s in self.slabs:
-            s.apply()
-        for s in self.slabs:
-            s.status()
+    def step(self, dtRatio=1.0, check=True):
+        if self.mode == "c":
+            rc = B.lib().weed_group_step(self.group, float(dtRatio))
+            if rc != B.WEED_OK:
+                raise B.WeedError(rc, B.lib().weed_group_last_error(self.group).decode())
+            if check:
+                rc = B.lib().weed_group_sync(self.group)
+                if rc != B.WEED_OK:
+                    raise B.WeedError(rc, B.lib().weed_group_last_error(self.group).decode())
+            return
+        if self.mode == "py":
+            for s in self.slabs:
+                s.frame_begin(dtRatio)
+            for s in self.slabs:
+                s.frame_end()
+        else:
+            for s in self.slabs:
+                s.run(dtRatio)
+            for s in self.slabs:
+                s.pack()
+            self.slabs[0].torch.cuda.synchronize()
+            for r, s in enumerate(self.slabs):
+                if r > 0:
+                    s.recv_low.copy_(self.slabs[r - 1].send_high)
+                if r + 1 < len(self.slabs):
+                    s.recv_high.copy_(self.slabs[r + 1].send_low)
+            self.slabs[0].torch.cuda.synchronize()
+            for s in self.slabs:
+                s.apply()
+        if check:
+            for s in self.slabs:
+                s.status()
 
     def gather(self, N, keys=("T.x", "T.y", "RB.px", "RB.py", "RB.vx", "RB.vy", "RB.speed", "RB.collisionCount")):
         out = {k: None for k in keys}
@@ -291,3 +460,6 @@ class SlabGroup:
     def close(self):
         for s in self.slabs:
             s.close()
+        if self.group is not None:
+            B.lib().weed_group_destroy(self.group)
+            self.group = None

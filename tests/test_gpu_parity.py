@@ -119,6 +119,38 @@ def test_split_workers_equal_fused_step():
     a.close(); b.close()
 
 
+def test_split_workers_with_a_host_tick_in_between():
+    """The flow that swaps ONE worker: weed_spatial, a host tick() that reads the fresh rows and writes
+    ax / ay, weed_upload(ax | ay), weed_physics.  Uploading accelerations must not invalidate the rows
+    (ADVICE r1); uploading a position must."""
+    rng = np.random.default_rng(11)
+    cfg, cols = random_scene(rng, N=900, M=24)
+    a = make_engine(cfg, cols)
+    b = make_engine(cfg, cols)
+    acc = a.mask("RB.ax", "RB.ay")
+    for f in range(3):
+        tick = np.random.default_rng(50 + f)
+        ax = ((tick.random(cfg["entityCount"]) - 0.5) * 2).astype(np.float32)
+        ay = ((tick.random(cfg["entityCount"]) - 0.5) * 2).astype(np.float32)
+        a.col["RB.ax"][:] = ax; a.col["RB.ay"][:] = ay
+        a.step(1.0, acc, ALL_DL)                         # fused: upload, spatial, physics
+        b.spatial.update()
+        b.fetch_neighbors()                              # what tick() would read
+        b.col["RB.ax"][:] = ax; b.col["RB.ay"][:] = ay
+        b.upload(acc)
+        b.physics_worker.update(16.67, 1.0)
+        b.download(ALL_DL)
+        assert_cols_equal(a.col, b.col)
+        assert np.array_equal(a.neighborData, b.neighborData)
+        n = int(a.collisionData[0])
+        assert np.array_equal(a.collisionData[:1 + 2 * n], b.collisionData[:1 + 2 * n])
+    b.spatial.update()
+    b.upload(b.mask("T.x"))                              # a teleport: the grid is stale now
+    with pytest.raises(B.WeedError):
+        b.physics_worker.update(16.67, 1.0)
+    a.close(); b.close()
+
+
 def test_config1_readme_scene_30_frames():
     cfg, cols = scenes.balls_readme()
     eng = make_engine(cfg, cols)

@@ -1,6 +1,7 @@
-"""Row-slab partition (multi-GPU path) exercised on ONE GPU: K slab contexts in one process
-exchange their boundary bands by device copies (the multi-process path swaps the copy for
-NCCL send/recv, everything else is the same code).  The partitioned world must reproduce the
+"""Row-slab partition (multi-GPU path) exercised on ONE GPU: K slab contexts in one process.
+Default: the library's own multi-GPU entry points (weed_group_create / weed_group_step: pack kernels
+write into the neighbours' receive buffers, the waits are on the device — the same kernels the
+multi-process path runs over CUDA IPC mappings).  The partitioned world must reproduce the
 unpartitioned engine BIT FOR BIT for every entity, every frame."""
 import numpy as np
 import pytest
@@ -63,10 +64,39 @@ def test_observer_on_a_cut_and_capped_rows():
 
 
 def test_plan_balances_entities():
+    from multithreadedgameengine_b200.slabs import halo_rows
     cfg, cols = scenes.scaled("config4", 50000)
     blocks, H = plan_slabs(cfg, cols, 4)
     assert blocks[0][0] == 0 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
-    assert H == 20         # max((S+1) * ceil(16/16), 2 * ceil(150/16)): the Mouse's range dominates
+    assert H == 20                         # clusters piled on the y = 0 wall pull the first cut next to the Mouse: 2 * ceil(150/16)
+    cfg, cols = scenes.scaled("config3", 50000)
+    blocks, H = plan_slabs(cfg, cols, 2)
+    assert H == 3                          # (S+1) * ceil(16/16): the Mouse sits in a corner, far from the cut
+    assert halo_rows(cfg, cols) == 20      # without the cuts its range counts
+
+
+@pytest.mark.parametrize("mode", ["c", "py", "nccl-buffers"])
+def test_every_transport_reproduces_the_single_context(mode):
+    """weed_group_* (mode c), SlabEngines connected through weed_slab_exchange_connect (py) and the
+    staging path weed_slab_pack / weed_slab_apply (what the NCCL fallback uses)."""
+    cfg, cols = scenes.scaled("config4", 50000)
+    run_case(cfg, cols, 3, frames=5, mode=mode).close()
+
+
+def test_reach_guard_reports_an_observer_that_comes_near_a_cut():
+    """The halo is planned for the entities near the cuts at the start (3 rows here: the Mouse is
+    far away).  Move the Mouse next to a cut: its capped row would need 20 rows of halo, the
+    partition could silently diverge — the slab must say so instead."""
+    cfg, cols = scenes.scaled("config3", 50000)
+    plan = plan_slabs(cfg, cols, 2)
+    assert plan[1] == 3
+    cols["T.x"][0] = 300.0
+    cols["T.y"][0] = plan[0][0][1] * 16.0 - 40.0          # two rows below the cut
+    grp = SlabGroup(cfg, cols, 2, plan=plan)
+    with pytest.raises(B.WeedError) as e:
+        grp.step(1.0)
+    assert e.value.code == B.WEED_E_OVERFLOW and "reach" in str(e.value)
+    grp.close()
 
 
 def test_dynamic_cuts_follow_the_load_and_stay_bit_exact():
