@@ -111,11 +111,9 @@ enum {
   WEED_FLAG_KERNEL_TIMING = 1u << 1,  /* per-kernel cudaEvent timing into weed_stats    */
   WEED_FLAG_NO_NEIGHBOR_ROWS = 1u << 2, /* do not allocate/write neighborData/distanceData
                                           (physics-only consumers); rows then unavailable */
-  /* measurement aids (A/B runs of tools/ab_kernels.py and the cross-check tests): run another
-   * form of a kernel.  Results are bit-identical whichever form runs.                       */
-  WEED_FLAG_K4_V1         = 1u << 8,  /* neighbor scan: k_neighbors (round 1) instead of k_neighbors2   */
-  WEED_FLAG_K6_V1         = 1u << 9,  /* collision sweep: k_substep (round 1) instead of k_sweep        */
-  WEED_FLAG_K6_TILE       = 1u << 10  /* collision sweep: k_sweep_tile (TMA-staged tiles; slower)       */
+  /* measurement aid (tools/ab_kernels.py and the cross-check tests): another form of the collision
+   * sweep.  Results are bit-identical whichever form runs.                                    */
+  WEED_FLAG_K6_TILE       = 1u << 10  /* k_sweep_tile (TMA-staged tiles; measured slower)        */
 };
 
 /* The "init" message: gameEngine.js:1049-1125 (entityCount, config.worldWidth/Height,

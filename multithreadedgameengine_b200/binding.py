@@ -38,8 +38,6 @@ COL_COLLISIONS = 1 << 25
 FLAG_NO_GRAPH = 1 << 0
 FLAG_KERNEL_TIMING = 1 << 1
 FLAG_NO_NEIGHBOR_ROWS = 1 << 2
-FLAG_K4_V1 = 1 << 8
-FLAG_K6_V1 = 1 << 9
 FLAG_K6_TILE = 1 << 10
 
 DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL, DEV_NEIGHBOR_COUNT, DEV_SLOT_OF = range(8)

@@ -323,9 +323,14 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return WEED_E_INVALID; }
   if (cfg->struct_size != sizeof(weed_config)) { g_create_error = "weed_config.struct_size mismatch (ABI)"; return WEED_E_INVALID; }
   if (cfg->entityCount == 0 || cfg->entityCount > 0x3FFFFFF0u) { g_create_error = "entityCount out of range"; return WEED_E_INVALID; }
-  if (((double)cfg->entityCount + 128.0) * (double)(((cfg->maxNeighbors + 7) / 8) * 8) >= 4294967295.0) {
-    g_create_error = "entityCount * maxNeighbors must stay below 2^32 per context (partition the world into slabs)";
-    return WEED_E_INVALID;
+  if (cfg->maxNeighbors > 32000) { g_create_error = "maxNeighbors above 32000"; return WEED_E_INVALID; }
+  {
+    const double mpad = (double)(((cfg->maxNeighbors + 7) / 8) * 8);
+    const double mint = mpad + std::max(16.0, std::min(mpad, 128.0));
+    if (((double)cfg->entityCount + 128.0) * mint >= 4294967295.0) {
+      g_create_error = "entityCount * (internal row capacity) must stay below 2^32 per context (partition the world into slabs)";
+      return WEED_E_INVALID;
+    }
   }
   if (!(cfg->cellSize > 0) || !(cfg->worldWidth > 0) || !(cfg->worldHeight > 0)) { g_create_error = "world/cell size must be positive"; return WEED_E_INVALID; }
   const double colsD = ceil(cfg->worldWidth / cfg->cellSize), rowsD = ceil(cfg->worldHeight / cfg->cellSize);  // spatial_worker.js:82-83
@@ -364,6 +369,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.N = cfg->entityCount;
   g.M = cfg->maxNeighbors;
   g.Mpad = ((g.M + 7) / 8) * 8; if (g.Mpad == 0) g.Mpad = 8;
+  g.Mint = g.Mpad + std::max(16u, std::min(g.Mpad, 128u));   // API row + lower-id partners found past the cap (then F_XOVER)
   g.Npad = ((g.N + TILE - 1) / TILE) * TILE;   // whole tiles: a tile's row words are one aligned bulk copy
   g.maxPairs = cfg->maxCollisionPairs;
   {
@@ -390,9 +396,9 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.CAPLIST, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
-  A(ctx->s.NST, (size_t)g.Npad * g.Mpad);
+  A(ctx->s.NST, (size_t)g.Npad * g.Mint);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
   ctx->rowWords = (size_t)g.Npad * g.Mpad;
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
@@ -581,18 +587,11 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
     if (ctx->nd) k_neighbors_wide<true><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
     else         k_neighbors_wide<false><<<wb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   } else {
-    if (ctx->cfg.flags & WEED_FLAG_K4_V1) {
-      const unsigned kb = blocks_for(g.N, K4_THREADS);
-      if (ctx->nd) k_neighbors<true><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
-      else         k_neighbors<false><<<kb, K4_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
-    } else {
-      const unsigned kb = blocks_for(g.N, K4V2_THREADS);
-      if (ctx->nd) k_neighbors2<true><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
-      else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
-    }
+    const unsigned kb = blocks_for(g.N, K4V2_THREADS);
+    if (ctx->nd) k_neighbors2<true><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->nd, ctx->dd, ctx->dCtr);
+    else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   }
   TIME_MARK(ctx, timing, 5);
-  k_capped_rescan<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
@@ -602,7 +601,6 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
 static int launch_constraints(weed_ctx* ctx, bool timing) {
   const GridDims& g = ctx->g;
   cudaStream_t st = ctx->stream;
-  const unsigned tb = blocks_for(g.N, K6_THREADS);
   const int S = ctx->phys.subStepCount;
   // sweep 0 reads GA (written by k_slot_prep), then GB / GA alternate
   const float4* in = ctx->s.GA;
@@ -613,12 +611,7 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
     float4* out = bufs[step & 1];
     const bool first = step == 0, last = step == S - 1;
 #define SWEEP_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step
-    if (kflags & WEED_FLAG_K6_V1) {
-      if (first && last)       k_substep<true, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else if (first)          k_substep<true, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else if (last)           k_substep<false, true><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-      else                     k_substep<false, false><<<tb, K6_THREADS, 0, st>>>(g, ctx->dParams, ctx->s, in, gs, out, ctx->cellStart, ctx->dCtr, (uint32_t)step);
-    } else if (kflags & WEED_FLAG_K6_TILE) {
+    if (kflags & WEED_FLAG_K6_TILE) {
       const unsigned sb = blocks_for(g.N, TILE);
       if (first && last)       k_sweep_tile<true, true><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
       else if (first)          k_sweep_tile<true, false><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
@@ -672,7 +665,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -756,7 +749,7 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
     if (rc) return rc;
   }
   const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
-  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
   rc = launch_spatial(ctx, true, false, waitUp, early ? ctx->evBuilt : nullptr);
   if (rc) return rc;
   if (early) {
@@ -863,7 +856,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 14 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 13 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
   return WEED_OK;

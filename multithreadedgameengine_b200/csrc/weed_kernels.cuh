@@ -227,13 +227,13 @@ struct BySlot {
   float4* GA;        // substep ping-pong: x, y, radius, flagword
   float4* GB;
   float2* PXY;       // px, py after the first substep
-  uint32_t* NCNT;    // neighbor count
+  uint32_t* NCNT;    // neighbor count of the API row | entries of the internal row << 16
   uint32_t* NST;     // internal rows, transposed: NST[k * Npad + slot]
   uint32_t* XHEAD;   // explicit incoming pairs: list head (0 = empty, else node + 1)
   uint32_t* XNEXT;   // next link, indexed by the OWNER's row position (k * Npad + slot)
   OutRec* OUT;       // last-substep result
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
-  uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
+  uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
   TileDesc* TD;      // one descriptor per TILE slots (k_slot_prep), or nullptr when no tiled kernel runs
 };
 
@@ -330,7 +330,7 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   if (s.SLID) s.SLID[slot] = i;
   uint32_t keep = 0;
   if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
-    keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & F_CAPPED;   // query position stays the pre-move one
+    keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & (F_CAPPED | F_XOVER);   // query position stays the pre-move one
     // no k_slot_prep follows on this path: the first sweep's boundary pass happens here
     if (INTEGRATE && moved && !clear_of_walls(g, dp.x, dp.y, at.y)) apply_bounds(g, p.boundaryElasticity, at.y, dp.x, dp.y, dp.z, dp.w);
   }
@@ -434,145 +434,43 @@ __device__ __forceinline__ void row_tail_fill(const GridDims& g, const BySlot& s
   for (uint32_t k = n; k < ((n + 3u) & ~3u); k++) s.NST[k * g.Npad + e] = e;
 }
 
+// Would the scan of the entity in slot tc accept me (ignoring its cap)?  Its precomputed window must hold
+// my clamped cell and its predicate 0 < d2 < vr^2 must pass (d2 is bitwise symmetric; d2 > 0 is known).
+__device__ __forceinline__ bool scan_accepts(const GridDims& g, const BySlot& s, uint32_t tc, double myX, double myY,
+                                             int32_t myCol, int32_t myRow, uint32_t myVrBits) {
+  const float4 c = s.CXY[tc];
+  const int4 wt = s.WIN[tc];
+  // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
+  bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+  if (back && __float_as_uint(c.z) != myVrBits) {
+    const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+    const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+    back = d2 < dmul((double)c.z, (double)c.z);
+  }
+  return back;
+}
+
+// End of an entity's scan: counts (API row | internal row << 16), the slot that closes a capped row,
+// flags, padding of the internal row.  A capped row is "everything the scan accepts up to LSLOT", so
+// `am I in the row of the capped entity t` is one comparison: my slot <= LSLOT[t].
+__device__ __forceinline__ void row_finish(const GridDims& g, const BySlot& s, Counters* ctr, uint32_t e, uint32_t n,
+                                           uint32_t lastApi, bool xover) {
+  const uint32_t api = min(n, g.M);
+  uint32_t add = 0;
+  if (api >= g.M && g.M > 0) { add |= F_CAPPED; ctr->anyCapped = 1; }
+  if (xover) add |= F_XOVER;
+  if (add) {
+    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
+    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+  }
+  s.NCNT[e] = api | (n << 16);
+  s.LSLOT[e] = lastApi;
+  row_tail_fill(g, s, e, n);
+}
+
 __device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, uint32_t dstSlot, uint32_t ownerRowPos) {
   s.XNEXT[ownerRowPos] = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
   atomicAdd(&ctr->explicitPairs, 1u);
-}
-
-static constexpr int K4_THREADS = 128;
-static constexpr int K4_CH = 15;        // staged entries per thread and round
-static constexpr int K4_STRIDE = 17;    // odd stride: conflict-free smem both ways
-
-template <bool WRITE_ROWS>
-__global__ void __launch_bounds__(K4_THREADS)
-k_neighbors(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
-            float* __restrict__ dd, Counters* ctr) {
-  // staged entries: three planes (row word, partner id, float32 d2 bits) of one array, so an
-  // accept is three stores off ONE running pointer
-  constexpr uint32_t PLANE = (K4_THREADS / 32) * 32 * K4_STRIDE;
-  __shared__ uint32_t sStage[3 * PLANE];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* const myW = &sStage[warp * 32 * K4_STRIDE + lane * K4_STRIDE];
-  uint32_t* const sId = &sStage[PLANE + warp * 32 * K4_STRIDE];
-  const float* const sD2 = reinterpret_cast<const float*>(&sStage[2 * PLANE + warp * 32 * K4_STRIDE]);
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t A = cellStart[g.cells];
-  const uint32_t M = g.M;
-  const bool live = e < A;
-  float2 q = make_float2(0.f, 0.f);
-  float vr = 0.f;
-  uint32_t id = 0, edge = CX_EDGE;
-  int4 win = make_int4(1, 0, 1, 0);
-  if (live) {
-    const float4 me = s.CXY[e];
-    q = make_float2(me.x, me.y);
-    vr = me.z; id = __float_as_uint(me.w) & ~CX_EDGE; edge = __float_as_uint(me.w) & CX_EDGE;
-    win = s.WIN[e];
-  }
-  bool done = !(live && M > 0 && win.x <= win.y);
-  const double myX = q.x, myY = q.y;
-  const double vrSq = dmul((double)vr, (double)vr);
-  const float vrSqF = vr * vr * 1.00001f;            // pre-filter threshold (NaN/Inf compare false)
-  const uint32_t vrBits = __float_as_uint(vr);
-  int32_t myCol = 0, myRow = 0;
-  if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
-  uint32_t n = 0;
-  int32_t row = win.x;
-  uint32_t t = 0, b = 0;
-  if (!done) {
-    t = cellStart[(uint32_t)row * g.cols + win.z];
-    b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-  }
-  do {
-    // ---- phase 1: scan -----------------------------------------------------------------------
-    uint32_t* sp = myW;                                   // next free staged entry
-    bool anySlow = false;
-    uint32_t room = done ? 0u : min((uint32_t)K4_CH, M - n);   // stage size and the cap (:264)
-    while (room) {
-      if (t >= b) {
-        if (++row > win.y) { done = true; break; }
-        t = cellStart[(uint32_t)row * g.cols + win.z];
-        b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-        continue;
-      }
-      // four candidate records in flight (consecutive slots), then decide one by one
-      const uint32_t m = min(4u, b - t);
-      float4 cand[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) cand[u] = __ldg(s.CXY + min(t + (uint32_t)u, b - 1));
-      uint32_t used = m;
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if ((uint32_t)u >= used) break;
-        const float4 c = cand[u];
-        const float fx = c.x - q.x, fy = c.y - q.y;
-        if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;   // certainly d2 >= vr2
-        const double dX = dsub((double)c.x, myX);           // :252-254
-        const double dY = dsub((double)c.y, myY);
-        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
-        // Would the partner's own scan accept me (ignoring its cap)?  Same visualRange and both
-        // centre cells inside the grid: yes (see k_slot_prep).  Anything else: phase 2 looks
-        // (flagged in the top bit of the staged id).
-        const uint32_t jw = __float_as_uint(c.w);
-        const uint32_t jid = jw & ~CX_EDGE;
-        const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
-        sp[0] = (t + (uint32_t)u) | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
-        sp[PLANE] = sure ? jid : (jid | CX_EDGE);
-        sp[2 * PLANE] = __float_as_uint(fround(d2));
-        sp++;
-        anySlow |= !sure;
-        if (--room == 0) used = (uint32_t)u + 1;
-      }
-      t += used;
-    }
-    const uint32_t cnt = (uint32_t)(sp - myW);
-    const uint32_t first = n;                             // row position of my first staged entry
-    n += cnt;
-    if (n >= M) done = true;
-    // ---- phase 2: staged entries whose partner differs in visualRange or sits on the rim ---------
-    if (anySlow) {
-      for (uint32_t k = 0; k < cnt; k++) {
-        const uint32_t jraw = myW[PLANE + k];
-        if (!(jraw & CX_EDGE)) continue;
-        myW[PLANE + k] = jraw & ~CX_EDGE;
-        const uint32_t wd = myW[k];
-        const uint32_t tc = wd & NS_SLOT_MASK;
-        const float4 c = s.CXY[tc];
-        const int4 wt = s.WIN[tc];
-        // An empty window is stored as r0 = 1 > r1 = 0, which no cell satisfies.
-        bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
-        if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
-          const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-          const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-          back = d2 < dmul((double)c.z, (double)c.z);
-        }
-        if (back) myW[k] = wd | NS_BACK;
-        // pair (id, jid) is in P but the partner cannot infer it from its own row
-        else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
-      }
-    }
-    __syncwarp();
-    // ---- warp-cooperative flush -------------------------------------------------------------
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
-    for (uint32_t k = 0; k < kmax; k++)
-      if (k < cnt) {
-        const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
-        s.NST[ix] = myW[k];
-        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)sId[lane * K4_STRIDE + k]); __stcs(dd + ix, sD2[lane * K4_STRIDE + k]); }   // :259-260
-      }
-    __syncwarp();
-  } while (__any_sync(0xffffffffu, !done));
-  if (!live) return;
-  // capped row: my row may be missing partners; K4b finds the lower-id ones
-  if (n >= M && M > 0) {
-    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
-    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
-    ctr->anyCapped = 1;
-    s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
-  }
-  s.NCNT[e] = n;
-  row_tail_fill(g, s, e, n);
 }
 
 // ---- K4, second form: survivor queue + converged exact pass ------------------------------------
@@ -626,7 +524,9 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
   const float2* __restrict__ QXY = s.QXY;
-  uint32_t n = 0;
+  uint32_t n = 0;                                    // entries of the internal row so far (the first M are the API row)
+  uint32_t lastApi = SLOT_NONE;                      // slot of the M-th entry once the row is capped
+  bool xover = false;
   int32_t row = win.x;
   uint32_t t = 0, b = 0;
   if (!done) {
@@ -672,13 +572,18 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
       const uint32_t jw = __float_as_uint(c.w);
       const uint32_t jid = jw & ~CX_EDGE;
+      // Past the cap (:264 ends the reference's scan) the scan goes on for the physics only: a LOWER-id
+      // candidate my predicate accepts may list me in ITS row, and that pair is in P although my capped
+      // row lost it.  Those entries follow the API row in the internal one (positions >= maxNeighbors).
+      if (n + cnt >= M && jid > id) continue;
+      if (n + cnt >= g.Mint) { xover = true; done = true; break; }     // internal row full: the sweeps rescan (rare)
       const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
       myW[cnt] = tc | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
       myW[PLANE + cnt] = sure ? jid : (jid | CX_EDGE);
       myW[2 * PLANE + cnt] = __float_as_uint(fround(d2));
       cnt++;
       anySlow |= !sure;
-      if (n + cnt >= M) { done = true; break; }           // :264
+      if (n + cnt == M) lastApi = tc;                     // the row is full: everything my scan accepts up to this slot is in it
     }
     const uint32_t first = n;                             // row position of my first staged entry
     n += cnt;
@@ -690,15 +595,8 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
         myW[PLANE + k] = jraw & ~CX_EDGE;
         const uint32_t wd = myW[k];
         const uint32_t tc = wd & NS_SLOT_MASK;
-        const float4 c = s.CXY[tc];
-        const int4 wt = s.WIN[tc];
-        bool back = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
-        if (back && __float_as_uint(c.z) != vrBits) {       // d2 is bitwise symmetric and d2 > 0 holds
-          const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-          const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-          back = d2 < dmul((double)c.z, (double)c.z);
-        }
-        if (back) myW[k] = wd | NS_BACK;
+        if (scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) myW[k] = wd | NS_BACK;
+        // pair (id, jid) is in P but the partner cannot infer it from its own row
         else if (wd & NS_OUT) explicit_push(s, ctr, tc, (first + k) * g.Npad + e);
       }
     }
@@ -709,20 +607,12 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       if (k < cnt) {
         const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
         s.NST[ix] = myW[k];
-        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
+        if (WRITE_ROWS && first + k < M) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
       }
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (!live) return;
-  // capped row: my row may be missing partners; K4b finds the lower-id ones
-  if (n >= M && M > 0) {
-    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
-    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
-    ctr->anyCapped = 1;
-    s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
-  }
-  s.NCNT[e] = n;
-  row_tail_fill(g, s, e, n);
+  row_finish(g, s, ctr, e, n, lastApi, xover);
 }
 
 // ---- K4 (wide variant): one WARP per entity -------------------------------------------------------
@@ -749,11 +639,14 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
   const float vrSqF = vr * vr * 1.00001f;
   int32_t myCol, myRow;
   cell_of(g, q.x, q.y, myCol, myRow);
-  uint32_t n = 0;
-  for (int32_t row = win.x; row <= win.y && n < M && M > 0; row++) {
+  uint32_t n = 0;                                   // entries of the internal row (the first M are the API row)
+  uint32_t lastApi = SLOT_NONE;
+  bool xover = false;
+  const uint32_t below = (1u << lane) - 1u;
+  for (int32_t row = win.x; row <= win.y && M > 0 && !xover; row++) {
     const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
     const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-    for (uint32_t t0 = a; t0 < b && n < M; t0 += 32) {
+    for (uint32_t t0 = a; t0 < b && !xover; t0 += 32) {
       const uint32_t t = t0 + lane;
       bool acc = false;
       double d2 = 0;
@@ -766,118 +659,38 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
           acc = d2 < vrSq && d2 > 0;                                              // :257, :249
         }
       }
+      uint4 pw = make_uint4(0, 0, 0, 0);
+      if (acc) pw = s.PW[t];
       const uint32_t bits = __ballot_sync(0xffffffffu, acc);
-      const uint32_t pos = n + __popc(bits & ((1u << lane) - 1));
-      if (acc && pos < M) {
-        const uint4 pw = s.PW[t];
+      // the API row takes the accepted candidates while it has room (:264); past the cap the scan goes on
+      // for the physics: lower-id candidates may list this entity in THEIR rows (see k_neighbors2)
+      const bool isApi = acc && n + (uint32_t)__popc(bits & below) < M;
+      const uint32_t apiBits = __ballot_sync(0xffffffffu, isApi);
+      const uint32_t napi = (uint32_t)__popc(apiBits);
+      const bool isBey = acc && !isApi && pw.y < id;
+      const uint32_t beyBits = __ballot_sync(0xffffffffu, isBey);
+      const uint32_t pos = isApi ? n + (uint32_t)__popc(apiBits & below) : n + napi + (uint32_t)__popc(beyBits & below);
+      if ((isApi || isBey) && pos < g.Mint) {
         const float vrT = __uint_as_float(pw.x);
         bool back = (uint32_t)myRow >= (pw.z & 0xFFFFu) && (uint32_t)myRow <= (pw.z >> 16) &&
                     (uint32_t)myCol >= (pw.w & 0xFFFFu) && (uint32_t)myCol <= (pw.w >> 16);
         if (back && vrT != vr) back = d2 < dmul((double)vrT, (double)vrT);
         const bool out = pw.y > id;
         s.NST[(size_t)pos * g.Npad + e] = t | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
-        if (WRITE_ROWS) {
-          nd[(size_t)pos * g.Npad + e] = (int32_t)pw.y;  // :259
-          dd[(size_t)pos * g.Npad + e] = fround(d2);     // :260
-        }
-        if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
-      }
-      n = min(M, n + (uint32_t)__popc(bits));           // :264
-    }
-  }
-  if (lane == 0) {
-    if (n >= M && M > 0) {
-      reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
-      reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
-      ctr->anyCapped = 1;
-      s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
-    }
-    s.NCNT[e] = n;
-    row_tail_fill(g, s, e, n);
-  }
-}
-
-// is slot `key` listed in the (ascending) internal row of entity k?  returns position or -1
-__device__ __forceinline__ int row_find(const GridDims& g, const BySlot& s, uint32_t k, uint32_t key) {
-  int lo = 0, hi = (int)s.NCNT[k] - 1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1;
-    const uint32_t v = s.NST[(size_t)mid * g.Npad + k] & NS_SLOT_MASK;
-    if (v == key) return mid;
-    if (v < key) lo = mid + 1; else hi = mid - 1;
-  }
-  return -1;
-}
-
-// ---- K4b: capped rows (rare) -----------------------------------------------------------------
-// A capped row may have lost lower-id partners that do list this entity.  One WARP per capped
-// entity rescans its window past the cap in DESCENDING slot order (lane 0 = highest slot) and
-// links every lower-id partner whose own row contains the entity in front of its explicit
-// list, so the list comes out ascending.  Only this warp touches this entity's list during
-// the kernel (other pushes happened in K4), so the links are plain stores.
-static constexpr int K4B_BLOCKS = 148 * 4;
-__global__ void __launch_bounds__(256)
-k_capped_rescan(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
-  const uint32_t nCapped = ctr->nCapped;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nCapped; w += warpsTotal) {
-    const uint32_t e = s.CAPLIST[w];
-    const uint32_t cnt = s.NCNT[e];
-    if (cnt == 0) continue;
-    const uint32_t lastSlot = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
-    const float2 q = s.QXY[e];
-    const float4 hi = s.SA[2 * (size_t)e + 1];
-    const float vr = hi.z;
-    const uint32_t id = __float_as_uint(hi.w);
-    const double vrSq = dmul((double)vr, (double)vr);
-    int32_t myCol, myRow;
-    cell_of(g, q.x, q.y, myCol, myRow);
-    const int4 win = s.WIN[e];
-    uint32_t head = s.XHEAD[e];
-    const bool wasEmpty = head == 0;
-    bool finished = false;
-    for (int32_t row = win.y; row >= win.x && !finished; row--) {
-      const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
-      const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-      for (uint32_t top = b; top > a && !finished; top = top > 32 ? top - 32 : 0) {
-        const bool inRange = top > lane && top - 1 - lane >= a;
-        const uint32_t t = inRange ? top - 1 - lane : 0;
-        const bool beyond = inRange && t > lastSlot;          // everything <= lastSlot is in my row
-        if (__ballot_sync(0xffffffffu, inRange && !beyond)) finished = true;
-        int pos = -1;
-        if (beyond) {
-          const float4 ht = s.SA[2 * (size_t)t + 1];
-          if (__float_as_uint(ht.w) < id) {                   // higher ids: my own pair, lost to the cap
-            const float2 c = s.QXY[t];
-            const double dX = dsub((double)c.x, (double)q.x), dY = dsub((double)c.y, (double)q.y);
-            const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-            if (d2 < vrSq && d2 > 0) {                        // else it does not see... I do not see it: it pushed the pair itself
-              const int4 wt = s.WIN[t];
-              if (d2 < dmul((double)ht.z, (double)ht.z) && myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w)
-                pos = row_find(g, s, t, e);
-            }
+        if (isApi) {
+          if (WRITE_ROWS) {
+            nd[(size_t)pos * g.Npad + e] = (int32_t)pw.y;  // :259
+            dd[(size_t)pos * g.Npad + e] = fround(d2);     // :260
           }
-        }
-        const uint32_t hits = __ballot_sync(0xffffffffu, pos >= 0);
-        if (hits) {
-          const uint32_t node = pos >= 0 ? (uint32_t)pos * g.Npad + t : 0;   // the partner's row position of me
-          // lane order = descending slot: the first hit links to the old head, each next one to
-          // the previous hit, the last one becomes the new head
-          const uint32_t before = hits & ((1u << lane) - 1);
-          const int prevLane = before ? 31 - __clz(before) : -1;
-          const uint32_t prevNode = __shfl_sync(0xffffffffu, node, prevLane < 0 ? 0 : prevLane);
-          if (pos >= 0) s.XNEXT[node] = prevLane < 0 ? head : prevNode + 1u;
-          head = __shfl_sync(0xffffffffu, node, 31 - __clz(hits)) + 1u;
-          if (lane == 0) atomicAdd(&ctr->explicitPairs, (uint32_t)__popc(hits));
+          if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
         }
       }
-    }
-    if (lane == 0) {
-      s.XHEAD[e] = head;
-      if (wasEmpty && head != 0) reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_XSORTED;
+      if (n < M && n + napi == M) lastApi = t0 + (uint32_t)(31 - __clz((int)apiBits));   // the slot that closes the row
+      n += napi + (uint32_t)__popc(beyBits);
+      if (n > g.Mint) { n = g.Mint; xover = true; }
     }
   }
+  if (lane == 0) row_finish(g, s, ctr, e, n, lastApi, xover);
 }
 
 // ---- K4c: put every explicit list in ascending source-slot order (adaptive insertion) ---------
@@ -888,7 +701,6 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
   if (e >= cellStart[g.cells]) return;
   uint32_t p = s.XHEAD[e];
   if (p == 0 || s.XNEXT[p - 1] == 0) return;
-  if (__float_as_uint(s.SA[2 * (size_t)e].w) & F_XSORTED) return;   // built in order by K4b
   uint32_t head = 0, tail = 0, tailKey = 0;
   while (p != 0) {
     const uint32_t nxt = s.XNEXT[p - 1];
@@ -918,11 +730,14 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
 // each one exactly like the reference's `x[i] += ...` on a Float32Array.
 //
 // Pair membership (P = {(i,j): i<j, j in row(i), both active colliders}), seen from entity e:
-//   - row entry with NS_OUT (partner id higher): the pair is mine.
+//   - row entry with NS_OUT (partner id higher, always inside my API row): the pair is mine.
 //   - partner k with lower id: the pair exists iff I am in row(k).
 //       k sees me, I do not see k      -> k pushed the pair on my explicit list in K4
-//       mutual, k in my row            -> NS_BACK; if k's row is capped, binary-search it for me
-//       mutual, k cut from my capped row -> found by K4b's uncapped rescan, on my explicit list
+//       mutual                         -> k is in my INTERNAL row (the scan of K4 goes on past the cap
+//                                         for lower ids) with NS_BACK set; a row is the first
+//                                         maxNeighbors candidates its scan accepts in ascending slot
+//                                         order, so if k's row is capped I am in it iff my slot <= LSLOT[k]
+//       my internal row overflowed too -> F_XOVER: the sweep resumes the scan after its last entry
 //
 // Two phases per entity: phase 1 walks the row with a float32 pre-filter of the overlap test
 // (physics_worker.js:455) and stages the few partners that may overlap; phase 2 runs the
@@ -955,118 +770,88 @@ __device__ __forceinline__ void exact_pair(const Params& p, const BySlot& s, uin
   }
 }
 
-// incoming row entry (partner id lower): am I in the partner's row?
-__device__ __forceinline__ bool incoming_in_P(const GridDims& g, const BySlot& s, uint32_t wd, uint32_t ft,
-                                              uint32_t t, uint32_t e) {
-  if (!(wd & NS_BACK)) return false;
-  if (!(ft & F_CAPPED)) return true;
-  return row_find(g, s, t, e) >= 0;
+// am I (slot e) in the row of the entity in slot t, whose scan accepts me?  (ft: its flag word)
+__device__ __forceinline__ bool in_row_of(const BySlot& s, uint32_t ft, uint32_t t, uint32_t e) {
+  return !(ft & F_CAPPED) || e <= s.LSLOT[t];
 }
 
-// slow path: entities with explicit incoming pairs.  The list was sorted by k_sort_lists, so
-// this is a linear merge of two ascending streams (row entries, explicit sources).
+// The lower-id partners past the end of a full internal row (F_XOVER): K4's scan, resumed after the
+// last stored slot.  next() returns their slots in ascending order, SLOT_NONE at the end.
+struct BeyondScan {
+  uint32_t id, vrBits, after, t, b;
+  double myX, myY, vrSq;
+  int32_t myCol, myRow, row;
+  int4 win;
+  __device__ void start(const GridDims& g, const BySlot& s, const uint32_t* __restrict__ cellStart, uint32_t e, uint32_t lastStored) {
+    const float4 me = s.CXY[e];
+    myX = me.x; myY = me.y; vrBits = __float_as_uint(me.z);
+    vrSq = dmul((double)me.z, (double)me.z);
+    id = __float_as_uint(me.w) & ~CX_EDGE;
+    cell_of(g, me.x, me.y, myCol, myRow);
+    win = s.WIN[e];
+    after = lastStored;
+    row = win.x - 1; t = 0; b = 0;
+  }
+  __device__ uint32_t next(const GridDims& g, const BySlot& s, const uint32_t* __restrict__ cellStart) {
+    while (true) {
+      if (t >= b) {
+        if (++row > win.y) return SLOT_NONE;
+        t = max(cellStart[(uint32_t)row * g.cols + win.z], after + 1u);
+        b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+        continue;
+      }
+      const uint32_t tc = t++;
+      const float4 c = s.CXY[tc];
+      if ((__float_as_uint(c.w) & ~CX_EDGE) >= id) continue;            // higher ids: my own pairs, lost to the cap
+      const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+      const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+      if (!(d2 < vrSq && d2 > 0)) continue;
+      if (!scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) continue;
+      return tc;
+    }
+  }
+};
+
+// slow path: entities with explicit incoming pairs (sorted by k_sort_lists) and / or an internal row
+// that overflowed.  A linear merge of ascending streams: the row entries followed by the resumed scan,
+// and the explicit sources.
 __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
-                                          const float4* __restrict__ Gin, uint32_t gs, uint32_t frame,
-                                          uint32_t substep, uint32_t e, float x, float y, float r, uint32_t fw,
-                                          uint32_t cnt, uint32_t head, SubstepAcc& acc) {
+                                          const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
+                                          uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
+                                          uint32_t fw, uint32_t cnt, uint32_t head, SubstepAcc& acc) {
+  const bool xover = (fw & F_XOVER) != 0;
+  BeyondScan bs;
+  if (xover) bs.start(g, s, cellStart, e, cnt ? (s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK) : 0u);
   uint32_t a = 0, pl = head;
-  while (a < cnt || pl != 0) {
-    const uint32_t wa = a < cnt ? s.NST[(size_t)a * g.Npad + e] : 0xFFFFFFFFu;
-    const uint32_t ta = a < cnt ? (wa & NS_SLOT_MASK) : 0xFFFFFFFFu;
-    const uint32_t tb = pl != 0 ? (pl - 1) % g.Npad : 0xFFFFFFFFu;
-    uint32_t t; bool lower;
+  uint32_t wa = 0, ta = SLOT_NONE;           // head of the row / resumed-scan stream
+  bool fromScan = false;
+  auto advance = [&]() {
+    if (a < cnt) { wa = s.NST[(size_t)a * g.Npad + e]; ta = wa & NS_SLOT_MASK; a++; fromScan = false; }
+    else if (xover) { ta = bs.next(g, s, cellStart); wa = ta | NS_BACK; fromScan = true; }
+    else ta = SLOT_NONE;
+  };
+  advance();
+  while (ta != SLOT_NONE || pl != 0) {
+    const uint32_t tb = pl != 0 ? (pl - 1) % g.Npad : SLOT_NONE;
+    uint32_t t; bool lower, viaList;
     if (tb <= ta) {               // explicit incoming: partner is i, I am j
       pl = s.XNEXT[pl - 1];
-      if (ta == tb) a++;
-      t = tb; lower = false;
+      t = tb; lower = false; viaList = true;
+      if (ta == tb) advance();
     } else {
-      a++;
-      t = ta; lower = (wa & NS_OUT) != 0;
-      if (!lower && !incoming_in_P(g, s, wa, __float_as_uint(Gin[(size_t)ta * gs].w), ta, e)) continue;
+      t = ta; lower = (wa & NS_OUT) != 0; viaList = false;
+      const bool back = (wa & NS_BACK) != 0;
+      advance();
+      if (!lower && !back) continue;
     }
-    const float4 gt = Gin[(size_t)t * gs];
+    const float4 gt = Gin[t];
     const uint32_t ft = __float_as_uint(gt.w);
     if ((ft & F_COLLIDER) != F_COLLIDER) continue;                 // :441
+    if (!lower && !viaList && !in_row_of(s, ft, t, e)) continue;
     float xt, yt;
     partner_pos(g, gt, xt, yt);
     if (surely_apart(x, y, r, xt, yt, gt.z)) continue;
     exact_pair(p, s, frame, substep, e, x, y, r, fw, t, xt, yt, gt.z, ft, lower, acc);
-  }
-}
-
-static constexpr int K6_THREADS = 256;
-static constexpr int K6_STAGE = 8;      // staged possible overlaps per thread
-
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(K6_THREADS, 5)
-k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin, uint32_t gs,
-          float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
-          uint32_t substep) {
-  __shared__ uint32_t sStage[K6_STAGE][K6_THREADS];
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cellStart[g.cells]) return;
-  const Params p = *pp;
-  const uint32_t frame = ctr->frame;
-  const float4 gme = Gin[(size_t)e * gs];
-  float2 pxy;
-  if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
-  else pxy = s.PXY[e];
-  float x = gme.x, y = gme.y;
-  const float r = gme.z;
-  const uint32_t fw = __float_as_uint(gme.w);
-  SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
-  if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
-    const uint32_t cnt = s.NCNT[e];
-    const uint32_t xhead = s.XHEAD[e];
-    if (xhead == 0) {
-      uint32_t k = 0;
-      while (k < cnt) {
-        // phase 1: stage the partners that may overlap (4 row words, then 4 gathers in flight)
-        uint32_t nh = 0;
-        for (; k < cnt && nh + 4 <= K6_STAGE; k += 4) {
-          uint32_t wd[4];
-          float4 gt[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) wd[u] = s.NST[(size_t)min(k + (uint32_t)u, cnt - 1) * g.Npad + e];
-#pragma unroll
-          for (int u = 0; u < 4; u++) gt[u] = __ldg(Gin + (size_t)(wd[u] & NS_SLOT_MASK) * gs);
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            if (k + (uint32_t)u >= cnt) break;
-            const uint32_t ft = __float_as_uint(gt[u].w);
-            if ((ft & F_COLLIDER) != F_COLLIDER) continue;        // :441
-            if (!(wd[u] & NS_OUT) && !incoming_in_P(g, s, wd[u], ft, wd[u] & NS_SLOT_MASK, e)) continue;
-            float xt, yt;
-            partner_pos(g, gt[u], xt, yt);
-            if (surely_apart(x, y, r, xt, yt, gt[u].z)) continue;
-            sStage[nh++][threadIdx.x] = wd[u];
-          }
-        }
-        // phase 2: exact pair code, in row order
-        for (uint32_t h = 0; h < nh; h++) {
-          const uint32_t wd = sStage[h][threadIdx.x];
-          const uint32_t t = wd & NS_SLOT_MASK;
-          const float4 gt = Gin[(size_t)t * gs];
-          float xt, yt;
-          partner_pos(g, gt, xt, yt);
-          exact_pair(p, s, frame, substep, e, x, y, r, fw, t, xt, yt, gt.z, __float_as_uint(gt.w), (wd & NS_OUT) != 0, acc);
-        }
-      }
-    } else {
-      substep_slow(g, p, s, Gin, gs, frame, substep, e, x, y, r, fw, cnt, xhead, acc);
-    }
-  }
-  const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
-  if (LAST) {
-    float4* o = reinterpret_cast<float4*>(s.OUT + e);
-    o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
-    o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
-  } else {
-    // boundary pass of the next sweep on my own result (:344-376)
-    if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
-      apply_bounds(g, p.boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
-    Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
-    s.PXY[e] = pxy;
   }
 }
 
@@ -1081,8 +866,8 @@ k_substep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __r
 //            a pair is +d/dist * h on its own side (negation is exact, so this is bit for bit the
 //            reference's `x[i] += ux` / `x[j] -= ux`, physics_worker.js:519-547); the static /
 //            trigger bookkeeping collapses to "do I move" and "does my partner".
-// A lane whose partner's row is capped (F_CAPPED) still resolves membership with row_find, inside
-// phase 2 and only for entries that passed the float32 test.
+// A lane whose partner's row is capped (F_CAPPED) resolves membership with one comparison against the
+// slot that closes that row (LSLOT), inside phase 2 and only for entries that passed the float32 test.
 __device__ __noinline__ void sweep_pair_coincident(const Params& p, const BySlot& s, uint32_t frame, uint32_t substep,
                                                    uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
                                                    float4 gt, bool lower, SubstepAcc& acc) {
@@ -1146,10 +931,10 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
   const uint32_t fw = __float_as_uint(gme.w);
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
-    const uint32_t cnt = s.NCNT[e];
+    const uint32_t cnt = s.NCNT[e] >> 16;                        // the INTERNAL row: API row + lower-id partners past the cap
     const uint32_t xhead = s.XHEAD[e];
-    if (xhead == 0) {
-      // row entry k lives at NST[k * Npad + e]; Npad * Mpad < 2^32 (weed_create), so 32-bit indices
+    if (xhead == 0 && !(fw & F_XOVER)) {
+      // row entry k lives at NST[k * Npad + e]; Npad * Mint < 2^32 (weed_create), so 32-bit indices
       const uint32_t* __restrict__ NST = s.NST;
       const uint32_t Npad = g.Npad;
       const double strength = pp->responseStrength;
@@ -1192,12 +977,12 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
           const uint32_t t = wd & NS_SLOT_MASK;
           const float4 gt = __ldg(slot_rec(Gin, t));
           const bool lower = (wd & NS_OUT) != 0;
-          if (!lower && (__float_as_uint(gt.w) & F_CAPPED) && row_find(g, s, t, e) < 0) continue;
+          if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
           sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
         }
       }
     } else {
-      substep_slow(g, *pp, s, Gin, 1u, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+      substep_slow(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
@@ -1286,8 +1071,8 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   const bool collider = live && (fw & F_COLLIDER) == F_COLLIDER;     // :430
   uint32_t cnt = 0, xhead = 0;
-  if (collider) { cnt = s.NCNT[e]; xhead = s.XHEAD[e]; }
-  const bool slow = xhead != 0;
+  if (collider) { cnt = s.NCNT[e] >> 16; xhead = s.XHEAD[e]; }
+  const bool slow = xhead != 0 || (collider && (fw & F_XOVER));
   const uint32_t walk = slow ? 0u : cnt;                     // rows walked here; explicit lists take substep_slow
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, walk);
   if ((tid & 31) == 0) sMax[tid >> 5] = wmax;
@@ -1338,7 +1123,7 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
         float4 gt;
         if (TILED) gt = tG[tile_pos(tm, t)]; else gt = __ldg(Gin + t);
         const bool lower = (wd & NS_OUT) != 0;
-        if (!lower && (__float_as_uint(gt.w) & F_CAPPED) && row_find(g, s, t, e) < 0) continue;
+        if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
         sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
       }
       if (k0 + K6T_GROUP >= blockMax) break;
@@ -1362,7 +1147,7 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
   };
   if (tiled) walk_rows(std::true_type{}); else walk_rows(std::false_type{});
   if (!live) return;
-  if (slow) substep_slow(g, *pp, s, Gin, 1u, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+  if (slow) substep_slow(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
   if (LAST) {
     float4* o = reinterpret_cast<float4*>(s.OUT + e);
@@ -1470,7 +1255,7 @@ k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   const float4 gme = Glast[(size_t)slot * gs];
   float x = gme.x, y = gme.y;
   const uint32_t fw = __float_as_uint(gme.w);
-  const uint32_t cnt = s.NCNT[slot];
+  const uint32_t cnt = s.NCNT[slot] & 0xFFFFu;                    // outgoing pairs live in the API row
   const uint32_t frame = ctr->frame;
   for (uint32_t k = 0; k < cnt && base < g.maxPairs; k++) {
     const uint32_t wd = s.NST[(size_t)k * g.Npad + slot];
@@ -2029,7 +1814,7 @@ k_rows_gather(RowView rows, uint32_t first, uint32_t count, uint32_t hostStride,
   const uint32_t i = first + w;
   const uint32_t slot = rows.slotOf[i];
   if (slot == SLOT_NONE) return;
-  const int32_t cnt = (int32_t)rows.ncnt[slot];
+  const int32_t cnt = (int32_t)(rows.ncnt[slot] & 0xFFFFu);
   const size_t o = (size_t)i * hostStride;
   if (lane == 0) { mnd[o] = cnt; mdd[o] = (float)cnt; }                         // :274-275
   for (int32_t k = (int32_t)lane; k < cnt; k += 32) { mnd[o + 1 + k] = rows.id(slot, k); mdd[o + 1 + k] = rows.d2(slot, k); }
@@ -2041,7 +1826,7 @@ k_stats(GridDims g, const uint32_t* __restrict__ NCNT, const uint32_t* __restric
   const uint32_t A = cellStart[g.cells];
   unsigned long long sum = 0; uint32_t capped = 0;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < A; e += gridDim.x * blockDim.x) {
-    const uint32_t n = NCNT[e];
+    const uint32_t n = NCNT[e] & 0xFFFFu;
     sum += n; capped += (n >= g.M);
   }
   for (int o = 16; o; o >>= 1) {

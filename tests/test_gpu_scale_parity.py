@@ -68,14 +68,24 @@ def test_config2_full_size_bit_exact():
     assert st["neighborsTotal"] > 0
 
 
-@pytest.mark.parametrize("flags", [B.FLAG_K4_V1 | B.FLAG_K6_V1, B.FLAG_K6_TILE], ids=["round1-forms", "tma-tiles"])
-def test_other_kernel_forms_are_bit_identical_at_scale(flags):
-    """The first-generation kernels and the TMA-tiled sweep stay in the library for A/B measurements:
-    they must produce the oracle's bits too (300 k entities, clusters: capped rows, explicit lists,
-    multi-group rows in the tiled sweep, tiles that straddle grid rows)."""
+def test_tiled_sweep_is_bit_identical_at_scale():
+    """The TMA-tiled sweep stays in the library for A/B measurements: it must produce the oracle's bits
+    too (300 k entities, clusters: capped rows, explicit lists, multi-group rows, tiles that straddle
+    grid rows)."""
     cfg, cols = scenes.scaled("config4", 300_000)
     cfg["physics"]["maxCollisionPairs"] = 1_500_000
-    run_and_compare(cfg, cols, 3, flags=flags)
+    run_and_compare(cfg, cols, 3, flags=B.FLAG_K6_TILE)
+
+
+def test_collapsed_bed_every_row_capped():
+    """The state the balls scenes settle into: far more than maxNeighbors candidates in range of everybody.
+    Every row is capped, most entities have lower-id partners past their cap (the extended internal rows)
+    and the densest ones more than those hold (F_XOVER: the sweep resumes the scan).  Small cap, dense
+    start, a few frames: state, rows and pairs against the oracle."""
+    cfg, cols = scenes.balls_synthetic(60_000, (640.0, 640.0), 16.0, 12, 2, (2.0, 5.0), 16.0, seed=5)
+    cfg["physics"]["maxCollisionPairs"] = 3_000_000
+    st = run_and_compare(cfg, cols, 4)
+    assert st["cappedRows"] > 50_000
 
 
 def test_tiled_sweep_with_four_substeps():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B measurement of kernel generations on one GPU (diagnostic; not part of bench.py).
 
-For every variant (a combination of WEED_FLAG_K4_V1 / WEED_FLAG_K6_V1 / WEED_FLAG_K6_TILE) the same seeded scene is
+For every variant (WEED_FLAG_K6_TILE or not; experimental builds through --lib) the same seeded scene is
 run for --warmup + --frames frames with per-span CUDA-event timing (WEED_FLAG_KERNEL_TIMING);
 the mean span times over the timed frames are printed, together with a hash of the final state,
 of collisionData and of a sample of API rows, so that a variant that is faster but different is
@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--entities", type=int, default=None)
     ap.add_argument("--frames", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--variants", default="22,11", help="comma list of <K4 form><K6 form>: 1 = round 1, 2 = current, T = TMA tiles (K6 only), e.g. 22,2T,11")
+    ap.add_argument("--variants", default="22", help="comma list of <K4 form><K6 form>: 2 = current, T = TMA tiles (K6 only), e.g. 22,2T (the round-1 forms were retired with the cap-path redesign; their numbers are in profiles/README.md)")
     ap.add_argument("--rows", type=int, default=200_000, help="API rows hashed per sample block (3 blocks)")
     ap.add_argument("--no-rows", action="store_true", help="WEED_FLAG_NO_NEIGHBOR_ROWS: what the scan costs without the API rows")
     ap.add_argument("--lib", default=None, help="tag of an experimental build (tools/build_variant.sh) to load instead of the product library")
@@ -51,8 +51,8 @@ def main():
     results = []
     for v in args.variants.split(","):
         flags = B.FLAG_KERNEL_TIMING
-        flags |= {"1": B.FLAG_K4_V1, "2": 0}[v[0]]
-        flags |= {"1": B.FLAG_K6_V1, "2": 0, "T": B.FLAG_K6_TILE}[v[1]]
+        flags |= {"2": 0}[v[0]]
+        flags |= {"2": 0, "T": B.FLAG_K6_TILE}[v[1]]
         if args.no_rows:
             flags |= B.FLAG_NO_NEIGHBOR_ROWS
         eng = GameEngine(cfg, flags=flags, host_neighbor_rows=False)
