@@ -399,6 +399,8 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mint);
+  g.xpoolRows = (uint32_t)std::max<size_t>(256, N / 32);     // 64 bytes per entity
+  A(ctx->s.XPID, N); A(ctx->s.XR, (size_t)g.xpoolRows * XPOOL_ROW); A(ctx->s.XRCNT, g.xpoolRows);
   A(ctx->s.XNEXT, (size_t)g.Npad * g.Mpad);
   ctx->rowWords = (size_t)g.Npad * g.Mpad;
   if (!(cfg->flags & WEED_FLAG_NO_NEIGHBOR_ROWS)) { A(ctx->nd, ctx->rowWords); A(ctx->dd, ctx->rowWords); }
@@ -592,6 +594,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
     else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   }
   TIME_MARK(ctx, timing, 5);
+  k_beyond_cap<<<blocks_for(g.N, 128), 128, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
@@ -665,7 +668,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -749,7 +752,7 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
     if (rc) return rc;
   }
   const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
-  ctx->launchesPerStep = 13 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
   rc = launch_spatial(ctx, true, false, waitUp, early ? ctx->evBuilt : nullptr);
   if (rc) return rc;
   if (early) {
@@ -856,9 +859,10 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 13 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 14 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
+  out->ms[9] = (float)c.xoverRows;         // a count, not a time: capped rows whose lost partners overflowed the internal row
   return WEED_OK;
 }
 

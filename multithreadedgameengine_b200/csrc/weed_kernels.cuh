@@ -91,7 +91,8 @@ __global__ void k_spatial_begin(Counters* ctr) {
   if (threadIdx.x == 0) {
     ctr->epoch++;
     ctr->anyCapped = 0;
-    ctr->nCapped = 0;
+    ctr->xoverRows = 0;
+    ctr->xpoolUsed = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
     ctr->tBegin = global_timer_ns();
@@ -234,6 +235,9 @@ struct BySlot {
   OutRec* OUT;       // last-substep result
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
   uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
+  uint32_t* XPID;    // F_XPOOL: which row of the overflow pool continues this entity's internal row
+  uint32_t* XR;      // overflow pool: XPOOL_ROW words per pool row (entity-major: one entity's words are consecutive)
+  uint32_t* XRCNT;   // entries in each pool row
   TileDesc* TD;      // one descriptor per TILE slots (k_slot_prep), or nullptr when no tiled kernel runs
 };
 
@@ -330,7 +334,7 @@ k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afte
   if (s.SLID) s.SLID[slot] = i;
   uint32_t keep = 0;
   if (afterSpatial) {        // rows of this frame already exist: keep the cap flag, and the
-    keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & (F_CAPPED | F_XOVER);   // query position stays the pre-move one
+    keep = __float_as_uint(s.SA[2 * (size_t)slot].w) & (F_CAPPED | F_XOVER | F_XPOOL);   // query position stays the pre-move one
     // no k_slot_prep follows on this path: the first sweep's boundary pass happens here
     if (INTEGRATE && moved && !clear_of_walls(g, dp.x, dp.y, at.y)) apply_bounds(g, p.boundaryElasticity, at.y, dp.x, dp.y, dp.z, dp.w);
   }
@@ -454,16 +458,13 @@ __device__ __forceinline__ bool scan_accepts(const GridDims& g, const BySlot& s,
 // flags, padding of the internal row.  A capped row is "everything the scan accepts up to LSLOT", so
 // `am I in the row of the capped entity t` is one comparison: my slot <= LSLOT[t].
 __device__ __forceinline__ void row_finish(const GridDims& g, const BySlot& s, Counters* ctr, uint32_t e, uint32_t n,
-                                           uint32_t lastApi, bool xover) {
-  const uint32_t api = min(n, g.M);
-  uint32_t add = 0;
-  if (api >= g.M && g.M > 0) { add |= F_CAPPED; ctr->anyCapped = 1; }
-  if (xover) add |= F_XOVER;
-  if (add) {
-    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
-    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+                                           uint32_t lastApi) {
+  if (n >= g.M && g.M > 0) {
+    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
+    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
+    ctr->anyCapped = 1;
   }
-  s.NCNT[e] = api | (n << 16);
+  s.NCNT[e] = n | (n << 16);          // k_beyond_cap extends the internal part of a capped row
   s.LSLOT[e] = lastApi;
   row_tail_fill(g, s, e, n);
 }
@@ -524,9 +525,8 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
   int32_t myCol = 0, myRow = 0;
   if (live) cell_of(g, q.x, q.y, myCol, myRow);      // my clamped cell (for partners' windows)
   const float2* __restrict__ QXY = s.QXY;
-  uint32_t n = 0;                                    // entries of the internal row so far (the first M are the API row)
+  uint32_t n = 0;
   uint32_t lastApi = SLOT_NONE;                      // slot of the M-th entry once the row is capped
-  bool xover = false;
   int32_t row = win.x;
   uint32_t t = 0, b = 0;
   if (!done) {
@@ -572,18 +572,13 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       if (!(d2 < vrSq && d2 > 0)) continue;               // :257 (d2 > 0 also skips myself, :249)
       const uint32_t jw = __float_as_uint(c.w);
       const uint32_t jid = jw & ~CX_EDGE;
-      // Past the cap (:264 ends the reference's scan) the scan goes on for the physics only: a LOWER-id
-      // candidate my predicate accepts may list me in ITS row, and that pair is in P although my capped
-      // row lost it.  Those entries follow the API row in the internal one (positions >= maxNeighbors).
-      if (n + cnt >= M && jid > id) continue;
-      if (n + cnt >= g.Mint) { xover = true; done = true; break; }     // internal row full: the sweeps rescan (rare)
       const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
       myW[cnt] = tc | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
       myW[PLANE + cnt] = sure ? jid : (jid | CX_EDGE);
       myW[2 * PLANE + cnt] = __float_as_uint(fround(d2));
       cnt++;
       anySlow |= !sure;
-      if (n + cnt == M) lastApi = tc;                     // the row is full: everything my scan accepts up to this slot is in it
+      if (n + cnt >= M) { lastApi = tc; done = true; break; }   // :264 — the row is full: everything my scan accepts up to this slot is in it
     }
     const uint32_t first = n;                             // row position of my first staged entry
     n += cnt;
@@ -607,12 +602,12 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       if (k < cnt) {
         const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
         s.NST[ix] = myW[k];
-        if (WRITE_ROWS && first + k < M) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
+        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
       }
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (!live) return;
-  row_finish(g, s, ctr, e, n, lastApi, xover);
+  row_finish(g, s, ctr, e, n, lastApi);
 }
 
 // ---- K4 (wide variant): one WARP per entity -------------------------------------------------------
@@ -639,14 +634,12 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
   const float vrSqF = vr * vr * 1.00001f;
   int32_t myCol, myRow;
   cell_of(g, q.x, q.y, myCol, myRow);
-  uint32_t n = 0;                                   // entries of the internal row (the first M are the API row)
+  uint32_t n = 0;
   uint32_t lastApi = SLOT_NONE;
-  bool xover = false;
-  const uint32_t below = (1u << lane) - 1u;
-  for (int32_t row = win.x; row <= win.y && M > 0 && !xover; row++) {
+  for (int32_t row = win.x; row <= win.y && n < M && M > 0; row++) {
     const uint32_t a = cellStart[(uint32_t)row * g.cols + win.z];
     const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-    for (uint32_t t0 = a; t0 < b && !xover; t0 += 32) {
+    for (uint32_t t0 = a; t0 < b && n < M; t0 += 32) {
       const uint32_t t = t0 + lane;
       bool acc = false;
       double d2 = 0;
@@ -659,38 +652,110 @@ k_neighbors_wide(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, i
           acc = d2 < vrSq && d2 > 0;                                              // :257, :249
         }
       }
-      uint4 pw = make_uint4(0, 0, 0, 0);
-      if (acc) pw = s.PW[t];
       const uint32_t bits = __ballot_sync(0xffffffffu, acc);
-      // the API row takes the accepted candidates while it has room (:264); past the cap the scan goes on
-      // for the physics: lower-id candidates may list this entity in THEIR rows (see k_neighbors2)
-      const bool isApi = acc && n + (uint32_t)__popc(bits & below) < M;
-      const uint32_t apiBits = __ballot_sync(0xffffffffu, isApi);
-      const uint32_t napi = (uint32_t)__popc(apiBits);
-      const bool isBey = acc && !isApi && pw.y < id;
-      const uint32_t beyBits = __ballot_sync(0xffffffffu, isBey);
-      const uint32_t pos = isApi ? n + (uint32_t)__popc(apiBits & below) : n + napi + (uint32_t)__popc(beyBits & below);
-      if ((isApi || isBey) && pos < g.Mint) {
+      const uint32_t pos = n + __popc(bits & ((1u << lane) - 1));
+      const bool take = acc && pos < M;
+      if (take) {
+        const uint4 pw = s.PW[t];
         const float vrT = __uint_as_float(pw.x);
         bool back = (uint32_t)myRow >= (pw.z & 0xFFFFu) && (uint32_t)myRow <= (pw.z >> 16) &&
                     (uint32_t)myCol >= (pw.w & 0xFFFFu) && (uint32_t)myCol <= (pw.w >> 16);
         if (back && vrT != vr) back = d2 < dmul((double)vrT, (double)vrT);
         const bool out = pw.y > id;
         s.NST[(size_t)pos * g.Npad + e] = t | (out ? NS_OUT : 0u) | (back ? NS_BACK : 0u);
-        if (isApi) {
-          if (WRITE_ROWS) {
-            nd[(size_t)pos * g.Npad + e] = (int32_t)pw.y;  // :259
-            dd[(size_t)pos * g.Npad + e] = fround(d2);     // :260
-          }
-          if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
+        if (WRITE_ROWS) {
+          nd[(size_t)pos * g.Npad + e] = (int32_t)pw.y;  // :259
+          dd[(size_t)pos * g.Npad + e] = fround(d2);     // :260
         }
+        if (out && !back) explicit_push(s, ctr, t, pos * g.Npad + e);
       }
-      if (n < M && n + napi == M) lastApi = t0 + (uint32_t)(31 - __clz((int)apiBits));   // the slot that closes the row
-      n += napi + (uint32_t)__popc(beyBits);
-      if (n > g.Mint) { n = g.Mint; xover = true; }
+      const uint32_t taken = __ballot_sync(0xffffffffu, take);
+      n += (uint32_t)__popc(taken);                     // :264
+      if (n >= M) lastApi = t0 + (uint32_t)(31 - __clz((int)taken));   // the slot that closes the row
     }
   }
-  if (lane == 0) row_finish(g, s, ctr, e, n, lastApi, xover);
+  if (lane == 0) row_finish(g, s, ctr, e, n, lastApi);
+}
+
+static constexpr uint32_t XPOOL_ROW = 512;   // entries of one overflow-pool row
+
+// ---- K4b: lower-id partners past the cap ---------------------------------------------------------------
+// A capped row may have lost LOWER-id partners that do list this entity in THEIR rows: those pairs are in
+// P, and the entity has to apply them.  Once every row and every LSLOT is known, each capped entity
+// resumes its scan after the slot that closed its row and appends what qualifies — lower id, mutual
+// acceptance, and my slot inside the partner's row: not capped, or my slot <= its LSLOT — to its
+// INTERNAL row (positions maxNeighbors .. Mint - 1), in scan order, membership already decided.  The
+// few entities a whole pile lists early in its scans ("popular" ones: hundreds of such partners) continue
+// in a row of the overflow pool (F_XPOOL: XPOOL_ROW more entries, drawn with one atomic); past that, or
+// with the pool exhausted, the entity is marked F_XOVER and the sweeps resume the scan themselves.
+// (Round 1 did this with one warp per capped entity and a binary search of the partner's row per
+// candidate: 0.3 ms for 55 k capped rows, 149 ms for the 4 M capped rows of a settled bed.)
+__global__ void __launch_bounds__(128)
+k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
+  if (!ctr->anyCapped) return;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cellStart[g.cells]) return;
+  const uint32_t last = s.LSLOT[e];
+  if (last == SLOT_NONE) return;                       // row not capped: nothing was lost
+  const float4 me = s.CXY[e];
+  const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE;
+  const uint32_t vrBits = __float_as_uint(me.z);
+  const double myX = me.x, myY = me.y, vrSq = dmul((double)me.z, (double)me.z);
+  const float vrSqF = me.z * me.z * 1.00001f;
+  int32_t myCol, myRow;
+  cell_of(g, me.x, me.y, myCol, myRow);
+  const int4 win = s.WIN[e];
+  uint32_t n = g.M;                                   // entries of the internal row
+  uint32_t pid = SLOT_NONE, m = 0;                    // overflow-pool row and its entries
+  bool xover = false;
+  for (int32_t row = win.x; row <= win.y && !xover; row++) {
+    uint32_t t = max(cellStart[(uint32_t)row * g.cols + win.z], last + 1u);
+    const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+    for (; t < b && !xover; t += 4) {
+      float4 c[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) c[u] = __ldg(s.CXY + min(t + (uint32_t)u, b - 1));
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t tc = t + (uint32_t)u;
+        if (tc >= b) break;
+        const uint32_t jid = __float_as_uint(c[u].w) & ~CX_EDGE;
+        if (jid >= id) continue;                       // higher ids past my cap: my own pairs, lost as in the reference
+        const float fx = c[u].x - me.x, fy = c[u].y - me.y;
+        if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;
+        const double dX = dsub((double)c[u].x, myX), dY = dsub((double)c[u].y, myY);
+        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+        if (!(d2 < vrSq && d2 > 0)) continue;
+        const uint32_t lk = s.LSLOT[tc];
+        if (lk != SLOT_NONE && e > lk) continue;       // its row closed before it reached me
+        if (!scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) continue;
+        if (n < g.Mint) { s.NST[n * g.Npad + e] = tc | NS_BACK; n++; continue; }
+        if (pid == SLOT_NONE) {                        // internal row full: continue in the overflow pool
+          pid = atomicAdd(&ctr->xpoolUsed, 1u);
+          if (pid >= g.xpoolRows) { pid = SLOT_NONE; xover = true; break; }
+        }
+        if (m >= XPOOL_ROW) { xover = true; break; }
+        s.XR[(size_t)pid * XPOOL_ROW + m] = tc | NS_BACK;
+        m++;
+      }
+    }
+  }
+  uint32_t add = xover ? F_XOVER : 0u;
+  if (pid != SLOT_NONE) {
+    add |= F_XPOOL;
+    s.XPID[e] = pid;
+    s.XRCNT[pid] = m;
+    for (uint32_t k = m; k < ((m + 3u) & ~3u); k++) s.XR[(size_t)pid * XPOOL_ROW + k] = e;   // padding: no membership bit
+  }
+  if (add) {
+    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
+    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+    if (xover) atomicAdd(&ctr->xoverRows, 1u);
+  }
+  if (n > g.M) {
+    s.NCNT[e] = g.M | (n << 16);
+    row_tail_fill(g, s, e, n);
+  }
 }
 
 // ---- K4c: put every explicit list in ascending source-slot order (adaptive insertion) ---------
@@ -733,8 +798,8 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
 //   - row entry with NS_OUT (partner id higher, always inside my API row): the pair is mine.
 //   - partner k with lower id: the pair exists iff I am in row(k).
 //       k sees me, I do not see k      -> k pushed the pair on my explicit list in K4
-//       mutual                         -> k is in my INTERNAL row (the scan of K4 goes on past the cap
-//                                         for lower ids) with NS_BACK set; a row is the first
+//       mutual                         -> k is in my INTERNAL row (k_beyond_cap appends the lower ids my
+//                                         capped row lost) with NS_BACK set; a row is the first
 //                                         maxNeighbors candidates its scan accepts in ascending slot
 //                                         order, so if k's row is capped I am in it iff my slot <= LSLOT[k]
 //       my internal row overflowed too -> F_XOVER: the sweep resumes the scan after its last entry
@@ -812,22 +877,27 @@ struct BeyondScan {
   }
 };
 
-// slow path: entities with explicit incoming pairs (sorted by k_sort_lists) and / or an internal row
-// that overflowed.  A linear merge of ascending streams: the row entries followed by the resumed scan,
-// and the explicit sources.
+// slow path: entities with explicit incoming pairs (sorted by k_sort_lists).  A linear merge of ascending
+// streams: the row entries, then the overflow-pool row, then the resumed scan — and the explicit sources.
 __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
                                           const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
                                           uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
                                           uint32_t fw, uint32_t cnt, uint32_t head, SubstepAcc& acc) {
   const bool xover = (fw & F_XOVER) != 0;
+  const uint32_t* pool = nullptr;
+  uint32_t pcnt = 0;
+  if (fw & F_XPOOL) { const uint32_t pid = s.XPID[e]; pool = s.XR + (size_t)pid * XPOOL_ROW; pcnt = s.XRCNT[pid]; }
+  uint32_t lastStored = 0;
+  if (pcnt) lastStored = pool[pcnt - 1] & NS_SLOT_MASK;
+  else if (cnt) lastStored = s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK;
   BeyondScan bs;
-  if (xover) bs.start(g, s, cellStart, e, cnt ? (s.NST[(size_t)(cnt - 1) * g.Npad + e] & NS_SLOT_MASK) : 0u);
-  uint32_t a = 0, pl = head;
-  uint32_t wa = 0, ta = SLOT_NONE;           // head of the row / resumed-scan stream
-  bool fromScan = false;
+  if (xover) bs.start(g, s, cellStart, e, lastStored);
+  uint32_t a = 0, pa = 0, pl = head;
+  uint32_t wa = 0, ta = SLOT_NONE;           // head of the row / pool / resumed-scan stream
   auto advance = [&]() {
-    if (a < cnt) { wa = s.NST[(size_t)a * g.Npad + e]; ta = wa & NS_SLOT_MASK; a++; fromScan = false; }
-    else if (xover) { ta = bs.next(g, s, cellStart); wa = ta | NS_BACK; fromScan = true; }
+    if (a < cnt) { wa = s.NST[(size_t)a * g.Npad + e]; ta = wa & NS_SLOT_MASK; a++; }
+    else if (pa < pcnt) { wa = pool[pa++]; ta = wa & NS_SLOT_MASK; }
+    else if (xover) { ta = bs.next(g, s, cellStart); wa = ta | NS_BACK; }
     else ta = SLOT_NONE;
   };
   advance();
@@ -852,6 +922,22 @@ __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, co
     partner_pos(g, gt, xt, yt);
     if (surely_apart(x, y, r, xt, yt, gt.z)) continue;
     exact_pair(p, s, frame, substep, e, x, y, r, fw, t, xt, yt, gt.z, ft, lower, acc);
+  }
+}
+
+// F_XOVER without an explicit list: the partners past everything that was stored, straight from the scan
+__device__ __noinline__ void sweep_resumed_scan(const GridDims& g, const Params& p, const BySlot& s,
+                                                const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
+                                                uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
+                                                uint32_t fw, uint32_t lastStored, SubstepAcc& acc) {
+  BeyondScan bs;
+  bs.start(g, s, cellStart, e, lastStored);
+  for (uint32_t t = bs.next(g, s, cellStart); t != SLOT_NONE; t = bs.next(g, s, cellStart)) {
+    const float4 gt = Gin[t];
+    const uint32_t ft = __float_as_uint(gt.w);
+    if ((ft & F_COLLIDER) != F_COLLIDER || !in_row_of(s, ft, t, e)) continue;
+    if (surely_apart(x, y, r, gt.x, gt.y, gt.z)) continue;
+    exact_pair(p, s, frame, substep, e, x, y, r, fw, t, gt.x, gt.y, gt.z, ft, false, acc);
   }
 }
 
@@ -933,53 +1019,64 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e] >> 16;                        // the INTERNAL row: API row + lower-id partners past the cap
     const uint32_t xhead = s.XHEAD[e];
-    if (xhead == 0 && !(fw & F_XOVER)) {
-      // row entry k lives at NST[k * Npad + e]; Npad * Mint < 2^32 (weed_create), so 32-bit indices
-      const uint32_t* __restrict__ NST = s.NST;
-      const uint32_t Npad = g.Npad;
+    if (xhead == 0) {
       const double strength = pp->responseStrength;
-      for (uint32_t kb = 0; kb < cnt; kb += 64) {
-        const uint32_t ke = min(cnt, kb + 64u);
-        // ---- phase 1: one bit per row entry that may overlap --------------------------------------
-        unsigned long long mask = 0;
-        uint32_t idx = kb * Npad + e;
-        // the spatial pass pads every row to a multiple of four entries with words that carry no
-        // membership bit (row_tail_fill), so a batch never needs a bounds test
-        uint32_t nx[4];
+      // Walks `n` row words rp[0], rp[stride], ...: the internal row (slot-major: stride Npad; Npad * Mint
+      // < 2^32, so 32-bit indices) or a row of the overflow pool (stride 1).  Rows are padded to a multiple
+      // of four entries with words that carry no membership bit, so a batch never needs a bounds test.
+      auto walk = [&](const uint32_t* __restrict__ rp, uint32_t stride, uint32_t n) {
+        for (uint32_t kb = 0; kb < n; kb += 64) {
+          const uint32_t ke = min(n, kb + 64u);
+          // ---- phase 1: one bit per row entry that may overlap --------------------------------------
+          unsigned long long mask = 0;
+          uint32_t idx = kb * stride;
+          uint32_t nx[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) nx[u] = NST[idx + (uint32_t)u * Npad];
-        for (uint32_t k = kb; k < ke; k += 4, idx += 4 * Npad) {
-          uint32_t wd[4];
-          float4 gt[4];
+          for (int u = 0; u < 4; u++) nx[u] = rp[idx + (uint32_t)u * stride];
+          for (uint32_t k = kb; k < ke; k += 4, idx += 4 * stride) {
+            uint32_t wd[4];
+            float4 gt[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) wd[u] = nx[u];
-          if (k + 4 < ke) {
+            for (int u = 0; u < 4; u++) wd[u] = nx[u];
+            if (k + 4 < ke) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) nx[u] = NST[idx + (uint32_t)(4 + u) * Npad];     // the next batch's words, in flight behind the gathers
+              for (int u = 0; u < 4; u++) nx[u] = rp[idx + (uint32_t)(4 + u) * stride];     // the next batch's words, in flight behind the gathers
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) gt[u] = __ldg(slot_rec(Gin, wd[u] & NS_SLOT_MASK));
+            uint32_t nib = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const uint32_t ft = __float_as_uint(gt[u].w);
+              const bool apart = surely_apart(x, y, r, gt[u].x, gt[u].y, gt[u].z);
+              const bool cand = ((ft & F_COLLIDER) == F_COLLIDER) & (wd[u] >= NS_OUT) & !apart;   // :441; OUT or BACK set
+              nib |= cand ? (1u << u) : 0u;
+            }
+            mask |= (unsigned long long)nib << (k - kb);
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++) gt[u] = __ldg(slot_rec(Gin, wd[u] & NS_SLOT_MASK));
-          uint32_t nib = 0;
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t ft = __float_as_uint(gt[u].w);
-            const bool apart = surely_apart(x, y, r, gt[u].x, gt[u].y, gt[u].z);
-            const bool cand = ((ft & F_COLLIDER) == F_COLLIDER) & (wd[u] >= NS_OUT) & !apart;   // :441; OUT or BACK set
-            nib |= cand ? (1u << u) : 0u;
+          // ---- phase 2: exact pair code on the marked entries, in row order --------------------------
+          while (mask) {
+            const uint32_t k = kb + (uint32_t)__ffsll((long long)mask) - 1u;
+            mask &= mask - 1;
+            const uint32_t wd = rp[k * stride];
+            const uint32_t t = wd & NS_SLOT_MASK;
+            const float4 gt = __ldg(slot_rec(Gin, t));
+            const bool lower = (wd & NS_OUT) != 0;
+            if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
+            sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
           }
-          mask |= (unsigned long long)nib << (k - kb);
         }
-        // ---- phase 2: exact pair code on the marked entries, in row order --------------------------
-        while (mask) {
-          const uint32_t k = kb + (uint32_t)__ffsll((long long)mask) - 1u;
-          mask &= mask - 1;
-          const uint32_t wd = NST[k * Npad + e];
-          const uint32_t t = wd & NS_SLOT_MASK;
-          const float4 gt = __ldg(slot_rec(Gin, t));
-          const bool lower = (wd & NS_OUT) != 0;
-          if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
-          sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
+      };
+      walk(s.NST + e, g.Npad, cnt);
+      if (fw & (F_XPOOL | F_XOVER)) {                              // a "popular" entity of a dense pile
+        uint32_t lastStored = cnt ? (s.NST[(cnt - 1) * g.Npad + e] & NS_SLOT_MASK) : 0u;
+        if (fw & F_XPOOL) {
+          const uint32_t pid = s.XPID[e], pcnt = s.XRCNT[pid];
+          const uint32_t* pool = s.XR + (size_t)pid * XPOOL_ROW;
+          walk(pool, 1u, pcnt);
+          if (pcnt) lastStored = pool[pcnt - 1] & NS_SLOT_MASK;
         }
+        if (fw & F_XOVER) sweep_resumed_scan(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, lastStored, acc);
       }
     } else {
       substep_slow(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
@@ -1072,7 +1169,7 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
   const bool collider = live && (fw & F_COLLIDER) == F_COLLIDER;     // :430
   uint32_t cnt = 0, xhead = 0;
   if (collider) { cnt = s.NCNT[e] >> 16; xhead = s.XHEAD[e]; }
-  const bool slow = xhead != 0 || (collider && (fw & F_XOVER));
+  const bool slow = xhead != 0 || (collider && (fw & (F_XOVER | F_XPOOL)));
   const uint32_t walk = slow ? 0u : cnt;                     // rows walked here; explicit lists take substep_slow
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, walk);
   if ((tid & 31) == 0) sMax[tid >> 5] = wmax;

@@ -96,7 +96,7 @@ def main():
                "K6_ms_per_sweep": round(float(ms[6]) / S, 4), "sum_ms": round(float(ms.sum()), 4),
                "device_frame_ms": round(dev / args.frames, 4),
                "kbar": st["neighborsTotal"] / max(1, st["activeInGrid"]), "capped_rows": st["cappedRows"],
-               "explicit_pairs": st["explicitPairs"], "collision_pairs": st["collisionPairs"],
+               "explicit_pairs": st["explicitPairs"], "xover_rows": int(st["ms"][9]), "collision_pairs": st["collisionPairs"],
                "state_hash": state_hash, "rows_hash": hr.hexdigest()[:16]}
         print(json.dumps(res), flush=True)
         results.append(res)
