@@ -42,7 +42,7 @@ TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r2_ncu_config4_16M_su
 }
 
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids+k_slot_rank", "k_build_slots+k_slot_prep", "k_neighbors2",
-                "k_capped_rescan+k_sort_lists", "k_sweep", "k_writeback+k_pair_scan+k_pair_emit"]
+                "k_beyond_cap+k_sort_lists", "k_sweep", "k_writeback+k_pair_scan+k_pair_emit"]
 # algorithmic bytes per active entity of each timed span (SURVEY 8 d); spans without compulsory
 # traffic of their own (the cap path, the pair log) can never be the "dominant kernel" of the roofline line
 def span_bytes(kbar):

@@ -396,7 +396,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N); A(ctx->s.CAPLIST, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mint);
   g.xpoolRows = (uint32_t)std::max<size_t>(256, N / 32);     // 64 bytes per entity
@@ -594,7 +594,8 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
     else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   }
   TIME_MARK(ctx, timing, 5);
-  k_beyond_cap<<<blocks_for(g.N, 128), 128, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  k_beyond_cap<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);            // few capped rows: a warp each
+  k_beyond_cap_dense<<<148 * 16, 128, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);  // many: a thread each (one of the two returns at once)
   k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
@@ -668,7 +669,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 15 + (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -752,7 +753,7 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
     if (rc) return rc;
   }
   const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
-  ctx->launchesPerStep = 14 + (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 15 + (uint32_t)ctx->phys.subStepCount;
   rc = launch_spatial(ctx, true, false, waitUp, early ? ctx->evBuilt : nullptr);
   if (rc) return rc;
   if (early) {
@@ -859,7 +860,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 14 + (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 15 + (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
   out->ms[9] = (float)c.xoverRows;         // a count, not a time: capped rows whose lost partners overflowed the internal row

@@ -93,6 +93,7 @@ __global__ void k_spatial_begin(Counters* ctr) {
     ctr->anyCapped = 0;
     ctr->xoverRows = 0;
     ctr->xpoolUsed = 0;
+    ctr->nCapped = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
     ctr->tBegin = global_timer_ns();
@@ -235,6 +236,7 @@ struct BySlot {
   OutRec* OUT;       // last-substep result
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
   uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
+  uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
   uint32_t* XPID;    // F_XPOOL: which row of the overflow pool continues this entity's internal row
   uint32_t* XR;      // overflow pool: XPOOL_ROW words per pool row (entity-major: one entity's words are consecutive)
   uint32_t* XRCNT;   // entries in each pool row
@@ -463,6 +465,7 @@ __device__ __forceinline__ void row_finish(const GridDims& g, const BySlot& s, C
     reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= F_CAPPED;
     reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
     ctr->anyCapped = 1;
+    s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
   }
   s.NCNT[e] = n | (n << 16);          // k_beyond_cap extends the internal part of a capped row
   s.LSLOT[e] = lastApi;
@@ -690,13 +693,102 @@ static constexpr uint32_t XPOOL_ROW = 512;   // entries of one overflow-pool row
 // with the pool exhausted, the entity is marked F_XOVER and the sweeps resume the scan themselves.
 // (Round 1 did this with one warp per capped entity and a binary search of the partner's row per
 // candidate: 0.3 ms for 55 k capped rows, 149 ms for the 4 M capped rows of a settled bed.)
-__global__ void __launch_bounds__(128)
+// Two forms, chosen on the device by how many rows are capped.  Few (the piles on the walls of the opening
+// frames): one WARP per capped entity from the list row_finish built, 32 candidates per step, ordered
+// ballot compaction — the handful of entities with hundreds of candidates left do not become a tail.
+// Many (a settled bed: most rows capped, some dozens of candidates left each): one THREAD per entity,
+// which keeps every lane busy.  Measured at 16M: 55 k capped rows 0.33 (thread) / 0.14 ms (warp);
+// 3.9 M capped rows 17.7 (thread) / 27.9 ms (warp).
+__device__ __forceinline__ bool beyond_dense_regime(uint32_t nCapped, uint32_t A) { return (unsigned long long)nCapped * 8ull > A; }
+static constexpr int K4B_BLOCKS = 148 * 8;
+__global__ void __launch_bounds__(256)
 k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
-  if (!ctr->anyCapped) return;
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cellStart[g.cells]) return;
+  const uint32_t nCapped = ctr->nCapped;
+  if (beyond_dense_regime(nCapped, cellStart[g.cells])) return;      // k_beyond_cap_dense takes this frame
+  const uint32_t lane = threadIdx.x & 31, below = (1u << lane) - 1u;
+  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nCapped; w += warpsTotal) {
+    const uint32_t e = s.CAPLIST[w];
+    const uint32_t last = s.LSLOT[e];
+    const float4 me = s.CXY[e];
+    const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE;
+    const uint32_t vrBits = __float_as_uint(me.z);
+    const double myX = me.x, myY = me.y, vrSq = dmul((double)me.z, (double)me.z);
+    const float vrSqF = me.z * me.z * 1.00001f;
+    int32_t myCol, myRow;
+    cell_of(g, me.x, me.y, myCol, myRow);
+    const int4 win = s.WIN[e];
+    uint32_t n = g.M;                                   // entries of the internal row + the pool row
+    uint32_t pid = SLOT_NONE;
+    const uint32_t room = g.Mint + XPOOL_ROW;
+    bool xover = false;
+    for (int32_t row = win.x; row <= win.y && !xover; row++) {
+      const uint32_t a = max(cellStart[(uint32_t)row * g.cols + win.z], last + 1u);
+      const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+      for (uint32_t t0 = a; t0 < b && !xover; t0 += 32) {
+        const uint32_t tc = t0 + lane;
+        bool ok = false;
+        if (tc < b) {
+          const float4 c = __ldg(s.CXY + tc);
+          const float fx = c.x - me.x, fy = c.y - me.y;
+          // lower ids only (higher ids past my cap are my own pairs, lost as in the reference)
+          if ((__float_as_uint(c.w) & ~CX_EDGE) < id && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF)) {
+            const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+            const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+            if (d2 < vrSq && d2 > 0) {
+              const uint32_t lk = s.LSLOT[tc];
+              // not capped, or its row closed after it reached me — and its scan accepts me
+              ok = (lk == SLOT_NONE || e <= lk) && scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits);
+            }
+          }
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (!bits) continue;
+        const uint32_t cntNew = (uint32_t)__popc(bits);
+        if (n + cntNew > g.Mint && pid == SLOT_NONE) {   // the internal row is full: continue in the overflow pool
+          if (lane == 0) pid = atomicAdd(&ctr->xpoolUsed, 1u);
+          pid = __shfl_sync(0xffffffffu, pid, 0);
+          if (pid >= g.xpoolRows) { pid = SLOT_NONE; xover = true; }
+        }
+        const uint32_t pos = n + (uint32_t)__popc(bits & below);
+        if (ok) {
+          if (pos < g.Mint) s.NST[pos * g.Npad + e] = tc | NS_BACK;
+          else if (pid != SLOT_NONE && pos < room) s.XR[(size_t)pid * XPOOL_ROW + (pos - g.Mint)] = tc | NS_BACK;
+        }
+        n += cntNew;
+        if (n > room || (n > g.Mint && pid == SLOT_NONE)) xover = true;
+      }
+    }
+    if (lane == 0) {
+      const uint32_t inRow = min(n, g.Mint);
+      uint32_t add = xover ? F_XOVER : 0u;
+      if (pid != SLOT_NONE) {
+        const uint32_t m = min(n, room) - g.Mint;
+        add |= F_XPOOL;
+        s.XPID[e] = pid;
+        s.XRCNT[pid] = m;
+        for (uint32_t k = m; k < ((m + 3u) & ~3u); k++) s.XR[(size_t)pid * XPOOL_ROW + k] = e;   // padding: no membership bit
+      }
+      if (add) {
+        reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
+        reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+        if (xover) atomicAdd(&ctr->xoverRows, 1u);
+      }
+      if (inRow > g.M) {
+        s.NCNT[e] = g.M | (inRow << 16);
+        row_tail_fill(g, s, e, inRow);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
+  const uint32_t A = cellStart[g.cells];
+  if (!beyond_dense_regime(ctr->nCapped, A)) return;   // k_beyond_cap took this frame
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < A; e += gridDim.x * blockDim.x) {
   const uint32_t last = s.LSLOT[e];
-  if (last == SLOT_NONE) return;                       // row not capped: nothing was lost
+  if (last == SLOT_NONE) continue;                     // row not capped: nothing was lost
   const float4 me = s.CXY[e];
   const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE;
   const uint32_t vrBits = __float_as_uint(me.z);
@@ -755,6 +847,7 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
   if (n > g.M) {
     s.NCNT[e] = g.M | (n << 16);
     row_tail_fill(g, s, e, n);
+  }
   }
 }
 
