@@ -1,10 +1,13 @@
 // weed_napi.cc — thin Node N-API addon over the C ABI of include/weedgpu.h.
 //
-// NOT compiled in this image (no node, no node_api.h); kept as the reference-side binding a
-// WeedJS maintainer would build with node-gyp:  it contains no logic, only argument
-// marshalling.  The SharedArrayBuffers the engine allocates (src/core/gameEngine.js:534-777)
-// are passed by reference: napi_get_arraybuffer_info yields the base pointer that
-// weed_bind() pins and mirrors on the device.
+// The reference-side binding a WeedJS maintainer builds with node-gyp: no logic, only argument
+// marshalling.  The SharedArrayBuffers the engine allocates (src/core/gameEngine.js:534-777) are
+// passed by reference: napi_get_arraybuffer_info yields the base pointer that weed_bind() pins and
+// mirrors on the device; the addon holds a napi_reference on every bound buffer until the context is
+// destroyed, so the garbage collector cannot free memory the DMA engine still writes.
+// This image has no Node: tests/test_addon.py compiles this file against tests/mock/node_api.h (the
+// declarations of the real header) and drives create -> bind -> step -> fetchNeighbors through a fake
+// napi_env (tests/mock/fake_napi.cc) into libweedgpu.so on the GPU box.
 //
 //   const weed = require('./build/Release/weed_napi.node');
 //   const ctx = weed.create({entityCount, worldWidth, worldHeight, cellSize, maxNeighbors,
@@ -25,6 +28,13 @@
       return nullptr;                                             \
     }                                                             \
   } while (0)
+
+// what the external handed to JavaScript points at
+struct Handle {
+  weed_ctx* ctx;
+  napi_ref bufs[WEED_BUF_COUNT];     // keeps every bound (Shared)ArrayBuffer alive
+  uint32_t maxPairs;
+};
 
 static bool get_double(napi_env env, napi_value obj, const char* key, double* out) {
   napi_value v;
@@ -80,30 +90,49 @@ static napi_value Create(napi_env env, napi_callback_info info) {
   weed_ctx* ctx = nullptr;
   const int rc = weed_create(&cfg, &ctx);
   if (rc != WEED_OK) return throw_weed(env, nullptr, rc);
+  Handle* h = new Handle();
+  h->ctx = ctx;
+  h->maxPairs = cfg.maxCollisionPairs;
+  for (napi_ref& r : h->bufs) r = nullptr;
   napi_value ext;
-  NAPI_OK(napi_create_external(env, ctx, [](napi_env, void* data, void*) { weed_destroy((weed_ctx*)data); }, nullptr, &ext));
+  NAPI_OK(napi_create_external(
+      env, h,
+      [](napi_env e, void* data, void*) {
+        Handle* hh = (Handle*)data;
+        weed_destroy(hh->ctx);                                 // unpins the buffers first ...
+        for (napi_ref r : hh->bufs) if (r) napi_delete_reference(e, r);   // ... then lets them go
+        delete hh;
+      },
+      nullptr, &ext));
   return ext;
 }
 
-static weed_ctx* ctx_of(napi_env env, napi_value v) {
+static Handle* handle_of(napi_env env, napi_value v) {
   void* p = nullptr;
-  napi_get_value_external(env, v, &p);
-  return (weed_ctx*)p;
+  if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_error(env, nullptr, "weed_napi: not a context"); return nullptr; }
+  return (Handle*)p;
 }
+#define CTX_OR_RETURN(h, v)          \
+  Handle* h = handle_of(env, (v));   \
+  if (!h) return nullptr;            \
+  weed_ctx* ctx = h->ctx
 
 // bind(ctx, bufferId, SharedArrayBuffer)
 static napi_value Bind(napi_env env, napi_callback_info info) {
   size_t argc = 3;
   napi_value a[3];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
   int32_t id;
   NAPI_OK(napi_get_value_int32(env, a[1], &id));
+  if (id < 0 || id >= WEED_BUF_COUNT) { napi_throw_error(env, nullptr, "weed_napi: bad buffer id"); return nullptr; }
   void* base = nullptr;
   size_t bytes = 0;
   NAPI_OK(napi_get_arraybuffer_info(env, a[2], &base, &bytes));   // also accepts SharedArrayBuffer (N-API >= 8)
   const int rc = weed_bind(ctx, (weed_buffer_id)id, base, bytes);
   if (rc != WEED_OK) return throw_weed(env, ctx, rc);
+  if (h->bufs[id]) { napi_delete_reference(env, h->bufs[id]); h->bufs[id] = nullptr; }   // rebinding: the old buffer was unpinned by weed_bind
+  NAPI_OK(napi_create_reference(env, a[2], 1, &h->bufs[id]));
   return nullptr;
 }
 
@@ -112,7 +141,8 @@ static napi_value Step(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value a[4];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
   double dt;
   uint32_t up, down;
   NAPI_OK(napi_get_value_double(env, a[1], &dt));
@@ -128,7 +158,8 @@ static napi_value SetPhysics(napi_env env, napi_callback_info info) {
   size_t argc = 2;
   napi_value a[2];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
   weed_physics_config p;
   weed_get_physics(ctx, &p);
   fill_physics(env, a[1], &p);
@@ -142,7 +173,8 @@ static napi_value FetchNeighbors(napi_env env, napi_callback_info info) {
   size_t argc = 3;
   napi_value a[3];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
   uint32_t first, count;
   NAPI_OK(napi_get_value_uint32(env, a[1], &first));
   NAPI_OK(napi_get_value_uint32(env, a[2], &count));
@@ -152,7 +184,10 @@ static napi_value FetchNeighbors(napi_env env, napi_callback_info info) {
 }
 
 // ---- device-side consumers (weed_system_*) --------------------------------------------------
-static void* typed_data(napi_env env, napi_value v) {     // TypedArray -> base pointer (or NULL)
+// TypedArray -> base pointer.  NULL (with *ok still true) when v is not a typed array: the C ABI treats
+// a NULL output as "not wanted".  A typed array of the wrong element type or with fewer than `need`
+// elements is an error (*ok = false, exception pending): native code must never write past it.
+static void* typed_data(napi_env env, napi_value v, napi_typedarray_type want, size_t need, bool* ok) {
   napi_valuetype t;
   if (napi_typeof(env, v, &t) != napi_ok || t != napi_object) return nullptr;
   bool is = false;
@@ -160,6 +195,11 @@ static void* typed_data(napi_env env, napi_value v) {     // TypedArray -> base 
   void* data = nullptr;
   napi_typedarray_type ty; size_t len; napi_value ab; size_t off;
   if (napi_get_typedarray_info(env, v, &ty, &len, &data, &ab, &off) != napi_ok) return nullptr;
+  if (ty != want || len < need) {
+    napi_throw_error(env, nullptr, "weed_napi: typed array of the wrong type or too short");
+    *ok = false;
+    return nullptr;
+  }
   return data;
 }
 
@@ -169,12 +209,16 @@ static napi_value CollisionEvents(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value a[4];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
   bool forget = false;
   if (argc > 3) napi_get_value_bool(env, a[3], &forget);
   weed_collision_event_counts c;
-  const int rc = weed_system_collision_events(ctx, forget ? WEED_EVENTS_FORGET_PREVIOUS : 0u, &c,
-                                              (uint8_t*)typed_data(env, a[1]), (int32_t*)typed_data(env, a[2]));
+  bool ok = true;
+  uint8_t* state = (uint8_t*)typed_data(env, a[1], napi_uint8_array, h->maxPairs, &ok);             // one byte per logged pair
+  int32_t* exits = (int32_t*)typed_data(env, a[2], napi_int32_array, 1 + 2 * (size_t)h->maxPairs, &ok);
+  if (!ok) return nullptr;
+  const int rc = weed_system_collision_events(ctx, forget ? WEED_EVENTS_FORGET_PREVIOUS : 0u, &c, state, exits);
   if (rc != WEED_OK) return throw_weed(env, ctx, rc);
   napi_value out, v;
   NAPI_OK(napi_create_object(env, &out));
@@ -189,14 +233,21 @@ static napi_value ScreenVisibility(napi_env env, napi_callback_info info) {
   size_t argc = 7;
   napi_value a[7];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
-  const float* cam = (const float*)typed_data(env, a[1]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
+  bool ok = true;
+  const float* cam = (const float*)typed_data(env, a[1], napi_float32_array, 3, &ok);
+  if (!ok) return nullptr;
   if (!cam) { napi_throw_error(env, nullptr, "weed_napi: cameraData must be a Float32Array"); return nullptr; }
   weed_camera c{cam[0], cam[1], cam[2], 0, 0};
   NAPI_OK(napi_get_value_double(env, a[2], &c.canvasWidth));
   NAPI_OK(napi_get_value_double(env, a[3], &c.canvasHeight));
-  const int rc = weed_system_screen_visibility(ctx, &c, (float*)typed_data(env, a[4]), (float*)typed_data(env, a[5]),
-                                               (uint8_t*)typed_data(env, a[6]));
+  const uint32_t N = weed_entity_count(ctx);
+  float* sx = (float*)typed_data(env, a[4], napi_float32_array, N, &ok);
+  float* sy = (float*)typed_data(env, a[5], napi_float32_array, N, &ok);
+  uint8_t* on = (uint8_t*)typed_data(env, a[6], napi_uint8_array, N, &ok);
+  if (!ok) return nullptr;
+  const int rc = weed_system_screen_visibility(ctx, &c, sx, sy, on);
   if (rc != WEED_OK) return throw_weed(env, ctx, rc);
   return nullptr;
 }
@@ -206,12 +257,18 @@ static napi_value Spawn(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value a[4];
   NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
-  weed_ctx* ctx = ctx_of(env, a[0]);
+  CTX_OR_RETURN(h, a[0]);
+  (void)h;
   uint32_t pool;
   NAPI_OK(napi_get_value_uint32(env, a[1], &pool));
   napi_typedarray_type ty; size_t len = 0; void* recs = nullptr; napi_value ab; size_t off;
   NAPI_OK(napi_get_typedarray_info(env, a[2], &ty, &len, &recs, &ab, &off));
-  const int rc = weed_pool_spawn(ctx, pool, (const weed_spawn_record*)recs, (uint32_t)(len / 4), (int32_t*)typed_data(env, a[3]));
+  if (ty != napi_float32_array) { napi_throw_error(env, nullptr, "weed_napi: records must be a Float32Array"); return nullptr; }
+  bool ok = true;
+  int32_t* idx = (int32_t*)typed_data(env, a[3], napi_int32_array, len / 4, &ok);      // one index per record
+  if (!ok) return nullptr;
+  if (!idx) { napi_throw_error(env, nullptr, "weed_napi: indices must be an Int32Array"); return nullptr; }
+  const int rc = weed_pool_spawn(ctx, pool, (const weed_spawn_record*)recs, (uint32_t)(len / 4), idx);
   if (rc != WEED_OK) return throw_weed(env, ctx, rc);
   return nullptr;
 }

@@ -211,6 +211,7 @@ int weed_fetch_neighbors(weed_ctx* ctx, uint32_t first, uint32_t count);
 int weed_fetch_neighbors_to(weed_ctx* ctx, uint32_t first, uint32_t count, int32_t* neighbor_out, float* distance_out);
 
 int weed_sync(weed_ctx* ctx);
+uint32_t weed_entity_count(weed_ctx* ctx);   /* entityCount the context was created with */
 int weed_get_stats(weed_ctx* ctx, weed_stats* out);
 const char* weed_last_error(weed_ctx* ctx);   /* ctx may be NULL: last create() failure */
 

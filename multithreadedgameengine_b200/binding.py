@@ -130,6 +130,7 @@ SYMBOLS = {
     "weed_last_error": (C.c_char_p, [C.c_void_p]),
     "weed_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "weed_row_pitch": (C.c_uint32, [C.c_void_p]),
+    "weed_entity_count": (C.c_uint32, [C.c_void_p]),
     "weed_system_boids": (C.c_int, [C.c_void_p, C.POINTER(BoidsParams), C.c_void_p, C.c_double]),
     "weed_system_flock": (C.c_int, [C.c_void_p, C.POINTER(FlockClass), C.c_uint32, C.POINTER(FlockParams), C.c_void_p]),
     "weed_system_collision_events": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CollisionEventCounts), C.c_void_p, C.c_void_p]),

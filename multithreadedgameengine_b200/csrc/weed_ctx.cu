@@ -160,6 +160,7 @@ struct weed_ctx {
   int32_t* mnd = nullptr; float* mdd = nullptr;   // the rows in the reference's layout, filled on demand (k_rows_gather)
   // control
   Params* dParams = nullptr;
+  FrameConst* dFrameConst = nullptr;   // GridDims + BySlot in device memory (slow paths of the sweep)
   Counters* dCtr = nullptr;
   Params hParams{};
   double lastDt = -1;
@@ -413,6 +414,12 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
     ctx->stage[c] = p;
   }
 #undef A
+  if ((rc = dalloc(ctx, &ctx->dFrameConst, 1)) != WEED_OK) return bail(rc);
+  {
+    FrameConst fc{ctx->g, ctx->s};
+    if (cudaMemcpyAsync(ctx->dFrameConst, &fc, sizeof(fc), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "FrameConst upload failed"; return bail(WEED_E_CUDA); }
+  }
   for (auto& e : ctx->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(WEED_E_CUDA); }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "init sync failed"; return bail(WEED_E_CUDA); }
@@ -614,7 +621,7 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
   for (int step = 0; step < S; step++) {
     float4* out = bufs[step & 1];
     const bool first = step == 0, last = step == S - 1;
-#define SWEEP_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step
+#define SWEEP_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step, ctx->dFrameConst
     if (kflags & WEED_FLAG_K6_TILE) {
       const unsigned sb = blocks_for(g.N, TILE);
       if (first && last)       k_sweep_tile<true, true><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
@@ -800,6 +807,8 @@ extern "C" int weed_run(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   GUARD(ctx);
   return run_frames(ctx, dtRatio, frames);
 }
+
+extern "C" uint32_t weed_entity_count(weed_ctx* ctx) { return ctx ? ctx->g.N : 0u; }
 
 extern "C" int weed_sync(weed_ctx* ctx) {
   GUARD(ctx);

@@ -243,6 +243,11 @@ struct BySlot {
   TileDesc* TD;      // one descriptor per TILE slots (k_slot_prep), or nullptr when no tiled kernel runs
 };
 
+// The same two structs in device memory, for the out-of-line slow paths of the sweep: a function that is
+// not inlined takes its arguments by address, and the address of a kernel parameter forces EVERY thread
+// to copy the struct to local memory on entry (measured: 2 GB of extra DRAM writes per sweep at 16M).
+struct FrameConst { GridDims g; BySlot s; };
+
 // stable position: number of ids in my cell smaller than mine (cell lists are ascending in the
 // reference because it inserts i = 0..N-1 in order, spatial_worker.js:146,168).  A kernel of its
 // own: the dependent gathers key -> cellStart -> ids of the cell need occupancy, not registers.
@@ -972,10 +977,13 @@ struct BeyondScan {
 
 // slow path: entities with explicit incoming pairs (sorted by k_sort_lists).  A linear merge of ascending
 // streams: the row entries, then the overflow-pool row, then the resumed scan — and the explicit sources.
-__device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, const BySlot& s,
+__device__ __noinline__ void substep_slow(const FrameConst* __restrict__ fc, const Params* __restrict__ pp,
                                           const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
                                           uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
                                           uint32_t fw, uint32_t cnt, uint32_t head, SubstepAcc& acc) {
+  const GridDims& g = fc->g;
+  const BySlot& s = fc->s;
+  const Params& p = *pp;
   const bool xover = (fw & F_XOVER) != 0;
   const uint32_t* pool = nullptr;
   uint32_t pcnt = 0;
@@ -1019,10 +1027,13 @@ __device__ __noinline__ void substep_slow(const GridDims& g, const Params& p, co
 }
 
 // F_XOVER without an explicit list: the partners past everything that was stored, straight from the scan
-__device__ __noinline__ void sweep_resumed_scan(const GridDims& g, const Params& p, const BySlot& s,
+__device__ __noinline__ void sweep_resumed_scan(const FrameConst* __restrict__ fc, const Params* __restrict__ pp,
                                                 const float4* __restrict__ Gin, const uint32_t* __restrict__ cellStart,
                                                 uint32_t frame, uint32_t substep, uint32_t e, float x, float y, float r,
                                                 uint32_t fw, uint32_t lastStored, SubstepAcc& acc) {
+  const GridDims& g = fc->g;
+  const BySlot& s = fc->s;
+  const Params& p = *pp;
   BeyondScan bs;
   bs.start(g, s, cellStart, e, lastStored);
   for (uint32_t t = bs.next(g, s, cellStart); t != SLOT_NONE; t = bs.next(g, s, cellStart)) {
@@ -1047,13 +1058,13 @@ __device__ __noinline__ void sweep_resumed_scan(const GridDims& g, const Params&
 //            trigger bookkeeping collapses to "do I move" and "does my partner".
 // A lane whose partner's row is capped (F_CAPPED) resolves membership with one comparison against the
 // slot that closes that row (LSLOT), inside phase 2 and only for entries that passed the float32 test.
-__device__ __noinline__ void sweep_pair_coincident(const Params& p, const BySlot& s, uint32_t frame, uint32_t substep,
-                                                   uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
+__device__ __noinline__ void sweep_pair_coincident(const FrameConst* __restrict__ fc, const Params* __restrict__ pp, uint32_t frame,
+                                                   uint32_t substep, uint32_t e, float x, float y, float r, uint32_t fw, uint32_t t,
                                                    float4 gt, bool lower, SubstepAcc& acc) {
-  exact_pair(p, s, frame, substep, e, x, y, r, fw, t, gt.x, gt.y, gt.z, __float_as_uint(gt.w), lower, acc);
+  exact_pair(*pp, fc->s, frame, substep, e, x, y, r, fw, t, gt.x, gt.y, gt.z, __float_as_uint(gt.w), lower, acc);
 }
 
-__device__ __forceinline__ void sweep_pair(const Params* __restrict__ pp, double strength, const BySlot& s,
+__device__ __forceinline__ void sweep_pair(const Params* __restrict__ pp, double strength, const FrameConst* __restrict__ fc,
                                            const Counters* __restrict__ ctr, uint32_t substep, uint32_t e,
                                            float x, float y, float r, uint32_t fw, uint32_t t, float4 gt, bool lower,
                                            SubstepAcc& acc) {
@@ -1063,7 +1074,7 @@ __device__ __forceinline__ void sweep_pair(const Params* __restrict__ pp, double
   const double minDist = dadd((double)r, (double)gt.z);              // :452
   if (dist2 >= dmul(minDist, minDist)) return;                       // :455
   const double dist = __dsqrt_rn(dist2);
-  if (dist == 0) { sweep_pair_coincident(*pp, s, ctr->frame, substep, e, x, y, r, fw, t, gt, lower, acc); return; }   // :460-507
+  if (dist == 0) { sweep_pair_coincident(fc, pp, ctr->frame, substep, e, x, y, r, fw, t, gt, lower, acc); return; }   // :460-507
   const double depth = dsub(minDist, dist);                          // :510
   if (!(depth > 0)) return;
   acc.hits++;                                                        // :551-552
@@ -1099,7 +1110,7 @@ template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(K6V2_THREADS, WEED_K6V2_MINBLOCKS)
 k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
         float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
-        uint32_t substep) {
+        uint32_t substep, const FrameConst* __restrict__ fc) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
   const float4 gme = Gin[e];
@@ -1156,7 +1167,7 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
             const float4 gt = __ldg(slot_rec(Gin, t));
             const bool lower = (wd & NS_OUT) != 0;
             if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
-            sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
+            sweep_pair(pp, strength, fc, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
           }
         }
       };
@@ -1169,10 +1180,10 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
           walk(pool, 1u, pcnt);
           if (pcnt) lastStored = pool[pcnt - 1] & NS_SLOT_MASK;
         }
-        if (fw & F_XOVER) sweep_resumed_scan(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, lastStored, acc);
+        if (fw & F_XOVER) sweep_resumed_scan(fc, pp, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, lastStored, acc);
       }
     } else {
-      substep_slow(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+      substep_slow(fc, pp, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
     }
   }
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
@@ -1213,7 +1224,7 @@ template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(TILE, 8)
 k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
              float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
-             uint32_t substep) {
+             uint32_t substep, const FrameConst* __restrict__ fc) {
   __shared__ __align__(128) float4 tG[K6T_CAP];
   __shared__ __align__(128) uint32_t tRow[K6T_GROUP][TILE];
   __shared__ __align__(8) unsigned long long bars[3];       // 0: partner ranges, 1 / 2: row words, first wave / rest
@@ -1314,7 +1325,7 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
         if (TILED) gt = tG[tile_pos(tm, t)]; else gt = __ldg(Gin + t);
         const bool lower = (wd & NS_OUT) != 0;
         if (!lower && !in_row_of(s, __float_as_uint(gt.w), t, e)) continue;
-        sweep_pair(pp, strength, s, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
+        sweep_pair(pp, strength, fc, ctr, substep, e, x, y, r, fw, t, gt, lower, acc);
       }
       if (k0 + K6T_GROUP >= blockMax) break;
       // ---- next group of rows (dense tiles only) --------------------------------------------------------
@@ -1337,7 +1348,7 @@ k_sweep_tile(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* 
   };
   if (tiled) walk_rows(std::true_type{}); else walk_rows(std::false_type{});
   if (!live) return;
-  if (slow) substep_slow(g, *pp, s, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
+  if (slow) substep_slow(fc, pp, Gin, cellStart, ctr->frame, substep, e, x, y, r, fw, cnt, xhead, acc);
   const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;    // Uint8 wrap (:551-552)
   if (LAST) {
     float4* o = reinterpret_cast<float4*>(s.OUT + e);
