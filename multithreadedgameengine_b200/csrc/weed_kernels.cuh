@@ -489,9 +489,15 @@ __device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, ui
 //            shared-memory queue (a predicated store and an increment: nothing else runs under
 //            divergence).  It ends when the queue is full or the window is exhausted.
 //   phase 2  every lane drains its queue in step with the others: 16-byte candidate record, the
-//            binary64 predicate of spatial_worker.js:252-257, row word / id / float32 d2 staged in
-//            place (accepted <= drained), cap of :264.
-//   then     partners with another visualRange or on the rim (as in k_neighbors), warp flush.
+//            binary64 predicate of spatial_worker.js:252-257, id and float32 d2 straight to the
+//            slot-major API planes, the internal row word staged in place (accepted <= drained),
+//            cap of :264.
+//   then     partners with another visualRange or on the rim resolve their NS_BACK bit, warp flush of
+//            the row words.
+// Measured at 16M (ms): rows scattered by entity id with a staged 16-lane flush 3.33 (round-1 layout);
+// slot-major planes, everything staged 2.19; ids / d2 written directly from phase 2 (8.7 KB of shared
+// memory instead of 26 KB) 1.82; row words written directly as well 1.88; queue of 12 / 8 instead of
+// 16 entries 2.24 / 2.54 (more rounds).
 #ifndef WEED_K4V2_Q
 #define WEED_K4V2_Q 16
 #endif
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(K4V2_THREADS, WEED_K4V2_MINBLOCKS)
 k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32_t* __restrict__ nd,
              float* __restrict__ dd, Counters* ctr) {
   constexpr uint32_t PLANE = (K4V2_THREADS / 32) * 32 * K4V2_STRIDE;
-  __shared__ uint32_t sStage[3 * PLANE];
+  __shared__ uint32_t sStage[PLANE];           // survivor queue, then the accepted row words of the round
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* const myW = &sStage[warp * 32 * K4V2_STRIDE + lane * K4V2_STRIDE];
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,6 +577,7 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
     // ---- phase 2: exact predicate, staged in place -------------------------------------------------
     uint32_t cnt = 0;
     bool anySlow = false;
+    uint32_t slowMask = 0;                               // staged entries whose NS_BACK bit is still open
     for (uint32_t k = 0; k < qn; k++) {
       const uint32_t tc = myW[k];
       const float4 c = __ldg(s.CXY + tc);
@@ -581,9 +588,16 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       const uint32_t jw = __float_as_uint(c.w);
       const uint32_t jid = jw & ~CX_EDGE;
       const bool sure = __float_as_uint(c.z) == vrBits && !((jw | edge) & CX_EDGE);
+      // the API row entry goes straight to its slot-major planes (lanes of a warp sit at similar row
+      // positions, so these stores touch a few lines each); the internal row word is staged, because its
+      // NS_BACK bit may still be open, and leaves with the warp flush below
+      if (WRITE_ROWS) {
+        const uint32_t ix = (n + cnt) * g.Npad + e;
+        __stcs(nd + ix, (int32_t)jid);                     // :259
+        __stcs(dd + ix, fround(d2));                       // :260
+      }
       myW[cnt] = tc | (jid > id ? NS_OUT : 0u) | (sure ? NS_BACK : 0u);
-      myW[PLANE + cnt] = sure ? jid : (jid | CX_EDGE);
-      myW[2 * PLANE + cnt] = __float_as_uint(fround(d2));
+      if (!sure) slowMask |= 1u << cnt;
       cnt++;
       anySlow |= !sure;
       if (n + cnt >= M) { lastApi = tc; done = true; break; }   // :264 — the row is full: everything my scan accepts up to this slot is in it
@@ -593,9 +607,7 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
     // ---- staged entries whose partner differs in visualRange or sits on the rim ---------------------
     if (anySlow) {
       for (uint32_t k = 0; k < cnt; k++) {
-        const uint32_t jraw = myW[PLANE + k];
-        if (!(jraw & CX_EDGE)) continue;
-        myW[PLANE + k] = jraw & ~CX_EDGE;
+        if (!(slowMask >> k & 1u)) continue;
         const uint32_t wd = myW[k];
         const uint32_t tc = wd & NS_SLOT_MASK;
         if (scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) myW[k] = wd | NS_BACK;
@@ -604,14 +616,10 @@ k_neighbors2(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, int32
       }
     }
     __syncwarp();
-    // ---- warp-cooperative flush ---------------------------------------------------------------------
+    // ---- warp flush of the internal row words: lane after lane at the same k -> full lines --------------
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, cnt);
     for (uint32_t k = 0; k < kmax; k++)
-      if (k < cnt) {
-        const uint32_t ix = (first + k) * g.Npad + e;       // slot-major planes: a full line per store
-        s.NST[ix] = myW[k];
-        if (WRITE_ROWS) { __stcs(nd + ix, (int32_t)myW[PLANE + k]); __stcs(dd + ix, __uint_as_float(myW[2 * PLANE + k])); }   // :259-260
-      }
+      if (k < cnt) s.NST[(first + k) * g.Npad + e] = myW[k];
     __syncwarp();
   } while (__any_sync(0xffffffffu, !done));
   if (!live) return;
