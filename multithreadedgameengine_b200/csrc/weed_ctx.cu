@@ -575,7 +575,8 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   TIME_MARK(ctx, timing, 0);
   k_cell_key<<<nb, 256, 0, st>>>(g, ctx->d.DP, ctx->d.F, ctx->key, ctx->rank, ctx->cellCount);
   TIME_MARK(ctx, timing, 1);
-  k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr);
+  k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr,
+                                                       slab_cuts(ctx), (uint32_t)g.cols, g.slabHalo);
   TIME_MARK(ctx, timing, 2);
   k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds, ctx->d.GID);
   k_slot_rank<<<nb, 256, 0, st>>>(g, ctx->d.F, ctx->d.GID, ctx->key, ctx->cellStart, ctx->arrIds, ctx->slotOf);

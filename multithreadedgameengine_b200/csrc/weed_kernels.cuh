@@ -128,7 +128,7 @@ k_cell_key(GridDims g, const float4* __restrict__ DP, const uint8_t* __restrict_
 // ---- K2: exclusive scan of the cell histogram, also clears it for the next frame ---------
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, uint32_t numTiles,
-            unsigned long long* status, Counters* ctr) {
+            unsigned long long* status, Counters* ctr, const int32_t* __restrict__ slabCuts, uint32_t cols, int32_t halo) {
   __shared__ uint32_t s_tile, s_excl, s_warp[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scanTile, 1u);
   __syncthreads();
@@ -137,10 +137,22 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
   constexpr int V = SCAN_ITEMS / 4;
   const size_t i0 = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
   uint4 c[V];                                                  // arrays are padded to whole tiles
+  // a slab only has entities in its own rows + halo: the tiles outside hold zeros, no need to read or clear them
+  bool populated = true;
+  if (slabCuts) {
+    const long long lo = (long long)(slabCuts[0] - halo) * cols, hi = (long long)(slabCuts[1] + halo) * cols;
+    const long long t0 = (long long)tile * SCAN_TILE;
+    populated = t0 + SCAN_TILE > lo && t0 < hi;
+  }
+  if (populated) {
 #pragma unroll
-  for (int v = 0; v < V; v++) c[v] = reinterpret_cast<const uint4*>(cellCount + i0)[v];
+    for (int v = 0; v < V; v++) c[v] = reinterpret_cast<const uint4*>(cellCount + i0)[v];
 #pragma unroll
-  for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellCount + i0)[v] = make_uint4(0, 0, 0, 0);
+    for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellCount + i0)[v] = make_uint4(0, 0, 0, 0);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) c[v] = make_uint4(0, 0, 0, 0);
+  }
   uint32_t tsum = 0, tmax = 0;
 #pragma unroll
   for (int v = 0; v < V; v++) {
@@ -1413,28 +1425,62 @@ k_writeback(GridDims g, ById d, BySlot s, const uint32_t* __restrict__ slotOf, u
   }
 }
 
-// one block: exclusive prefix of the tile counts (a few 10^4 values)
+// one block: exclusive prefix of the tile counts (a few 10^4 values), 4096 at a time: every thread takes
+// four consecutive counts (one 16-byte load, the next chunk's already in flight), the block scans the
+// 1024 partial sums with shuffles, a running carry links the chunks.  (The first version gave every
+// thread a contiguous run of tiles: strided, uncoalesced loads — 0.055 ms at 62 k tiles.)
 __global__ void __launch_bounds__(1024)
 k_pair_scan(const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tilePrefix, uint32_t numTiles,
             uint32_t maxPairs, Counters* ctr, int32_t* __restrict__ coll) {
-  __shared__ uint32_t s_part[1024];
-  const uint32_t per = (numTiles + 1023) / 1024;
-  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, numTiles);
-  uint32_t sum = 0;
-  for (uint32_t t = lo; t < hi; t++) sum += tileCount[t];
-  s_part[threadIdx.x] = sum;
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  auto load4 = [&](uint32_t base) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const uint32_t i = base + threadIdx.x * 4;
+    if (i + 3 < numTiles) v = *reinterpret_cast<const uint4*>(tileCount + i);     // tileCount is cudaMalloc'ed: 16-byte aligned
+    else {
+      if (i < numTiles) v.x = tileCount[i];
+      if (i + 1 < numTiles) v.y = tileCount[i + 1];
+      if (i + 2 < numTiles) v.z = tileCount[i + 2];
+    }
+    return v;
+  };
+  uint4 nxt = load4(0);
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan
-    const uint32_t v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0;
+  for (uint32_t base = 0; base < numTiles; base += 4096) {
+    const uint4 c = nxt;
+    if (base + 4096 < numTiles) nxt = load4(base + 4096);
+    const uint32_t mine = c.x + c.y + c.z + c.w;
+    uint32_t inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    s_part[threadIdx.x] += v;
+    const uint32_t carry = s_carry;
+    uint32_t w = s_warp[lane], winc = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += v;
+    }
+    const uint32_t warpExcl = __shfl_sync(0xffffffffu, winc - w, warp);
+    const uint32_t total = __shfl_sync(0xffffffffu, winc, 31);
+    uint32_t e = carry + warpExcl + (inc - mine);
+    const uint32_t i = base + threadIdx.x * 4;
+    if (i < numTiles) tilePrefix[i] = e;
+    e += c.x; if (i + 1 < numTiles) tilePrefix[i + 1] = e;
+    e += c.y; if (i + 2 < numTiles) tilePrefix[i + 2] = e;
+    e += c.z; if (i + 3 < numTiles) tilePrefix[i + 3] = e;
+    __syncthreads();                               // everybody has read s_carry and s_warp
+    if (threadIdx.x == 0) s_carry = carry + total;
     __syncthreads();
   }
-  uint32_t run = s_part[threadIdx.x] - sum;
-  for (uint32_t t = lo; t < hi; t++) { tilePrefix[t] = run; run += tileCount[t]; }
-  if (threadIdx.x == 1023) {
-    ctr->collisionPairs = s_part[1023];
-    if (coll) coll[0] = (int32_t)min(s_part[1023], maxPairs);      // :565-567
+  if (threadIdx.x == 0) {
+    ctr->collisionPairs = s_carry;
+    if (coll) coll[0] = (int32_t)min(s_carry, maxPairs);      // :565-567
   }
 }
 
