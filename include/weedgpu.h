@@ -113,7 +113,9 @@ enum {
                                           (physics-only consumers); rows then unavailable */
   /* measurement aid (tools/ab_kernels.py and the cross-check tests): another form of the collision
    * sweep.  Results are bit-identical whichever form runs.                                    */
-  WEED_FLAG_K6_TILE       = 1u << 10  /* k_sweep_tile (TMA-staged tiles; measured slower)        */
+  WEED_FLAG_K6_TILE       = 1u << 10, /* k_sweep_tile (TMA-staged tiles; measured slower)        */
+  WEED_FLAG_K4_WIDE       = 1u << 12, /* neighbor scan: one warp per entity whatever maxNeighbors */
+  WEED_FLAG_K4_THREAD     = 1u << 13  /* neighbor scan: one thread per entity whatever maxNeighbors */
 };
 
 /* The "init" message: gameEngine.js:1049-1125 (entityCount, config.worldWidth/Height,

@@ -39,6 +39,8 @@ FLAG_NO_GRAPH = 1 << 0
 FLAG_KERNEL_TIMING = 1 << 1
 FLAG_NO_NEIGHBOR_ROWS = 1 << 2
 FLAG_K6_TILE = 1 << 10
+FLAG_K4_WIDE = 1 << 12
+FLAG_K4_THREAD = 1 << 13
 
 DEV_NEIGHBOR, DEV_DISTANCE, DEV_COLLISION, DEV_STATE, DEV_ATTR, DEV_VEL, DEV_NEIGHBOR_COUNT, DEV_SLOT_OF = range(8)
 

@@ -192,7 +192,7 @@ struct weed_ctx {
   std::vector<Pool> pools;
   void* poolStage = nullptr; size_t poolStageBytes = 0;   // device staging for a batch (records / indices)
   uint32_t* poolScalars = nullptr;
-  bool k4Wide = false;        // warp-per-entity neighbor scan (long rows); WEED_K4=wide|thread overrides at create
+  bool k4Wide = false;        // warp-per-entity neighbor scan (long rows: maxNeighbors >= 256; WEED_FLAG_K4_WIDE / _THREAD force one)
   // slabs
   bool slab = false;
   uint32_t* holes = nullptr;
@@ -373,10 +373,7 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   g.Mint = g.Mpad + std::max(16u, std::min(g.Mpad, 128u));   // API row + lower-id partners found past the cap (then F_XOVER)
   g.Npad = ((g.N + TILE - 1) / TILE) * TILE;   // whole tiles: a tile's row words are one aligned bulk copy
   g.maxPairs = cfg->maxCollisionPairs;
-  {
-    const char* k4 = getenv("WEED_K4");   // diagnostic override, read once
-    ctx->k4Wide = k4 ? (strcmp(k4, "wide") == 0) : (cfg->maxNeighbors >= 256);
-  }
+  ctx->k4Wide = (cfg->flags & WEED_FLAG_K4_WIDE) ? true : (cfg->flags & WEED_FLAG_K4_THREAD) ? false : cfg->maxNeighbors >= 256;
   g.slabBegin = 0; g.slabEnd = g.rows; g.slabHalo = 0;
   if (cfg->slabRowEnd > 0) {
     if (cfg->slabRowBegin >= cfg->slabRowEnd || (int32_t)cfg->slabRowEnd > g.rows) { ctx->err = "bad slab rows"; return bail(WEED_E_INVALID); }

@@ -278,8 +278,11 @@ k_slot_rank(GridDims g, const uint8_t* __restrict__ F, const uint32_t* __restric
   slotOf[i] = s0 + r;
 }
 
+#ifndef WEED_BUILD_MINBLOCKS
+#define WEED_BUILD_MINBLOCKS 1
+#endif
 template <bool INTEGRATE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WEED_BUILD_MINBLOCKS)
 k_build_slots(GridDims g, const Params* __restrict__ pp, int subSteps, bool afterSpatial, ById d, BySlot s,
               const uint32_t* __restrict__ key, const uint32_t* __restrict__ cellStart,
               const uint32_t* __restrict__ arrIds, uint32_t* __restrict__ slotOf,

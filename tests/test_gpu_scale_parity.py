@@ -88,6 +88,17 @@ def test_collapsed_bed_every_row_capped():
     assert st["cappedRows"] > 50_000
 
 
+@pytest.mark.parametrize("flags,M,vr", [(B.FLAG_K4_WIDE, 24, 16.0), (B.FLAG_K4_THREAD, 300, 40.0)], ids=["wide-short-rows", "thread-long-rows"])
+def test_both_scan_forms_on_the_other_side_of_their_threshold(flags, M, vr):
+    """The library picks the warp-per-entity scan for maxNeighbors >= 256 and the thread-per-entity one
+    below; forcing each onto the other's ground (capped rows, rows of several hundred entries walked 64 at
+    a time by the sweep, windows of 7 x 7 cells) must not change a bit."""
+    cfg, cols = scenes.balls_synthetic(30_000, (800.0, 800.0), 16.0, M, 2, (2.0, 5.0), vr, seed=17)
+    cfg["physics"]["maxCollisionPairs"] = 2_000_000
+    st = run_and_compare(cfg, cols, 3, flags=flags)
+    assert st["neighborsTotal"] > 0
+
+
 def test_tiled_sweep_with_four_substeps():
     cfg, cols = scenes.scaled("config5", 300_000)            # S = 4: FIRST / middle / LAST instantiations
     run_and_compare(cfg, cols, 2, flags=B.FLAG_K6_TILE)
