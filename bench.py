@@ -443,7 +443,9 @@ def run_ours(args):
 
         # ---- verification of the partitioned run against ONE context (N > 1) ---------------------------------
         verified = None
-        if world > 1 and args.verify:
+        if world > 1 and args.verify and N > 40_000_000:
+            verified = {"ok": None, "skipped": "one context cannot hold this scene (the comparison needs the whole world on rank 0)"}
+        elif world > 1 and args.verify:
             vf = args.verify
             obj_v, eng_v = make()
             frames(obj_v, vf)
@@ -491,7 +493,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak" if name == "config5" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
-                "verified": None if verified is None else verified["ok"],
+                "verified": None if verified is None else verified.get("ok"),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk.summary()}
         print(json.dumps(line))
