@@ -393,8 +393,8 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
-  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N); A(ctx->s.CAPLIST, N);
+  A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); if (ctx->k4Wide) A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N); A(ctx->s.CAPLIST, N); A(ctx->s.SORTLIST, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mint);
   g.xpoolRows = (uint32_t)std::max<size_t>(256, N / 32);     // 64 bytes per entity
@@ -601,7 +601,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   TIME_MARK(ctx, timing, 5);
   k_beyond_cap<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);            // few capped rows: a warp each
   k_beyond_cap_dense<<<148 * 16, 128, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);  // many: a thread each (one of the two returns at once)
-  k_sort_lists<<<nb, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  k_sort_lists<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
   return WEED_OK;

@@ -94,6 +94,7 @@ __global__ void k_spatial_begin(Counters* ctr) {
     ctr->xoverRows = 0;
     ctr->xpoolUsed = 0;
     ctr->nCapped = 0;
+    ctr->nSort = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
     ctr->tBegin = global_timer_ns();
@@ -249,6 +250,7 @@ struct BySlot {
   uint32_t* SLID;    // slab mode: local index of the entity in this slot (nullptr: id = index)
   uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
   uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
+  uint32_t* SORTLIST;// slots that received explicit pairs this frame (unordered)
   uint32_t* XPID;    // F_XPOOL: which row of the overflow pool continues this entity's internal row
   uint32_t* XR;      // overflow pool: XPOOL_ROW words per pool row (entity-major: one entity's words are consecutive)
   uint32_t* XRCNT;   // entries in each pool row
@@ -390,8 +392,9 @@ k_slot_prep(GridDims g, const Params* __restrict__ pp, BySlot s, const uint32_t*
     Window w;
     if (query_window(g, x0, y0, hi.z, w)) wi = make_int4(w.r0, w.r1, w.c0, w.c1);
     s.WIN[e] = wi;
-    s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
-                         (uint32_t)wi.z | ((uint32_t)wi.w << 16));
+    if (s.PW)      // only the warp-per-entity scan gathers this record
+      s.PW[e] = make_uint4(__float_as_uint(hi.z), __float_as_uint(hi.w), (uint32_t)wi.x | ((uint32_t)wi.y << 16),
+                           (uint32_t)wi.z | ((uint32_t)wi.w << 16));
     // CX_EDGE clear: my unclamped centre cell is my (clamped) grid cell and trunc == floor.  Two
     // such entities with the same visualRange that pass 0 < d2 < vr^2 always lie in each other's
     // window: |x_a - x_b| < vr  =>  |floor(x_a inv) - floor(x_b inv)| <= ceil(vr inv).
@@ -493,8 +496,11 @@ __device__ __forceinline__ void row_finish(const GridDims& g, const BySlot& s, C
 }
 
 __device__ __forceinline__ void explicit_push(const BySlot& s, Counters* ctr, uint32_t dstSlot, uint32_t ownerRowPos) {
-  s.XNEXT[ownerRowPos] = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
+  const uint32_t prev = atomicExch(&s.XHEAD[dstSlot], ownerRowPos + 1u);
+  s.XNEXT[ownerRowPos] = prev;
   atomicAdd(&ctr->explicitPairs, 1u);
+  // exactly one pusher finds the list empty: it enters the slot in the list k_sort_lists walks
+  if (prev == 0) s.SORTLIST[atomicAdd(&ctr->nSort, 1u)] = dstSlot;
 }
 
 // ---- K4, second form: survivor queue + converged exact pass ------------------------------------
@@ -882,11 +888,11 @@ k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart,
 // ---- K4c: put every explicit list in ascending source-slot order (adaptive insertion) ---------
 __global__ void __launch_bounds__(256)
 k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr) {
-  if (!ctr->explicitPairs) return;
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cellStart[g.cells]) return;
+  const uint32_t nSort = ctr->nSort;                 // slots that received explicit pairs this frame
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nSort; w += gridDim.x * blockDim.x) {
+  const uint32_t e = s.SORTLIST[w];
   uint32_t p = s.XHEAD[e];
-  if (p == 0 || s.XNEXT[p - 1] == 0) return;
+  if (p == 0 || s.XNEXT[p - 1] == 0) continue;
   uint32_t head = 0, tail = 0, tailKey = 0;
   while (p != 0) {
     const uint32_t nxt = s.XNEXT[p - 1];
@@ -907,6 +913,7 @@ k_sort_lists(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
     p = nxt;
   }
   s.XHEAD[e] = head;
+  }
 }
 
 // ---- K6: one constraint substep (physics_worker.js:323-395, 405-568), J-order ---------------
