@@ -1494,6 +1494,8 @@ k_pair_scan(const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileP
   }
 }
 
+static constexpr uint32_t PE_BATCH = 8;   // row words / partner records in flight per thread in k_pair_emit
+
 __global__ void __launch_bounds__(WB_THREADS)
 k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const float4* __restrict__ Glast,
             uint32_t gs, const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ tilePrefix,
@@ -1522,22 +1524,35 @@ k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   const uint32_t fw = __float_as_uint(gme.w);
   const uint32_t cnt = s.NCNT[slot] & 0xFFFFu;                    // outgoing pairs live in the API row
   const uint32_t frame = ctr->frame;
-  for (uint32_t k = 0; k < cnt && base < g.maxPairs; k++) {
-    const uint32_t wd = s.NST[(size_t)k * g.Npad + slot];
-    if (!(wd & NS_OUT)) continue;
-    const uint32_t t = wd & NS_SLOT_MASK;
-    const float4 gt = Glast[(size_t)t * gs];
-    const uint32_t ft = __float_as_uint(gt.w);
-    if ((ft & F_COLLIDER) != F_COLLIDER) continue;
-    float xt, yt;
-    partner_pos(g, gt, xt, yt);
-    if (surely_apart(x, y, gme.z, xt, yt, gt.z)) continue;
-    SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
-    exact_pair(p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, xt, yt, gt.z, ft, true, acc);
-    if (acc.hits) {
-      coll[1 + 2 * (size_t)base] = (int32_t)(d.GID ? d.GID[i] : i);  // :556-557
-      coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.SA[2 * (size_t)t + 1].w);
-      base++;
+  // The few tiles below the cap decide this kernel's duration, and each thread's walk is a chain of dependent
+  // loads: fetch PE_BATCH row words, then their partners, then evaluate in row order; stop at the entity's own
+  // count of colliding outgoing pairs (known from the write-back).
+  uint32_t found = 0;
+  for (uint32_t k0 = 0; k0 < cnt && found < outCnt && base < g.maxPairs; k0 += PE_BATCH) {
+    uint32_t wd[PE_BATCH];
+    float4 gt[PE_BATCH];
+#pragma unroll
+    for (uint32_t j = 0; j < PE_BATCH; j++) wd[j] = (k0 + j < cnt) ? s.NST[(size_t)(k0 + j) * g.Npad + slot] : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < PE_BATCH; j++)
+      if (wd[j] & NS_OUT) gt[j] = Glast[(size_t)(wd[j] & NS_SLOT_MASK) * gs];
+#pragma unroll
+    for (uint32_t j = 0; j < PE_BATCH; j++) {
+      if (!(wd[j] & NS_OUT) || base >= g.maxPairs) continue;
+      const uint32_t t = wd[j] & NS_SLOT_MASK;
+      const uint32_t ft = __float_as_uint(gt[j].w);
+      if ((ft & F_COLLIDER) != F_COLLIDER) continue;
+      float xt, yt;
+      partner_pos(g, gt[j], xt, yt);
+      if (surely_apart(x, y, gme.z, xt, yt, gt[j].z)) continue;
+      SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
+      exact_pair(p, s, frame, lastSubstep, slot, x, y, gme.z, fw, t, xt, yt, gt[j].z, ft, true, acc);
+      if (acc.hits) {
+        coll[1 + 2 * (size_t)base] = (int32_t)(d.GID ? d.GID[i] : i);  // :556-557
+        coll[2 + 2 * (size_t)base] = (int32_t)__float_as_uint(s.SA[2 * (size_t)t + 1].w);
+        base++;
+        found++;
+      }
     }
   }
 }
