@@ -756,41 +756,58 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
     uint32_t pid = SLOT_NONE;
     const uint32_t room = g.Mint + XPOOL_ROW;
     bool xover = false;
-    for (int32_t row = win.x; row <= win.y && !xover; row++) {
-      const uint32_t a = max(cellStart[(uint32_t)row * g.cols + win.z], last + 1u);
-      const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
-      for (uint32_t t0 = a; t0 < b && !xover; t0 += 32) {
-        const uint32_t tc = t0 + lane;
-        bool ok = false;
-        if (tc < b) {
-          const float4 c = __ldg(s.CXY + tc);
-          const float fx = c.x - me.x, fy = c.y - me.y;
-          // lower ids only (higher ids past my cap are my own pairs, lost as in the reference)
-          if ((__float_as_uint(c.w) & ~CX_EDGE) < id && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF)) {
-            const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-            const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-            if (d2 < vrSq && d2 > 0) {
+    // One warp, one chain of dependent loads: keep it short.  The window rows' slot ranges are fetched by 32 lanes
+    // at once, the next 32 candidate records are in flight while the current ones are tested, and a candidate in
+    // range fetches its LSLOT and WIN together.
+    for (int32_t rowBase = win.x; rowBase <= win.y && !xover; rowBase += 32) {
+      const int32_t myR = rowBase + (int32_t)lane;
+      uint32_t ra = 0, rb = 0;
+      if (myR <= win.y) {
+        ra = cellStart[(uint32_t)myR * g.cols + win.z];
+        rb = cellStart[(uint32_t)myR * g.cols + win.w + 1];
+      }
+      const int32_t nr = min(32, win.y - rowBase + 1);
+      for (int32_t r = 0; r < nr && !xover; r++) {
+        const uint32_t a = max(__shfl_sync(0xffffffffu, ra, r), last + 1u);
+        const uint32_t b = __shfl_sync(0xffffffffu, rb, r);
+        float4 cNext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a + lane < b) cNext = __ldg(s.CXY + a + lane);
+        for (uint32_t t0 = a; t0 < b && !xover; t0 += 32) {
+          const uint32_t tc = t0 + lane;
+          const float4 c = cNext;
+          if (tc + 32 < b) cNext = __ldg(s.CXY + tc + 32);
+          bool ok = false;
+          if (tc < b) {
+            const float fx = c.x - me.x, fy = c.y - me.y;
+            // lower ids only (higher ids past my cap are my own pairs, lost as in the reference)
+            if ((__float_as_uint(c.w) & ~CX_EDGE) < id && !(__fmaf_rn(fx, fx, fy * fy) > vrSqF)) {
               const uint32_t lk = s.LSLOT[tc];
-              // not capped, or its row closed after it reached me — and its scan accepts me
-              ok = (lk == SLOT_NONE || e <= lk) && scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits);
+              const int4 wt = s.WIN[tc];
+              const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+              const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+              // in my range; it is not capped, or its row closed after it reached me — and its scan accepts me
+              if (d2 < vrSq && d2 > 0 && (lk == SLOT_NONE || e <= lk)) {
+                ok = myRow >= wt.x && myRow <= wt.y && myCol >= wt.z && myCol <= wt.w;
+                if (ok && __float_as_uint(c.z) != vrBits) ok = d2 < dmul((double)c.z, (double)c.z);   // scan_accepts
+              }
             }
           }
+          const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+          if (!bits) continue;
+          const uint32_t cntNew = (uint32_t)__popc(bits);
+          if (n + cntNew > g.Mint && pid == SLOT_NONE) {   // the internal row is full: continue in the overflow pool
+            if (lane == 0) pid = atomicAdd(&ctr->xpoolUsed, 1u);
+            pid = __shfl_sync(0xffffffffu, pid, 0);
+            if (pid >= g.xpoolRows) { pid = SLOT_NONE; xover = true; }
+          }
+          const uint32_t pos = n + (uint32_t)__popc(bits & below);
+          if (ok) {
+            if (pos < g.Mint) s.NST[pos * g.Npad + e] = tc | NS_BACK;
+            else if (pid != SLOT_NONE && pos < room) s.XR[(size_t)pid * XPOOL_ROW + (pos - g.Mint)] = tc | NS_BACK;
+          }
+          n += cntNew;
+          if (n > room || (n > g.Mint && pid == SLOT_NONE)) xover = true;
         }
-        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-        if (!bits) continue;
-        const uint32_t cntNew = (uint32_t)__popc(bits);
-        if (n + cntNew > g.Mint && pid == SLOT_NONE) {   // the internal row is full: continue in the overflow pool
-          if (lane == 0) pid = atomicAdd(&ctr->xpoolUsed, 1u);
-          pid = __shfl_sync(0xffffffffu, pid, 0);
-          if (pid >= g.xpoolRows) { pid = SLOT_NONE; xover = true; }
-        }
-        const uint32_t pos = n + (uint32_t)__popc(bits & below);
-        if (ok) {
-          if (pos < g.Mint) s.NST[pos * g.Npad + e] = tc | NS_BACK;
-          else if (pid != SLOT_NONE && pos < room) s.XR[(size_t)pid * XPOOL_ROW + (pos - g.Mint)] = tc | NS_BACK;
-        }
-        n += cntNew;
-        if (n > room || (n > g.Mint && pid == SLOT_NONE)) xover = true;
       }
     }
     if (lane == 0) {
