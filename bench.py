@@ -397,13 +397,49 @@ def run_ours(args):
         # ---- end to end through the host-facing API -----------------------------------------------
         up = eng.mask("RB.ax", "RB.ay")
         down = eng.mask("T.x", "T.y", "RB.vx", "RB.vy", "RB.velocityAngle", "RB.speed")
+        e2e_steps = max(1, args.steps // 4) if args.quick else args.steps
+        e2e_balance = None
+        if world > 1 and args.e2e_balance and not args.quick:
+            # The end-to-end frame is bound by each GPU's host link, and the links of one box are not equal
+            # (tools/e2e_phases.py).  Re-plan the slabs for THIS leg on the measured end-to-end step time of every
+            # rank (outside the timed region, like the kernel-time re-plans of the device-resident leg), then time
+            # the same frame window with static cuts.
+            from multithreadedgameengine_b200.slabs import halo_rows, replan_by_rank_speed
+            obj.close()
+            e_plan, row_weight = plan, row_costs(cfg, cols)[0]
+            rank_ms = []
+            for it in range(args.e2e_balance + 1):
+                obj = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=e_plan,
+                                 balance_rows=0, transport=args.transport)
+                eng = obj.eng
+                frames(obj, args.warmup + args.steps)            # where the device-resident leg left the scene
+                if it == args.e2e_balance:
+                    break
+                ts = []
+                for _ in range(6):
+                    barrier()
+                    t0 = time.perf_counter()
+                    eng.step(1.0, up, down)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                    obj.exchange_dist()
+                barrier()
+                obj.close()
+                t = torch.tensor([float(np.median(ts[1:]))], device="cuda", dtype=torch.float64)
+                allt = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                rank_ms = [round(float(x.item()), 3) for x in allt]
+                blocks = replan_by_rank_speed(e_plan[0], rank_ms, row_weight)
+                e_plan = (blocks, halo_rows(cfg, cols, blocks))
+            e2e_balance = {"passes": args.e2e_balance, "step_ms_per_rank_before_last_replan": rank_ms,
+                           "slab_rows_begin_end": [list(b) for b in e_plan[0]], "halo_rows": e_plan[1],
+                           "what": "slabs re-planned on every rank's measured GameEngine.step time (copies included): the host links of "
+                                   "one box differ, so kernel-time balance leaves the ranks on slow links late; static cuts while timed"}
 
         def e2e_frame():
             eng.step(1.0, up, down)
             if world > 1:
                 obj.exchange_dist()
 
-        e2e_steps = max(1, args.steps // 4) if args.quick else args.steps
         for _ in range(1 if args.quick else min(3, args.warmup)):
             e2e_frame()
         barrier()
@@ -417,7 +453,8 @@ def run_ours(args):
                "h2d_bytes_per_step": int(sum_over_ranks(8 * n_host)), "d2h_bytes_per_step": int(sum_over_ranks(24 * n_host)),
                "ms_per_step": ms_e2e / e2e_steps,
                "api": "GameEngine.step(dtRatio, upload=ax|ay, download=x|y|vx|vy|velocityAngle|speed) -> weed_step"
-                      + ("; + SlabEngine.exchange_dist per frame" if world > 1 else "")}
+                      + ("; + SlabEngine.exchange_dist per frame" if world > 1 else ""),
+               "slab_balance": e2e_balance}
         launches = st["kernelLaunchesPerStep"] * args.steps + (6 * args.steps if world > 1 else 0)
         (obj.close if world > 1 else eng.close)()
 
@@ -517,6 +554,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
     ap.add_argument("--balance-rows", type=int, default=2, help="N>1: rows a cut may move per frame toward the slower slab (weed_slab_balance; 0 = static cuts)")
     ap.add_argument("--autobalance", type=int, default=3, help="measured-feedback slab re-plans before timing (N>1)")
+    ap.add_argument("--e2e-balance", type=int, default=2, help="N>1: re-plans of the slabs on the measured end-to-end step time before the e2e leg (0 = keep the device leg's slabs)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 neighbour exchange: peer-to-peer writes over NVLink (default) or the NCCL send/recv fallback")
     ap.add_argument("--verify", type=int, default=8, help="N>1: frames of the checksum comparison against one context (0 = skip)")

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from multithreadedgameengine_b200 import binding as B, scenes
-from multithreadedgameengine_b200.slabs import cell_rows, exchange_fixed, halo_rows, header_count, plan_slabs, replan_from_times
+from multithreadedgameengine_b200.slabs import cell_rows, exchange_fixed, halo_rows, header_count, plan_slabs, replan_by_rank_speed, replan_from_times
 
 
 def test_cell_rows_follow_the_reference_key():
@@ -78,6 +78,21 @@ def test_replan_from_times_moves_cuts_toward_the_slow_slab():
     assert new[-1][1] - new[-1][0] < 100 and new[0][1] - new[0][0] > 100
     # equal times are a fixed point (up to one row of rounding)
     same = replan_from_times(blocks, [2.0] * 4)
+    assert all(abs(a[0] - b[0]) <= 1 and abs(a[1] - b[1]) <= 1 for a, b in zip(same, blocks))
+
+
+def test_replan_by_rank_speed_gives_slow_links_fewer_rows():
+    # four ranks, uniform rows; ranks 0-1 sit on links half as fast: the same 100 rows took them twice as long
+    blocks = [(0, 100), (100, 200), (200, 300), (300, 400)]
+    new = replan_by_rank_speed(blocks, [2.0, 2.0, 1.0, 1.0], np.ones(400))
+    sizes = [b - a for a, b in new]
+    assert new[0][0] == 0 and new[-1][1] == 400 and all(a[1] == b[0] for a, b in zip(new, new[1:]))
+    assert all(abs(n - e) <= 2 for n, e in zip(sizes, [67, 67, 133, 133]))
+    # with the speeds unchanged, the new cuts equalise the predicted times
+    pred = [n / sp for n, sp in zip(sizes, [50, 50, 100, 100])]
+    assert max(pred) / min(pred) < 1.05
+    # equal times are a fixed point
+    same = replan_by_rank_speed(blocks, [1.5] * 4, np.ones(400))
     assert all(abs(a[0] - b[0]) <= 1 and abs(a[1] - b[1]) <= 1 for a, b in zip(same, blocks))
 
 

@@ -29,6 +29,34 @@ def main():
     from multithreadedgameengine_b200.slabs import SlabEngine, plan_slabs
     cfg, cols = bench.workload(args.workload, None)
     stream = torch.cuda.Stream()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # PCIe with every rank copying at once: is the link per GPU or shared?
+    nb = 128 << 20
+    dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    hbuf = torch.empty(nb, dtype=torch.uint8).pin_memory()
+    hbuf2 = torch.empty(nb, dtype=torch.uint8).pin_memory()
+    dbuf2 = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    s2 = torch.cuda.Stream()
+    pcie = {}
+    for name in ("d2h", "h2d", "both"):
+        for rep in range(3):
+            sync_all()
+            t0 = time.perf_counter()
+            if name in ("d2h", "both"):
+                hbuf.copy_(dbuf, non_blocking=True)
+            if name in ("h2d", "both"):
+                with torch.cuda.stream(s2):
+                    dbuf2.copy_(hbuf2, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        pcie[name] = round(nb * (2 if name == "both" else 1) / dt / 1e9, 1)
+    del dbuf, hbuf, hbuf2, dbuf2
     with torch.cuda.stream(stream):
         if world > 1:
             sl = SlabEngine(cfg, cols, rank, world, device=local, stream=stream.cuda_stream, plan=plan_slabs(cfg, cols, world))
@@ -66,8 +94,17 @@ def main():
             if f >= 3:
                 rows.append([t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5])
         r = np.array(rows).mean(0) * 1e3
+        # the bench's e2e loop: free running, ranks meet only through the exchange
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.frames):
+            eng.step(1.0, up, down)
+            if sl:
+                sl.exchange_dist()
+        sync_all()
+        free_ms = (time.perf_counter() - t0) * 1e3 / args.frames
         n_host = eng.totalEntityCount if world == 1 else sl.status()["top"]
-        out = {"rank": rank, "entities_moved": int(n_host),
+        out = {"rank": rank, "entities_moved": int(n_host), "pcie_GBps_all_ranks_at_once": pcie, "e2e_loop_ms": round(free_ms, 3),
                "ms": {"step(up only)": round(r[0], 3), "step(down only)": round(r[1], 3), "step(up+down)": round(r[2], 3),
                       "exchange call": round(r[3], 3), "exchange wait": round(r[4], 3), "run(1) no copies": round(r[5], 3)},
                "GBps_down": round(24 * n_host / (r[1] - r[5]) / 1e6, 1) if r[1] > r[5] else None}
