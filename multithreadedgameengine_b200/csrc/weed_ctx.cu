@@ -639,8 +639,8 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
   TIME_MARK(ctx, timing, 7);
   k_writeback<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->d, ctx->s, ctx->slotOf, ctx->tileCount);
   k_pair_scan<<<1, 1024, 0, st>>>(ctx->tileCount, ctx->tilePrefix, ctx->wbTiles, g.maxPairs, ctx->dCtr, ctx->coll);
-  k_pair_emit<<<ctx->wbTiles, WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, in, gs, ctx->slotOf, ctx->tilePrefix,
-                                                   ctx->dCtr, ctx->coll, (uint32_t)(S - 1));
+  k_pair_emit<<<std::min<uint32_t>(ctx->wbTiles, 148u * 8u), WB_THREADS, 0, st>>>(g, ctx->dParams, ctx->d, ctx->s, in, gs, ctx->slotOf,
+                                                                                  ctx->tilePrefix, ctx->dCtr, ctx->coll, (uint32_t)(S - 1), ctx->wbTiles);
   k_physics_end<<<1, 32, 0, st>>>(ctx->dCtr);
   TIME_MARK(ctx, timing, 8);
   CK(cudaGetLastError());

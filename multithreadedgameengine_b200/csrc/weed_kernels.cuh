@@ -1516,11 +1516,15 @@ static constexpr uint32_t PE_BATCH = 8;   // row words / partner records in flig
 __global__ void __launch_bounds__(WB_THREADS)
 k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const float4* __restrict__ Glast,
             uint32_t gs, const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ tilePrefix,
-            const Counters* __restrict__ ctr, int32_t* __restrict__ coll, uint32_t lastSubstep) {
+            const Counters* __restrict__ ctr, int32_t* __restrict__ coll, uint32_t lastSubstep, uint32_t numTiles) {
   __shared__ uint32_t s_warp[WB_THREADS / 32];
-  const uint32_t tileBase = tilePrefix[blockIdx.x];
-  if (tileBase >= g.maxPairs) return;                              // whole tile past the cap
-  const uint32_t i = blockIdx.x * WB_THREADS + threadIdx.x;
+  // The tile prefixes ascend, so the tiles below the cap are a prefix of the tile sequence: a small grid strides
+  // over the tiles and every block leaves at the first tile past the cap (a launch of one block per tile spent
+  // 0.06 ms at 16 M entities on blocks that read one word and returned).
+  for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+  const uint32_t tileBase = tilePrefix[tile];
+  if (tileBase >= g.maxPairs) return;                              // this tile and all later ones are past the cap
+  const uint32_t i = tile * WB_THREADS + threadIdx.x;
   uint32_t slot;
   const uint32_t outCnt = wb_out_count(s, slotOf, i, g.N, slot);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1533,7 +1537,7 @@ k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
   __syncthreads();
   uint32_t base = tileBase + (inc - outCnt);
   for (uint32_t w = 0; w < warp; w++) base += s_warp[w];
-  if (outCnt == 0 || base >= g.maxPairs) return;
+  if (outCnt != 0 && base < g.maxPairs) {
   // re-derive my colliding outgoing pairs on the last sweep's start positions
   const Params p = *pp;
   const float4 gme = Glast[(size_t)slot * gs];
@@ -1571,6 +1575,9 @@ k_pair_emit(GridDims g, const Params* __restrict__ pp, ById d, BySlot s, const f
         found++;
       }
     }
+  }
+  }
+  __syncthreads();                                              // s_warp is rewritten by the next tile
   }
 }
 
