@@ -37,8 +37,10 @@ UNIT = "entity-substeps/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/), config4 16M on one B200; None = not captured for this kernel.
-TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r2_ncu_config4_16M_summary.md
-    "k_neighbors2": None, "k_sweep": None, "k_build_slots+k_slot_prep": None,
+TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r2_ncu_config4_16M_final_frame_summary.md (frame 6 of the scene)
+    "k_neighbors2": 4.742e9,                      # 1.695 read + 3.047 written
+    "k_sweep": 2.32e9,                            # first sweep 2.05 + 0.41, last sweep 1.66 + 0.52
+    "k_build_slots+k_slot_prep": 3.226e9,         # 0.80 + 1.01 and 0.51 + 0.91
 }
 
 KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids+k_slot_rank", "k_build_slots+k_slot_prep", "k_neighbors2",
