@@ -95,6 +95,8 @@ __global__ void k_spatial_begin(Counters* ctr) {
     ctr->xpoolUsed = 0;
     ctr->nCapped = 0;
     ctr->nSort = 0;
+    ctr->nBigCells = 0;
+    ctr->nHeavy = 0;
     ctr->explicitPairs = 0;
     ctr->maxCellFrame = 0;
     ctr->tBegin = global_timer_ns();
@@ -127,9 +129,14 @@ k_cell_key(GridDims g, const float4* __restrict__ DP, const uint8_t* __restrict_
 }
 
 // ---- K2: exclusive scan of the cell histogram, also clears it for the next frame ---------
+// cells above BIG_CELL entities get their id lists sorted by a block (k_sort_big_cells, below)
+static constexpr uint32_t BIG_CELL = 128, BIG_CELL_SORT_CAP = 4096;
+__device__ __forceinline__ bool big_cell_sorted(uint32_t n) { return n > BIG_CELL && n <= BIG_CELL_SORT_CAP; }
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, uint32_t numTiles,
-            unsigned long long* status, Counters* ctr, const int32_t* __restrict__ slabCuts, uint32_t cols, int32_t halo) {
+            unsigned long long* status, Counters* ctr, const int32_t* __restrict__ slabCuts, uint32_t cols, int32_t halo,
+            uint32_t* __restrict__ bigCells, uint32_t bigCap, uint32_t* __restrict__ cellMaxL) {
   __shared__ uint32_t s_tile, s_excl, s_warp[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scanTile, 1u);
   __syncthreads();
@@ -150,6 +157,8 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
     for (int v = 0; v < V; v++) c[v] = reinterpret_cast<const uint4*>(cellCount + i0)[v];
 #pragma unroll
     for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellCount + i0)[v] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellMaxL + i0)[v] = make_uint4(0, 0, 0, 0);   // k_cell_lslot_max
   } else {
 #pragma unroll
     for (int v = 0; v < V; v++) c[v] = make_uint4(0, 0, 0, 0);
@@ -159,6 +168,18 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
   for (int v = 0; v < V; v++) {
     tsum += c[v].x + c[v].y + c[v].z + c[v].w;
     tmax = max(tmax, max(max(c[v].x, c[v].y), max(c[v].z, c[v].w)));
+  }
+  if (tmax > BIG_CELL) {                                       // piles: their lists are sorted by a block each
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const uint32_t cv[4] = {c[v].x, c[v].y, c[v].z, c[v].w};
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (cv[u] > BIG_CELL) {
+          const uint32_t at = atomicAdd(&ctr->nBigCells, 1u);
+          if (at < bigCap) bigCells[at] = (uint32_t)(i0 + (size_t)v * 4 + u);
+        }
+    }
   }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = tsum;
@@ -251,6 +272,7 @@ struct BySlot {
   uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
   uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
   uint32_t* SORTLIST;// slots that received explicit pairs this frame (unordered)
+  uint32_t* HEAVY;   // slots marked F_XPOOL / F_XOVER this frame (unordered): a warp each in the sweeps (k_sweep_heavy)
   uint32_t* XPID;    // F_XPOOL: which row of the overflow pool continues this entity's internal row
   uint32_t* XR;      // overflow pool: XPOOL_ROW words per pool row (entity-major: one entity's words are consecutive)
   uint32_t* XRCNT;   // entries in each pool row
@@ -265,6 +287,41 @@ struct FrameConst { GridDims g; BySlot s; };
 // stable position: number of ids in my cell smaller than mine (cell lists are ascending in the
 // reference because it inserts i = 0..N-1 in order, spatial_worker.js:146,168).  A kernel of its
 // own: the dependent gathers key -> cellStart -> ids of the cell need occupancy, not registers.
+// Piles.  A settled bed puts hundreds to thousands of entities into one cell (config 4 after 300 frames:
+// 3.6 M entities in cells of 500-1900), and counting the smaller ids of a cell costs occupancy^2 per cell
+// (6.6 ms per frame there).  Cells above BIG_CELL entities are listed by k_cell_scan; one block sorts each
+// list in shared memory (bitonic), and k_slot_rank finds its rank by binary search.  Lists beyond
+// BIG_CELL_SORT_CAP stay unsorted and keep the linear count (both kernels apply the same rule).
+
+__global__ void __launch_bounds__(256)
+k_sort_big_cells(const uint32_t* __restrict__ bigCells, uint32_t bigCap, const Counters* __restrict__ ctr,
+                 const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ arrIds) {
+  __shared__ uint32_t sm[BIG_CELL_SORT_CAP];
+  const uint32_t nBig = min(ctr->nBigCells, bigCap);
+  for (uint32_t w = blockIdx.x; w < nBig; w += gridDim.x) {
+    const uint32_t c = bigCells[w];
+    const uint32_t s0 = cellStart[c], n = cellStart[c + 1] - s0;
+    if (!big_cell_sorted(n)) continue;              // block-uniform
+    uint32_t P = 256;
+    while (P < n) P <<= 1;
+    for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) sm[k] = k < n ? arrIds[s0 + k] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t idx = threadIdx.x; idx < P; idx += blockDim.x) {
+          const uint32_t ixj = idx ^ j;
+          if (ixj > idx) {
+            const uint32_t a = sm[idx], b = sm[ixj];
+            if ((a > b) == ((idx & k) == 0)) { sm[idx] = b; sm[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) arrIds[s0 + k] = sm[k];
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_slot_rank(GridDims g, const uint8_t* __restrict__ F, const uint32_t* __restrict__ GID,
             const uint32_t* __restrict__ key, const uint32_t* __restrict__ cellStart,
@@ -276,7 +333,16 @@ k_slot_rank(GridDims g, const uint8_t* __restrict__ F, const uint32_t* __restric
   const uint32_t gid = GID ? GID[i] : i;
   const uint32_t s0 = cellStart[k], s1 = cellStart[k + 1];
   uint32_t r = 0;
-  for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < gid;
+  if (big_cell_sorted(s1 - s0)) {                  // k_sort_big_cells left this list in id order
+    uint32_t lo = s0, hi = s1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (arrIds[mid] < gid) lo = mid + 1; else hi = mid;
+    }
+    r = lo - s0;
+  } else {
+    for (uint32_t t = s0; t < s1; t++) r += arrIds[t] < gid;
+  }
   slotOf[i] = s0 + r;
 }
 
@@ -823,6 +889,7 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
       if (add) {
         reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
         reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+        s.HEAVY[atomicAdd(&ctr->nHeavy, 1u)] = e;
         if (xover) atomicAdd(&ctr->xoverRows, 1u);
       }
       if (inRow > g.M) {
@@ -833,13 +900,35 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
+// Dense regime only (returns at once otherwise): per cell, the largest "my row is open up to slot ..." bound
+// of its entities — SLOT_NONE's all-ones for an uncapped row.  Consecutive slots share cells, so a warp
+// reduces per cell before the atomic.  k_cell_scan cleared the array.
+__global__ void __launch_bounds__(256)
+k_cell_lslot_max(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
+                 uint32_t* __restrict__ cellMaxL) {
   const uint32_t A = cellStart[g.cells];
-  if (!beyond_dense_regime(ctr->nCapped, A)) return;   // k_beyond_cap took this frame
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < A; e += gridDim.x * blockDim.x) {
+  if (!beyond_dense_regime(ctr->nCapped, A)) return;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < A; t0 += gridDim.x * blockDim.x) {
+    const uint32_t t = t0 + lane;
+    uint32_t cell = 0xFFFFFFFFu, v = 0;
+    if (t < A) {
+      const float4 c = s.CXY[t];
+      int32_t col, row;
+      cell_of(g, c.x, c.y, col, row);
+      cell = (uint32_t)row * g.cols + (uint32_t)col;
+      v = s.LSLOT[t];                                  // SLOT_NONE = 0xFFFFFFFF: an open row accepts every later slot
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, cell);
+    const uint32_t m = __reduce_max_sync(peers, v);
+    if (t < A && lane == (uint32_t)(__ffs(peers) - 1)) atomicMax(&cellMaxL[cell], m);
+  }
+}
+
+__device__ __forceinline__ void beyond_cap_one(const GridDims& g, const BySlot& s, const uint32_t* __restrict__ cellStart,
+                                               Counters* ctr, const uint32_t* __restrict__ cellMaxL, uint32_t e) {
   const uint32_t last = s.LSLOT[e];
-  if (last == SLOT_NONE) continue;                     // row not capped: nothing was lost
+  if (last == SLOT_NONE) return;                       // row not capped: nothing was lost
   const float4 me = s.CXY[e];
   const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE;
   const uint32_t vrBits = __float_as_uint(me.z);
@@ -852,25 +941,35 @@ k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart,
   uint32_t pid = SLOT_NONE, m = 0;                    // overflow-pool row and its entries
   bool xover = false;
   for (int32_t row = win.x; row <= win.y && !xover; row++) {
-    uint32_t t = max(cellStart[(uint32_t)row * g.cols + win.z], last + 1u);
-    const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+   const uint32_t rowBase = (uint32_t)row * g.cols;
+   uint32_t cellA = cellStart[rowBase + win.z];
+   for (int32_t col = win.z; col <= win.w && !xover; col++) {
+    // A candidate counts only if its row is open or closed at or after me (LSLOT >= e); cellMaxL holds the
+    // largest such bound of a cell (k_cell_lslot_max), so a pile whose rows all closed before me is skipped whole.
+    const uint32_t b = cellStart[rowBase + col + 1];
+    uint32_t t = max(cellA, last + 1u);
+    cellA = b;
+    if (t >= b || e > cellMaxL[rowBase + col]) continue;
     for (; t < b && !xover; t += 4) {
-      float4 c[4];
+      // In a pile nearly every row closed long before it reached me: test that first, on four 4-byte words,
+      // before any 16-byte candidate record is fetched (SLOT_NONE, an open row, is all ones: never below me).
+      uint32_t lk[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) c[u] = __ldg(s.CXY + min(t + (uint32_t)u, b - 1));
+      for (int u = 0; u < 4; u++) lk[u] = __ldg(s.LSLOT + min(t + (uint32_t)u, b - 1));
+      if (e > lk[0] && e > lk[1] && e > lk[2] && e > lk[3]) continue;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const uint32_t tc = t + (uint32_t)u;
         if (tc >= b) break;
-        const uint32_t jid = __float_as_uint(c[u].w) & ~CX_EDGE;
+        if (e > lk[u]) continue;                       // its row closed before it reached me
+        const float4 c = __ldg(s.CXY + tc);
+        const uint32_t jid = __float_as_uint(c.w) & ~CX_EDGE;
         if (jid >= id) continue;                       // higher ids past my cap: my own pairs, lost as in the reference
-        const float fx = c[u].x - me.x, fy = c[u].y - me.y;
+        const float fx = c.x - me.x, fy = c.y - me.y;
         if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;
-        const double dX = dsub((double)c[u].x, myX), dY = dsub((double)c[u].y, myY);
+        const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
         const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
         if (!(d2 < vrSq && d2 > 0)) continue;
-        const uint32_t lk = s.LSLOT[tc];
-        if (lk != SLOT_NONE && e > lk) continue;       // its row closed before it reached me
         if (!scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) continue;
         if (n < g.Mint) { s.NST[n * g.Npad + e] = tc | NS_BACK; n++; continue; }
         if (pid == SLOT_NONE) {                        // internal row full: continue in the overflow pool
@@ -882,6 +981,7 @@ k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart,
         m++;
       }
     }
+   }
   }
   uint32_t add = xover ? F_XOVER : 0u;
   if (pid != SLOT_NONE) {
@@ -893,12 +993,30 @@ k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart,
   if (add) {
     reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
     reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+    s.HEAVY[atomicAdd(&ctr->nHeavy, 1u)] = e;
     if (xover) atomicAdd(&ctr->xoverRows, 1u);
   }
   if (n > g.M) {
     s.NCNT[e] = g.M | (n << 16);
     row_tail_fill(g, s, e, n);
   }
+}
+
+static constexpr int K4D_THREADS = 128, K4D_BLOCKS = 148 * 9;     // one wave (52 registers: 9 blocks of 128 per SM)
+__global__ void __launch_bounds__(K4D_THREADS)
+k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr,
+                   const uint32_t* __restrict__ cellMaxL) {
+  const uint32_t A = cellStart[g.cells];
+  if (!beyond_dense_regime(ctr->nCapped, A)) return;   // k_beyond_cap took this frame
+  // One resident wave of threads strides over the slots from the top: the settled bed lies in the last cell rows
+  // and its entities cost hundreds of times more than the others, so they start first and spread over all warps
+  // (a second wave of blocks left the SMs uneven: 57 % busy; chunks drawn from a counter per block stalled the
+  // block on its slowest warp, per warp they were too coarse for the 1790 heavy chunks of config 3).
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t groups = (A + stride - 1u) / stride;
+  for (uint32_t k = 0; k < groups; k++) {
+    const uint32_t e = (groups - 1u - k) * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < A) beyond_cap_one(g, s, cellStart, ctr, cellMaxL, e);
   }
 }
 
@@ -1153,12 +1271,20 @@ __device__ __forceinline__ const float4* slot_rec(const float4* __restrict__ G, 
 #endif
 static constexpr int K6V2_THREADS = WEED_K6V2_THREADS;
 
+#ifndef WEED_HEAVY_SPLIT
+#define WEED_HEAVY_SPLIT 1
+#endif
+static constexpr bool HEAVY_SPLIT = WEED_HEAVY_SPLIT != 0;   // 0: k_sweep walks pool rows and resumed scans itself, one thread each
+
 template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(K6V2_THREADS, WEED_K6V2_MINBLOCKS)
 k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
         float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
         uint32_t substep, const FrameConst* __restrict__ fc) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  // Blocks are dispatched in index order and slots ascend with the cell row: a bed settled on the floor (the
+  // last rows) would be the last blocks, heavy work with nothing left to run beside it (config 3, frame 100:
+  // SMs busy 51 % of the sweep).  Walk the slots from the top.
+  const uint32_t e = (gridDim.x - 1u - blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= cellStart[g.cells]) return;
   const float4 gme = Gin[e];
   float2 pxy;
@@ -1166,6 +1292,7 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
   else pxy = s.PXY[e];
   const float x = gme.x, y = gme.y, r = gme.z;
   const uint32_t fw = __float_as_uint(gme.w);
+  if (HEAVY_SPLIT && (fw & (F_XPOOL | F_XOVER)) && s.XHEAD[e] == 0) return;   // a "popular" entity of a pile: k_sweep_heavy
   SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
   if ((fw & F_COLLIDER) == F_COLLIDER) {                         // :430
     const uint32_t cnt = s.NCNT[e] >> 16;                        // the INTERNAL row: API row + lower-id partners past the cap
@@ -1244,6 +1371,143 @@ k_sweep(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __res
       apply_bounds(g, pp->boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
     Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
     s.PXY[e] = pxy;
+  }
+}
+
+// ---- K6 for the popular entities of a pile: one warp each ------------------------------------------------
+// An entity with an overflow-pool row (F_XPOOL: up to 64 + 512 lower-id partners past its cap) or a resumed scan
+// (F_XOVER: more than that; the candidates of its whole window) kept ONE thread of k_sweep busy for
+// milliseconds while the rest of the GPU had finished (config 3, frame 300: 5.4 ms for both sweeps, SMs busy
+// half of it).  J-order lets a warp share the work: every pair is evaluated on start-of-sweep positions, so 32
+// lanes evaluate 32 partners at once and the displacements are then ADDED in ascending partner order, with the
+// float32 rounding after each — the same sequence of operations the single thread performs, bit for bit.
+// Streams in the order of substep_slow: internal row, pool row, resumed scan.  Entities with an explicit list
+// (XHEAD) stay with k_sweep's merge path.
+struct LaneMove { double ax, ay; bool hit, out, move; };
+__device__ __forceinline__ LaneMove lane_pair(const Params& p, const BySlot& s, uint32_t frame, uint32_t substep, uint32_t e,
+                                              float x, float y, float r, uint32_t fw, uint32_t t, float4 gt, bool lower) {
+  const uint32_t ft = __float_as_uint(gt.w);
+  PairMove m;
+  if (lower) m = pair_eval(p, frame, substep, s.SA, e, t, x, y, r, fw, gt.x, gt.y, gt.z, ft);
+  else       m = pair_eval(p, frame, substep, s.SA, t, e, gt.x, gt.y, gt.z, ft, x, y, r, fw);
+  LaneMove lm;
+  lm.hit = m.hit; lm.out = m.hit && lower;
+  lm.move = m.hit && (lower ? m.moveI : m.moveJ);
+  lm.ax = lower ? m.mx : -m.mx; lm.ay = lower ? m.my : -m.my;
+  return lm;
+}
+// the warp's 32 results into the accumulator, ascending lane = ascending partner slot
+__device__ __forceinline__ void lanes_apply(const LaneMove& lm, bool valid, SubstepAcc& acc) {
+  acc.hits += (uint32_t)__popc(__ballot_sync(0xffffffffu, valid && lm.hit));
+  acc.outHits += (uint32_t)__popc(__ballot_sync(0xffffffffu, valid && lm.out));
+  uint32_t mb = __ballot_sync(0xffffffffu, valid && lm.move);
+  while (mb) {
+    const int l = __ffs((int)mb) - 1;
+    mb &= mb - 1;
+    const double ax = __shfl_sync(0xffffffffu, lm.ax, l), ay = __shfl_sync(0xffffffffu, lm.ay, l);
+    acc.x = fround(dadd((double)acc.x, ax));
+    acc.y = fround(dadd((double)acc.y, ay));
+  }
+}
+
+static constexpr int K6H_THREADS = 256, K6H_BLOCKS = 148 * 4;
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(K6H_THREADS)
+k_sweep_heavy(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
+              float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
+              uint32_t substep) {
+  const uint32_t nHeavy = ctr->nHeavy;
+  if (nHeavy == 0) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+  const Params& p = *pp;
+  const uint32_t frame = ctr->frame;
+  for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nHeavy; w += warpsTotal) {
+    const uint32_t e = s.HEAVY[w];
+    if (s.XHEAD[e] != 0) continue;                                 // explicit list: k_sweep merged it
+    const float4 gme = Gin[e];
+    float2 pxy;
+    if (FIRST) { const float4 hi = s.SA[2 * (size_t)e + 1]; pxy = make_float2(hi.x, hi.y); }
+    else pxy = s.PXY[e];
+    const float x = gme.x, y = gme.y, r = gme.z;
+    const uint32_t fw = __float_as_uint(gme.w);
+    SubstepAcc acc; acc.x = x; acc.y = y; acc.hits = 0; acc.outHits = 0;
+    if ((fw & F_COLLIDER) == F_COLLIDER) {
+      const uint32_t cnt = s.NCNT[e] >> 16;
+      uint32_t lastStored = cnt ? (s.NST[(cnt - 1) * g.Npad + e] & NS_SLOT_MASK) : 0u;
+      // row words rp[0], rp[stride], ...: 32 at a time
+      auto walk = [&](const uint32_t* __restrict__ rp, uint32_t stride, uint32_t n) {
+        for (uint32_t kb = 0; kb < n; kb += 32) {
+          const uint32_t k = kb + lane;
+          const uint32_t wd = k < n ? rp[k * stride] : 0u;
+          bool cand = wd >= NS_OUT;                                // OUT or BACK set (padding words carry neither)
+          const uint32_t t = wd & NS_SLOT_MASK;
+          const bool lower = (wd & NS_OUT) != 0;
+          float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cand) {
+            gt = __ldg(slot_rec(Gin, t));
+            const uint32_t ft = __float_as_uint(gt.w);
+            cand = (ft & F_COLLIDER) == F_COLLIDER && !surely_apart(x, y, r, gt.x, gt.y, gt.z) &&
+                   (lower || in_row_of(s, ft, t, e));
+          }
+          LaneMove lm; lm.hit = lm.out = lm.move = false; lm.ax = lm.ay = 0;
+          if (cand) lm = lane_pair(p, s, frame, substep, e, x, y, r, fw, t, gt, lower);
+          lanes_apply(lm, cand, acc);
+        }
+      };
+      walk(s.NST + e, g.Npad, cnt);
+      if (fw & F_XPOOL) {
+        const uint32_t pid = s.XPID[e], pcnt = s.XRCNT[pid];
+        const uint32_t* pool = s.XR + (size_t)pid * XPOOL_ROW;
+        walk(pool, 1u, pcnt);
+        if (pcnt) lastStored = pool[pcnt - 1] & NS_SLOT_MASK;
+      }
+      if (fw & F_XOVER) {                                           // BeyondScan, 32 candidates at a time
+        const float4 me = s.CXY[e];
+        const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE, vrBits = __float_as_uint(me.z);
+        const double myX = me.x, myY = me.y, vrSq = dmul((double)me.z, (double)me.z);
+        int32_t myCol, myRow;
+        cell_of(g, me.x, me.y, myCol, myRow);
+        const int4 win = s.WIN[e];
+        for (int32_t row = win.x; row <= win.y; row++) {
+          const uint32_t a = max(cellStart[(uint32_t)row * g.cols + win.z], lastStored + 1u);
+          const uint32_t b = cellStart[(uint32_t)row * g.cols + win.w + 1];
+          for (uint32_t t0 = a; t0 < b; t0 += 32) {
+            const uint32_t tc = t0 + lane;
+            bool cand = false;
+            float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tc < b && e <= __ldg(s.LSLOT + tc)) {                 // in_row_of, first: most rows of a pile closed before me
+              const float4 c = __ldg(s.CXY + tc);
+              if ((__float_as_uint(c.w) & ~CX_EDGE) < id) {          // higher ids: my own pairs, lost to the cap
+                const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
+                const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
+                if (d2 < vrSq && d2 > 0 && scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) {
+                  gt = __ldg(slot_rec(Gin, tc));
+                  const uint32_t ft = __float_as_uint(gt.w);
+                  cand = (ft & F_COLLIDER) == F_COLLIDER && in_row_of(s, ft, tc, e) && !surely_apart(x, y, r, gt.x, gt.y, gt.z);
+                }
+              }
+            }
+            LaneMove lm; lm.hit = lm.out = lm.move = false; lm.ax = lm.ay = 0;
+            if (cand) lm = lane_pair(p, s, frame, substep, e, x, y, r, fw, tc, gt, false);
+            lanes_apply(lm, cand, acc);
+          }
+        }
+      }
+    }
+    if (lane == 0) {                                                // k_sweep's epilogue
+      const uint32_t cc = ((fw >> F_CC_SHIFT) + acc.hits) & 0xFFu;
+      if (LAST) {
+        float4* o = reinterpret_cast<float4*>(s.OUT + e);
+        o[0] = make_float4(acc.x, acc.y, pxy.x, pxy.y);
+        o[1] = make_float4(__uint_as_float(cc | ((acc.outHits & 0x7FFFFFu) << 8) | ((fw & F_OWNED) ? 0x80000000u : 0u)), 0.f, 0.f, 0.f);
+      } else {
+        if ((fw & F_DYNAMIC_MASK) == F_DYNAMIC_VAL && !clear_of_walls(g, acc.x, acc.y, r))
+          apply_bounds(g, pp->boundaryElasticity, r, acc.x, acc.y, pxy.x, pxy.y);
+        Gout[e] = make_float4(acc.x, acc.y, r, __uint_as_float((fw & 0xFFFF00FFu) | (cc << F_CC_SHIFT)));
+        s.PXY[e] = pxy;
+      }
+    }
   }
 }
 

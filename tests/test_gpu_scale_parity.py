@@ -88,6 +88,27 @@ def test_collapsed_bed_every_row_capped():
     assert st["cappedRows"] > 50_000
 
 
+def test_piles_of_hundreds_to_thousands_in_one_cell():
+    """What a settled bed does to the grid (config 4 after 300 frames: cells of 500-1900 entities).  Cell lists
+    above 128 entities are sorted by a block and ranked by binary search, above 4096 they keep the linear
+    count; with most rows capped the lower-id partners past a cap are searched cell by cell, skipping the
+    cells whose rows all closed before the searcher's slot.  Piles of 200, 1500 and 5000 entities in single
+    cells on top of a dense uniform scene, small cap: state, rows and pairs against the oracle."""
+    cfg, cols = scenes.balls_synthetic(26_700, (320.0, 320.0), 16.0, 12, 2, (2.0, 5.0), 16.0, seed=11)
+    rng = np.random.Generator(np.random.PCG64(3))
+    at = 20_001
+    for n, (cx, cy) in ((200, (3, 5)), (1500, (10, 10)), (5000, (17, 19))):
+        sl = slice(at, at + n)
+        cols["T.x"][sl] = (cx * 16.0 + 0.25 + rng.random(n) * 15.5).astype(np.float32)
+        cols["T.y"][sl] = (cy * 16.0 + 0.25 + rng.random(n) * 15.5).astype(np.float32)
+        cols["RB.px"][sl] = cols["T.x"][sl]
+        cols["RB.py"][sl] = cols["T.y"][sl]
+        at += n
+    cfg["physics"]["maxCollisionPairs"] = 3_000_000
+    st = run_and_compare(cfg, cols, 3)
+    assert st["cappedRows"] > 20_000 and st["maxCellOccupancy"] > 4096
+
+
 @pytest.mark.parametrize("flags,M,vr", [(B.FLAG_K4_WIDE, 24, 16.0), (B.FLAG_K4_THREAD, 300, 40.0)], ids=["wide-short-rows", "thread-long-rows"])
 def test_both_scan_forms_on_the_other_side_of_their_threshold(flags, M, vr):
     """The library picks the warp-per-entity scan for maxNeighbors >= 256 and the thread-per-entity one
