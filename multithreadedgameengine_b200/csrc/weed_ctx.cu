@@ -149,7 +149,7 @@ struct weed_ctx {
   uint32_t *key = nullptr, *rank = nullptr, *arrIds = nullptr, *slotOf = nullptr;
   // grid
   uint32_t *cellCount = nullptr, *cellStart = nullptr;
-  uint32_t *bigCells = nullptr, *cellMaxL = nullptr;   // cells above BIG_CELL entities; per cell max LSLOT (dense cap regime)
+  uint32_t *bigCells = nullptr;   // cells above BIG_CELL entities
   uint32_t bigCap = 0;
   uint32_t scanTiles = 0, wbTiles = 0;
   unsigned long long *scanStatus = nullptr;
@@ -392,14 +392,13 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
   ctx->scanTiles = (uint32_t)(((size_t)g.cells + 1 + SCAN_TILE - 1) / SCAN_TILE);
   A(ctx->cellCount, (size_t)ctx->scanTiles * SCAN_TILE);
   A(ctx->cellStart, (size_t)ctx->scanTiles * SCAN_TILE);
-  A(ctx->cellMaxL, (size_t)ctx->scanTiles * SCAN_TILE);
   ctx->bigCap = (uint32_t)(N / BIG_CELL + 16);
   A(ctx->bigCells, ctx->bigCap);
   A(ctx->scanStatus, ctx->scanTiles);
   ctx->wbTiles = (uint32_t)((N + WB_THREADS - 1) / WB_THREADS);
   A(ctx->tileCount, ctx->wbTiles); A(ctx->tilePrefix, ctx->wbTiles);
   A(ctx->s.SA, 2 * N); A(ctx->s.QXY, N + 4);     /* k_neighbors2 reads up to three positions past a range */ A(ctx->s.CXY, N); A(ctx->s.WIN, N); if (ctx->k4Wide) A(ctx->s.PW, N); A(ctx->s.GA, N); A(ctx->s.GB, N); A(ctx->s.PXY, N);
-  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N); A(ctx->s.CAPLIST, N); A(ctx->s.SORTLIST, N); A(ctx->s.HEAVY, N);
+  A(ctx->s.NCNT, N); A(ctx->s.XHEAD, N); A(ctx->s.OUT, N); A(ctx->s.LSLOT, N); A(ctx->s.CAPLIST, N); A(ctx->s.SORTLIST, N); A(ctx->s.HEAVY, N); A(ctx->s.BCNT, N); A(ctx->s.BCUR, N);
   if (cfg->flags & WEED_FLAG_K6_TILE) A(ctx->s.TD, ((N + PREP_THREADS - 1) / PREP_THREADS) * (PREP_THREADS / TILE));
   A(ctx->s.NST, (size_t)g.Npad * g.Mint);
   g.xpoolRows = (uint32_t)std::max<size_t>(256, N / 32);     // 64 bytes per entity
@@ -578,7 +577,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   k_cell_key<<<nb, 256, 0, st>>>(g, ctx->d.DP, ctx->d.F, ctx->key, ctx->rank, ctx->cellCount);
   TIME_MARK(ctx, timing, 1);
   k_cell_scan<<<ctx->scanTiles, SCAN_THREADS, 0, st>>>(ctx->cellCount, ctx->cellStart, ctx->scanTiles, ctx->scanStatus, ctx->dCtr,
-                                                       slab_cuts(ctx), (uint32_t)g.cols, g.slabHalo, ctx->bigCells, ctx->bigCap, ctx->cellMaxL);
+                                                       slab_cuts(ctx), (uint32_t)g.cols, g.slabHalo, ctx->bigCells, ctx->bigCap);
   TIME_MARK(ctx, timing, 2);
   k_scatter_ids<<<nb, 256, 0, st>>>(g.N, ctx->key, ctx->rank, ctx->cellStart, ctx->arrIds, ctx->d.GID);
   k_sort_big_cells<<<148 * 4, 256, 0, st>>>(ctx->bigCells, ctx->bigCap, ctx->dCtr, ctx->cellStart, ctx->arrIds);
@@ -606,8 +605,9 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   }
   TIME_MARK(ctx, timing, 5);
   k_beyond_cap<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);            // few capped rows: a warp each
-  k_cell_lslot_max<<<148 * 8, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr, ctx->cellMaxL);       // many capped rows only
-  k_beyond_cap_dense<<<K4D_BLOCKS, K4D_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr, ctx->cellMaxL);  // many: a thread each (one of the two returns at once)
+  k_back_alloc<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);                // many capped rows (a settled bed): the reverse-edge form;
+  k_back_write<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);             // each of these returns at once in the other regime
+  k_back_sort<<<148 * 8, BSORT_WARPS * 32, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
@@ -689,7 +689,7 @@ static int run_frames(weed_ctx* ctx, double dtRatio, uint32_t frames) {
   if (rc) return rc;
   const bool timing = (ctx->cfg.flags & WEED_FLAG_KERNEL_TIMING) != 0;
   const bool direct = timing || (ctx->cfg.flags & WEED_FLAG_NO_GRAPH);
-  ctx->launchesPerStep = 17 + ((ctx->cfg.flags & WEED_FLAG_K6_TILE) ? 1u : 2u) * (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 18 + ((ctx->cfg.flags & WEED_FLAG_K6_TILE) ? 1u : 2u) * (uint32_t)ctx->phys.subStepCount;
   if (!direct) {
     rc = ensure_graph(ctx);
     if (rc) return rc;
@@ -773,7 +773,7 @@ static int step_pipelined(weed_ctx* ctx, double dtRatio, uint32_t upload_mask, u
     if (rc) return rc;
   }
   const uint32_t early = download_mask & WEED_COLS_INPUT_ALL & ~kLateCols;
-  ctx->launchesPerStep = 17 + ((ctx->cfg.flags & WEED_FLAG_K6_TILE) ? 1u : 2u) * (uint32_t)ctx->phys.subStepCount;
+  ctx->launchesPerStep = 18 + ((ctx->cfg.flags & WEED_FLAG_K6_TILE) ? 1u : 2u) * (uint32_t)ctx->phys.subStepCount;
   rc = launch_spatial(ctx, true, false, waitUp, early ? ctx->evBuilt : nullptr);
   if (rc) return rc;
   if (early) {
@@ -882,7 +882,7 @@ extern "C" int weed_get_stats(weed_ctx* ctx, weed_stats* out) {
   out->cappedRows = c.cappedRows;
   out->explicitPairs = c.explicitPairs;
   out->collisionPairs = c.collisionPairs;
-  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 17 + 2 * (uint32_t)ctx->phys.subStepCount;
+  out->kernelLaunchesPerStep = ctx->launchesPerStep ? ctx->launchesPerStep : 18 + 2 * (uint32_t)ctx->phys.subStepCount;
   memcpy(out->ms, ctx->ms, sizeof(out->ms));
   out->ms[8] = (float)c.frameNs * 1e-6f;   // device clock, k_spatial_begin -> k_physics_end of the last frame
   out->ms[9] = (float)c.xoverRows;         // a count, not a time: capped rows whose lost partners overflowed the internal row

@@ -136,7 +136,7 @@ __device__ __forceinline__ bool big_cell_sorted(uint32_t n) { return n > BIG_CEL
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, uint32_t numTiles,
             unsigned long long* status, Counters* ctr, const int32_t* __restrict__ slabCuts, uint32_t cols, int32_t halo,
-            uint32_t* __restrict__ bigCells, uint32_t bigCap, uint32_t* __restrict__ cellMaxL) {
+            uint32_t* __restrict__ bigCells, uint32_t bigCap) {
   __shared__ uint32_t s_tile, s_excl, s_warp[SCAN_THREADS / 32], s_max[SCAN_THREADS / 32];
   if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scanTile, 1u);
   __syncthreads();
@@ -157,8 +157,6 @@ k_cell_scan(uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellStart, 
     for (int v = 0; v < V; v++) c[v] = reinterpret_cast<const uint4*>(cellCount + i0)[v];
 #pragma unroll
     for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellCount + i0)[v] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int v = 0; v < V; v++) reinterpret_cast<uint4*>(cellMaxL + i0)[v] = make_uint4(0, 0, 0, 0);   // k_cell_lslot_max
   } else {
 #pragma unroll
     for (int v = 0; v < V; v++) c[v] = make_uint4(0, 0, 0, 0);
@@ -272,6 +270,8 @@ struct BySlot {
   uint32_t* LSLOT;   // capped rows: slot of the last listed entry (SLOT_NONE: row not capped)
   uint32_t* CAPLIST; // slots whose row hit the cap this frame (unordered)
   uint32_t* SORTLIST;// slots that received explicit pairs this frame (unordered)
+  uint32_t* BCNT;    // capped rows, dense regime: lost lower-id partners reported to this slot; BCUR: the write cursor
+  uint32_t* BCUR;
   uint32_t* HEAVY;   // slots marked F_XPOOL / F_XOVER this frame (unordered): a warp each in the sweeps (k_sweep_heavy)
   uint32_t* XPID;    // F_XPOOL: which row of the overflow pool continues this entity's internal row
   uint32_t* XR;      // overflow pool: XPOOL_ROW words per pool row (entity-major: one entity's words are consecutive)
@@ -555,6 +555,8 @@ __device__ __forceinline__ void row_finish(const GridDims& g, const BySlot& s, C
     reinterpret_cast<uint32_t*>(s.GA + e)[3] |= F_CAPPED;
     ctr->anyCapped = 1;
     s.CAPLIST[atomicAdd(&ctr->nCapped, 1u)] = e;
+    s.BCNT[e] = 0;
+    s.BCUR[e] = 0;
   }
   s.NCNT[e] = n | (n << 16);          // k_beyond_cap extends the internal part of a capped row
   s.LSLOT[e] = lastApi;
@@ -800,11 +802,15 @@ static constexpr uint32_t XPOOL_ROW = 512;   // entries of one overflow-pool row
 // which keeps every lane busy.  Measured at 16M: 55 k capped rows 0.33 (thread) / 0.14 ms (warp);
 // 3.9 M capped rows 17.7 (thread) / 27.9 ms (warp).
 __device__ __forceinline__ bool beyond_dense_regime(uint32_t nCapped, uint32_t A) { return (unsigned long long)nCapped * 8ull > A; }
+__device__ __forceinline__ void back_count_rows(const GridDims& g, const BySlot& s, uint32_t A);
 static constexpr int K4B_BLOCKS = 148 * 8;
 __global__ void __launch_bounds__(256)
 k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
   const uint32_t nCapped = ctr->nCapped;
-  if (beyond_dense_regime(nCapped, cellStart[g.cells])) return;      // k_beyond_cap_dense takes this frame
+  if (beyond_dense_regime(nCapped, cellStart[g.cells])) {            // a settled bed: reverse edges (below), this launch counts them
+    back_count_rows(g, s, cellStart[g.cells]);
+    return;
+  }
   const uint32_t lane = threadIdx.x & 31, below = (1u << lane) - 1u;
   const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
   for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nCapped; w += warpsTotal) {
@@ -900,123 +906,137 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
   }
 }
 
-// Dense regime only (returns at once otherwise): per cell, the largest "my row is open up to slot ..." bound
-// of its entities — SLOT_NONE's all-ones for an uncapped row.  Consecutive slots share cells, so a warp
-// reduces per cell before the atomic.  k_cell_scan cleared the array.
+// ---- the dense regime (a settled bed: most rows capped): reverse edges instead of a search ---------------------
+// The search above visits every candidate left in the window of every capped entity: 1e10 candidates for the
+// 4 M capped rows of config 4 after 300 frames (cells of 500-1900 entities), 16 ms however the loop is
+// arranged (per-cell skips, LSLOT tested first, heavy slots first: all measured, profiles/README.md).  But the
+// pairs it looks for are already written down, from the other side: t is a lost lower-id partner of e exactly
+// when e sits in t's API row with both membership bits (NS_OUT: t has the lower id; NS_BACK: e's scan accepts
+// t) and t lies past the slot that closed e's row.  So every entity walks its own row once — 4e8 words instead
+// of 1e10 candidates — and reports itself to those partners:
+//   k_beyond_cap (dense branch)  counts the reports per capped entity            (BCNT)
+//   k_back_alloc                 sizes the internal row, draws a pool row, or marks F_XOVER (nothing stored:
+//                                the sweeps resume the scan from LSLOT, as they do for the search's overflow)
+//   k_back_write                 stores the reports through a cursor                (BCUR), in arrival order
+//   k_back_sort                  one warp per capped entity sorts them ascending: the order of the scan
+// Same stored sets, same order, hence the same sweep results as the search, bit for bit.
+__device__ __forceinline__ void back_count_rows(const GridDims& g, const BySlot& s, uint32_t A) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < A; t += gridDim.x * blockDim.x) {
+    const uint32_t n = s.NCNT[t] & 0xFFFFu;
+    for (uint32_t k = 0; k < n; k++) {
+      const uint32_t wd = s.NST[k * g.Npad + t];
+      if ((wd >> 30) != 3u) continue;                    // NS_OUT and NS_BACK
+      const uint32_t e = wd & NS_SLOT_MASK;
+      if (__ldg(s.LSLOT + e) < t) atomicAdd(&s.BCNT[e], 1u);     // SLOT_NONE (row not capped) is never below t
+    }
+  }
+}
+
+static constexpr uint32_t BACK_XOVER = 0x80000000u;   // BCNT: more reports than the internal row and a pool row hold
 __global__ void __launch_bounds__(256)
-k_cell_lslot_max(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
-                 uint32_t* __restrict__ cellMaxL) {
+k_back_alloc(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr) {
+  const uint32_t nCapped = ctr->nCapped;
+  if (!beyond_dense_regime(nCapped, cellStart[g.cells])) return;
+  const uint32_t room = g.Mint - g.M;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nCapped; w += gridDim.x * blockDim.x) {
+    const uint32_t e = s.CAPLIST[w];
+    const uint32_t c = s.BCNT[e];
+    if (c == 0) continue;                                // NCNT and the padding are row_finish's
+    uint32_t add = 0, inRow = g.M + min(c, room);
+    if (c > room) {
+      uint32_t pid = SLOT_NONE;
+      if (c - room <= XPOOL_ROW) {
+        pid = atomicAdd(&ctr->xpoolUsed, 1u);
+        if (pid >= g.xpoolRows) pid = SLOT_NONE;
+      }
+      if (pid != SLOT_NONE) {
+        const uint32_t m = c - room;
+        add = F_XPOOL;
+        s.XPID[e] = pid;
+        s.XRCNT[pid] = m;
+        for (uint32_t k = m; k < ((m + 3u) & ~3u); k++) s.XR[(size_t)pid * XPOOL_ROW + k] = e;   // padding: no membership bit
+      } else {
+        add = F_XOVER;
+        inRow = g.M;
+        s.BCNT[e] = c | BACK_XOVER;
+        atomicAdd(&ctr->xoverRows, 1u);
+      }
+      reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
+      reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
+      s.HEAVY[atomicAdd(&ctr->nHeavy, 1u)] = e;
+    }
+    if (inRow > g.M) {
+      s.NCNT[e] = g.M | (inRow << 16);
+      row_tail_fill(g, s, e, inRow);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_back_write(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr) {
   const uint32_t A = cellStart[g.cells];
   if (!beyond_dense_regime(ctr->nCapped, A)) return;
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < A; t0 += gridDim.x * blockDim.x) {
-    const uint32_t t = t0 + lane;
-    uint32_t cell = 0xFFFFFFFFu, v = 0;
-    if (t < A) {
-      const float4 c = s.CXY[t];
-      int32_t col, row;
-      cell_of(g, c.x, c.y, col, row);
-      cell = (uint32_t)row * g.cols + (uint32_t)col;
-      v = s.LSLOT[t];                                  // SLOT_NONE = 0xFFFFFFFF: an open row accepts every later slot
+  const uint32_t room = g.Mint - g.M;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < A; t += gridDim.x * blockDim.x) {
+    const uint32_t n = s.NCNT[t] & 0xFFFFu;
+    for (uint32_t k = 0; k < n; k++) {
+      const uint32_t wd = s.NST[k * g.Npad + t];
+      if ((wd >> 30) != 3u) continue;
+      const uint32_t e = wd & NS_SLOT_MASK;
+      if (!(__ldg(s.LSLOT + e) < t)) continue;
+      if (s.BCNT[e] & BACK_XOVER) continue;              // nothing is stored for it
+      const uint32_t pos = atomicAdd(&s.BCUR[e], 1u);
+      if (pos < room) s.NST[(g.M + pos) * g.Npad + e] = t | NS_BACK;
+      else s.XR[(size_t)s.XPID[e] * XPOOL_ROW + (pos - room)] = t | NS_BACK;
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, cell);
-    const uint32_t m = __reduce_max_sync(peers, v);
-    if (t < A && lane == (uint32_t)(__ffs(peers) - 1)) atomicMax(&cellMaxL[cell], m);
   }
 }
 
-__device__ __forceinline__ void beyond_cap_one(const GridDims& g, const BySlot& s, const uint32_t* __restrict__ cellStart,
-                                               Counters* ctr, const uint32_t* __restrict__ cellMaxL, uint32_t e) {
-  const uint32_t last = s.LSLOT[e];
-  if (last == SLOT_NONE) return;                       // row not capped: nothing was lost
-  const float4 me = s.CXY[e];
-  const uint32_t id = __float_as_uint(me.w) & ~CX_EDGE;
-  const uint32_t vrBits = __float_as_uint(me.z);
-  const double myX = me.x, myY = me.y, vrSq = dmul((double)me.z, (double)me.z);
-  const float vrSqF = me.z * me.z * 1.00001f;
-  int32_t myCol, myRow;
-  cell_of(g, me.x, me.y, myCol, myRow);
-  const int4 win = s.WIN[e];
-  uint32_t n = g.M;                                   // entries of the internal row
-  uint32_t pid = SLOT_NONE, m = 0;                    // overflow-pool row and its entries
-  bool xover = false;
-  for (int32_t row = win.x; row <= win.y && !xover; row++) {
-   const uint32_t rowBase = (uint32_t)row * g.cols;
-   uint32_t cellA = cellStart[rowBase + win.z];
-   for (int32_t col = win.z; col <= win.w && !xover; col++) {
-    // A candidate counts only if its row is open or closed at or after me (LSLOT >= e); cellMaxL holds the
-    // largest such bound of a cell (k_cell_lslot_max), so a pile whose rows all closed before me is skipped whole.
-    const uint32_t b = cellStart[rowBase + col + 1];
-    uint32_t t = max(cellA, last + 1u);
-    cellA = b;
-    if (t >= b || e > cellMaxL[rowBase + col]) continue;
-    for (; t < b && !xover; t += 4) {
-      // In a pile nearly every row closed long before it reached me: test that first, on four 4-byte words,
-      // before any 16-byte candidate record is fetched (SLOT_NONE, an open row, is all ones: never below me).
-      uint32_t lk[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) lk[u] = __ldg(s.LSLOT + min(t + (uint32_t)u, b - 1));
-      if (e > lk[0] && e > lk[1] && e > lk[2] && e > lk[3]) continue;
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t tc = t + (uint32_t)u;
-        if (tc >= b) break;
-        if (e > lk[u]) continue;                       // its row closed before it reached me
-        const float4 c = __ldg(s.CXY + tc);
-        const uint32_t jid = __float_as_uint(c.w) & ~CX_EDGE;
-        if (jid >= id) continue;                       // higher ids past my cap: my own pairs, lost as in the reference
-        const float fx = c.x - me.x, fy = c.y - me.y;
-        if (__fmaf_rn(fx, fx, fy * fy) > vrSqF) continue;
-        const double dX = dsub((double)c.x, myX), dY = dsub((double)c.y, myY);
-        const double d2 = dadd(dmul(dX, dX), dmul(dY, dY));
-        if (!(d2 < vrSq && d2 > 0)) continue;
-        if (!scan_accepts(g, s, tc, myX, myY, myCol, myRow, vrBits)) continue;
-        if (n < g.Mint) { s.NST[n * g.Npad + e] = tc | NS_BACK; n++; continue; }
-        if (pid == SLOT_NONE) {                        // internal row full: continue in the overflow pool
-          pid = atomicAdd(&ctr->xpoolUsed, 1u);
-          if (pid >= g.xpoolRows) { pid = SLOT_NONE; xover = true; break; }
+static constexpr int BSORT_WARPS = 4, BSORT_CAP = 1024;      // room (at most 128) + XPOOL_ROW = 640 entries at most
+__global__ void __launch_bounds__(BSORT_WARPS * 32)
+k_back_sort(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr) {
+  __shared__ uint32_t sm[BSORT_WARPS][BSORT_CAP];
+  const uint32_t nCapped = ctr->nCapped;
+  if (!beyond_dense_regime(nCapped, cellStart[g.cells])) return;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t room = g.Mint - g.M;
+  const uint32_t warpsTotal = gridDim.x * BSORT_WARPS;
+  for (uint32_t w = blockIdx.x * BSORT_WARPS + warp; w < nCapped; w += warpsTotal) {
+    const uint32_t e = s.CAPLIST[w];
+    const uint32_t c = s.BCNT[e];
+    if (c < 2 || (c & BACK_XOVER)) continue;
+    const uint32_t* pool = c > room ? s.XR + (size_t)s.XPID[e] * XPOOL_ROW : nullptr;
+    auto get = [&](uint32_t k) { return k < room ? s.NST[(g.M + k) * g.Npad + e] : pool[k - room]; };
+    auto put = [&](uint32_t k, uint32_t v) { if (k < room) s.NST[(g.M + k) * g.Npad + e] = v; else const_cast<uint32_t*>(pool)[k - room] = v; };
+    if (c <= 32) {                                       // one entry per lane, bitonic network over the warp
+      uint32_t v = lane < c ? get(lane) : 0xFFFFFFFFu;
+      for (uint32_t k = 2; k <= 32; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+          const bool keepMin = ((lane & k) == 0) == ((lane & j) == 0);
+          v = keepMin ? min(v, o) : max(v, o);
         }
-        if (m >= XPOOL_ROW) { xover = true; break; }
-        s.XR[(size_t)pid * XPOOL_ROW + m] = tc | NS_BACK;
-        m++;
-      }
+      if (lane < c) put(lane, v);
+    } else {
+      uint32_t P = 64;
+      while (P < c) P <<= 1;
+      uint32_t* a = sm[warp];
+      for (uint32_t k = lane; k < P; k += 32) a[k] = k < c ? get(k) : 0xFFFFFFFFu;
+      __syncwarp();
+      for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t idx = lane; idx < P; idx += 32) {
+            const uint32_t ixj = idx ^ j;
+            if (ixj > idx) {
+              const uint32_t x0 = a[idx], x1 = a[ixj];
+              if ((x0 > x1) == ((idx & k) == 0)) { a[idx] = x1; a[ixj] = x0; }
+            }
+          }
+          __syncwarp();
+        }
+      for (uint32_t k = lane; k < c; k += 32) put(k, a[k]);
+      __syncwarp();
     }
-   }
-  }
-  uint32_t add = xover ? F_XOVER : 0u;
-  if (pid != SLOT_NONE) {
-    add |= F_XPOOL;
-    s.XPID[e] = pid;
-    s.XRCNT[pid] = m;
-    for (uint32_t k = m; k < ((m + 3u) & ~3u); k++) s.XR[(size_t)pid * XPOOL_ROW + k] = e;   // padding: no membership bit
-  }
-  if (add) {
-    reinterpret_cast<uint32_t*>(s.SA + 2 * (size_t)e)[3] |= add;
-    reinterpret_cast<uint32_t*>(s.GA + e)[3] |= add;
-    s.HEAVY[atomicAdd(&ctr->nHeavy, 1u)] = e;
-    if (xover) atomicAdd(&ctr->xoverRows, 1u);
-  }
-  if (n > g.M) {
-    s.NCNT[e] = g.M | (n << 16);
-    row_tail_fill(g, s, e, n);
-  }
-}
-
-static constexpr int K4D_THREADS = 128, K4D_BLOCKS = 148 * 9;     // one wave (52 registers: 9 blocks of 128 per SM)
-__global__ void __launch_bounds__(K4D_THREADS)
-k_beyond_cap_dense(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Counters* ctr,
-                   const uint32_t* __restrict__ cellMaxL) {
-  const uint32_t A = cellStart[g.cells];
-  if (!beyond_dense_regime(ctr->nCapped, A)) return;   // k_beyond_cap took this frame
-  // One resident wave of threads strides over the slots from the top: the settled bed lies in the last cell rows
-  // and its entities cost hundreds of times more than the others, so they start first and spread over all warps
-  // (a second wave of blocks left the SMs uneven: 57 % busy; chunks drawn from a counter per block stalled the
-  // block on its slowest warp, per warp they were too coarse for the 1790 heavy chunks of config 3).
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t groups = (A + stride - 1u) / stride;
-  for (uint32_t k = 0; k < groups; k++) {
-    const uint32_t e = (groups - 1u - k) * stride + blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < A) beyond_cap_one(g, s, cellStart, ctr, cellMaxL, e);
   }
 }
 
