@@ -607,7 +607,7 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
   k_beyond_cap<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);            // few capped rows: a warp each
   k_back_alloc<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);                // many capped rows (a settled bed): the reverse-edge form;
   k_back_write<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);             // each of these returns at once in the other regime
-  k_back_sort<<<148 * 8, BSORT_WARPS * 32, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  k_back_sort<<<148 * BSORT_BLOCKS_PER_SM, BSORT_WARPS * 32, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   k_sort_lists<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());

@@ -923,11 +923,16 @@ k_beyond_cap(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, Count
 __device__ __forceinline__ void back_count_rows(const GridDims& g, const BySlot& s, uint32_t A) {
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < A; t += gridDim.x * blockDim.x) {
     const uint32_t n = s.NCNT[t] & 0xFFFFu;
-    for (uint32_t k = 0; k < n; k++) {
-      const uint32_t wd = s.NST[k * g.Npad + t];
-      if ((wd >> 30) != 3u) continue;                    // NS_OUT and NS_BACK
-      const uint32_t e = wd & NS_SLOT_MASK;
-      if (__ldg(s.LSLOT + e) < t) atomicAdd(&s.BCNT[e], 1u);     // SLOT_NONE (row not capped) is never below t
+    for (uint32_t k = 0; k < n; k += 4) {                // four row words, then their partners' LSLOT, in flight together
+      uint32_t wd[4], lk[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++) wd[u] = k + u < n ? s.NST[(k + u) * g.Npad + t] : 0u;
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++)                   // NS_OUT and NS_BACK; SLOT_NONE (row not capped) is never below t
+        lk[u] = (wd[u] >> 30) == 3u ? __ldg(s.LSLOT + (wd[u] & NS_SLOT_MASK)) : SLOT_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++)
+        if (lk[u] < t) atomicAdd(&s.BCNT[wd[u] & NS_SLOT_MASK], 1u);
     }
   }
 }
@@ -979,21 +984,32 @@ k_back_write(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
   const uint32_t room = g.Mint - g.M;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < A; t += gridDim.x * blockDim.x) {
     const uint32_t n = s.NCNT[t] & 0xFFFFu;
-    for (uint32_t k = 0; k < n; k++) {
-      const uint32_t wd = s.NST[k * g.Npad + t];
-      if ((wd >> 30) != 3u) continue;
-      const uint32_t e = wd & NS_SLOT_MASK;
-      if (!(__ldg(s.LSLOT + e) < t)) continue;
-      if (s.BCNT[e] & BACK_XOVER) continue;              // nothing is stored for it
-      const uint32_t pos = atomicAdd(&s.BCUR[e], 1u);
-      if (pos < room) s.NST[(g.M + pos) * g.Npad + e] = t | NS_BACK;
-      else s.XR[(size_t)s.XPID[e] * XPOOL_ROW + (pos - room)] = t | NS_BACK;
+    for (uint32_t k = 0; k < n; k += 4) {
+      uint32_t wd[4], lk[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++) wd[u] = k + u < n ? s.NST[(k + u) * g.Npad + t] : 0u;
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++)
+        lk[u] = (wd[u] >> 30) == 3u ? __ldg(s.LSLOT + (wd[u] & NS_SLOT_MASK)) : SLOT_NONE;
+#pragma unroll
+      for (uint32_t u = 0; u < 4; u++) {
+        if (!(lk[u] < t)) continue;
+        const uint32_t e = wd[u] & NS_SLOT_MASK;
+        if (s.BCNT[e] & BACK_XOVER) continue;            // nothing is stored for it
+        const uint32_t pos = atomicAdd(&s.BCUR[e], 1u);
+        if (pos < room) s.NST[(g.M + pos) * g.Npad + e] = t | NS_BACK;
+        else s.XR[(size_t)s.XPID[e] * XPOOL_ROW + (pos - room)] = t | NS_BACK;
+      }
     }
   }
 }
 
 static constexpr int BSORT_WARPS = 4, BSORT_CAP = 1024;      // room (at most 128) + XPOOL_ROW = 640 entries at most
-__global__ void __launch_bounds__(BSORT_WARPS * 32)
+// Latency-bound (gather the entries, sort, scatter them back: three dependent round trips per entity): as many
+// resident warps as the registers allow, one wave.  A thread-local network for the short lists was slower
+// (2.8 vs 2.0 ms at 16 M, frame 300): the lists of a pile are not short.
+static constexpr int BSORT_BLOCKS_PER_SM = 12;
+__global__ void __launch_bounds__(BSORT_WARPS * 32, BSORT_BLOCKS_PER_SM)
 k_back_sort(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr) {
   __shared__ uint32_t sm[BSORT_WARPS][BSORT_CAP];
   const uint32_t nCapped = ctr->nCapped;
@@ -1001,6 +1017,8 @@ k_back_sort(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t room = g.Mint - g.M;
   const uint32_t warpsTotal = gridDim.x * BSORT_WARPS;
+  // one list per warp and step (32 list heads per step, then their sorts one after the other, was no faster at
+  // 16 M and slower at 1 M: the sorts, not the heads, are the work)
   for (uint32_t w = blockIdx.x * BSORT_WARPS + warp; w < nCapped; w += warpsTotal) {
     const uint32_t e = s.CAPLIST[w];
     const uint32_t c = s.BCNT[e];
@@ -1432,7 +1450,7 @@ __device__ __forceinline__ void lanes_apply(const LaneMove& lm, bool valid, Subs
 
 static constexpr int K6H_THREADS = 256, K6H_BLOCKS = 148 * 4;
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(K6H_THREADS)
+__global__ void __launch_bounds__(K6H_THREADS, 4)            // latency-bound: 32 resident warps per SM, one wave
 k_sweep_heavy(GridDims g, const Params* __restrict__ pp, BySlot s, const float4* __restrict__ Gin,
               float4* __restrict__ Gout, const uint32_t* __restrict__ cellStart, const Counters* __restrict__ ctr,
               uint32_t substep) {
