@@ -173,6 +173,8 @@ struct weed_ctx {
   // second stream + events of the pipelined weed_step (column copies overlap the frame)
   cudaStream_t copyStream = nullptr;
   cudaEvent_t evUp = nullptr, evBuilt = nullptr, evCopied = nullptr;
+  cudaStream_t sideStream = nullptr;                 // k_sweep_heavy beside k_sweep, k_sort_lists beside the cap path (fork / join, also under capture)
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   // graph of one full frame
   cudaGraphExec_t frameGraph = nullptr;
   int graphSubSteps = -1;
@@ -307,7 +309,8 @@ extern "C" void weed_destroy(weed_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
-  for (cudaEvent_t e : {ctx->evUp, ctx->evBuilt, ctx->evCopied})
+  if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
+  for (cudaEvent_t e : {ctx->evUp, ctx->evBuilt, ctx->evCopied, ctx->evFork, ctx->evJoin})
     if (e) cudaEventDestroy(e);
   if (ctx->frameGraph) cudaGraphExecDestroy(ctx->frameGraph);
   for (int b = 0; b < WEED_BUF_COUNT; b++)
@@ -364,6 +367,9 @@ extern "C" int weed_create(const weed_config* cfg, weed_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return bail(WEED_E_CUDA); }
     ctx->ownStream = true;
   }
+  if (cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "side stream / events failed"; return bail(WEED_E_CUDA); }
   GridDims& g = ctx->g;
   g.inv = 1.0 / cfg->cellSize;                     // spatial_worker.js:81
   g.worldW = cfg->worldWidth; g.worldH = cfg->worldHeight;
@@ -604,11 +610,16 @@ static int launch_spatial(weed_ctx* ctx, bool integrate, bool timing, cudaEvent_
     else         k_neighbors2<false><<<kb, K4V2_THREADS, 0, st>>>(g, ctx->s, ctx->cellStart, nullptr, nullptr, ctx->dCtr);
   }
   TIME_MARK(ctx, timing, 5);
+  // explicit lists (K4's own pushes) are sorted beside the cap path: nothing in common but their predecessor
+  CK(cudaEventRecord(ctx->evFork, st));
+  CK(cudaStreamWaitEvent(ctx->sideStream, ctx->evFork, 0));
+  k_sort_lists<<<148 * 4, 256, 0, ctx->sideStream>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  CK(cudaEventRecord(ctx->evJoin, ctx->sideStream));
   k_beyond_cap<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);            // few capped rows: a warp each
   k_back_alloc<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);                // many capped rows (a settled bed): the reverse-edge form;
   k_back_write<<<K4B_BLOCKS, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);             // each of these returns at once in the other regime
   k_back_sort<<<148 * BSORT_BLOCKS_PER_SM, BSORT_WARPS * 32, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
-  k_sort_lists<<<148 * 4, 256, 0, st>>>(g, ctx->s, ctx->cellStart, ctx->dCtr);
+  CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));
   TIME_MARK(ctx, timing, 6);
   CK(cudaGetLastError());
   return WEED_OK;
@@ -635,18 +646,24 @@ static int launch_constraints(weed_ctx* ctx, bool timing) {
       else                     k_sweep_tile<false, false><<<sb, TILE, 0, st>>>(SWEEP_ARGS);
     } else {
       const unsigned sb = blocks_for(g.N, K6V2_THREADS);
+      if (HEAVY_SPLIT) {       // the popular entities of piles (F_XPOOL / F_XOVER), a warp each, on a parallel branch: other entities,
+                               // same input, so the few long warps run beside k_sweep instead of after it
+        cudaStream_t hs = ctx->sideStream;
+        CK(cudaEventRecord(ctx->evFork, st));
+        CK(cudaStreamWaitEvent(hs, ctx->evFork, 0));
+#define HEAVY_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step
+        if (first && last)     k_sweep_heavy<true, true><<<K6H_BLOCKS, K6H_THREADS, 0, hs>>>(HEAVY_ARGS);
+        else if (first)        k_sweep_heavy<true, false><<<K6H_BLOCKS, K6H_THREADS, 0, hs>>>(HEAVY_ARGS);
+        else if (last)         k_sweep_heavy<false, true><<<K6H_BLOCKS, K6H_THREADS, 0, hs>>>(HEAVY_ARGS);
+        else                   k_sweep_heavy<false, false><<<K6H_BLOCKS, K6H_THREADS, 0, hs>>>(HEAVY_ARGS);
+#undef HEAVY_ARGS
+        CK(cudaEventRecord(ctx->evJoin, hs));
+      }
       if (first && last)       k_sweep<true, true><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
       else if (first)          k_sweep<true, false><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
       else if (last)           k_sweep<false, true><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
       else                     k_sweep<false, false><<<sb, K6V2_THREADS, 0, st>>>(SWEEP_ARGS);
-      if (HEAVY_SPLIT) {       // the popular entities of piles (F_XPOOL / F_XOVER), a warp each; returns at once when there are none
-#define HEAVY_ARGS g, ctx->dParams, ctx->s, in, out, ctx->cellStart, ctx->dCtr, (uint32_t)step
-        if (first && last)     k_sweep_heavy<true, true><<<K6H_BLOCKS, K6H_THREADS, 0, st>>>(HEAVY_ARGS);
-        else if (first)        k_sweep_heavy<true, false><<<K6H_BLOCKS, K6H_THREADS, 0, st>>>(HEAVY_ARGS);
-        else if (last)         k_sweep_heavy<false, true><<<K6H_BLOCKS, K6H_THREADS, 0, st>>>(HEAVY_ARGS);
-        else                   k_sweep_heavy<false, false><<<K6H_BLOCKS, K6H_THREADS, 0, st>>>(HEAVY_ARGS);
-#undef HEAVY_ARGS
-      }
+      if (HEAVY_SPLIT) CK(cudaStreamWaitEvent(st, ctx->evJoin, 0));
     }
 #undef SWEEP_ARGS
     if (!last) in = out;     // k_pair_emit re-derives the pairs on the LAST sweep's input
