@@ -43,8 +43,9 @@ TRAFFIC_FROM_NCU = {          # bytes per launch, profiles/r2_ncu_config4_16M_fi
     "k_build_slots+k_slot_prep": 3.226e9,         # 0.80 + 1.01 and 0.51 + 0.91
 }
 
-KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids+k_slot_rank", "k_build_slots+k_slot_prep", "k_neighbors2",
-                "k_beyond_cap+k_sort_lists", "k_sweep", "k_writeback+k_pair_scan+k_pair_emit"]
+KERNEL_NAMES = ["k_cell_key", "k_cell_scan", "k_scatter_ids+k_sort_big_cells+k_slot_rank", "k_build_slots+k_slot_prep", "k_neighbors2",
+                "k_beyond_cap+k_back_alloc+k_back_write+k_back_sort+k_sort_lists", "k_sweep", "k_writeback+k_pair_scan+k_pair_emit"]
+# ("k_sweep": one launch of k_sweep with its k_sweep_heavy branch beside it)
 # algorithmic bytes per active entity of each timed span (SURVEY 8 d); spans without compulsory
 # traffic of their own (the cap path, the pair log) can never be the "dominant kernel" of the roofline line
 def span_bytes(kbar):

@@ -153,8 +153,9 @@ typedef struct weed_stats {
   uint32_t collisionPairs;       /* pairs found in the last substep (uncapped)          */
   uint32_t kernelLaunchesPerStep;
   float    ms[12];               /* WEED_FLAG_KERNEL_TIMING: ms of the last frame's spans: 0 k_cell_key,
-                                    1 k_cell_scan, 2 k_scatter_ids+k_slot_rank, 3 k_build_slots+k_slot_prep, 4 k_neighbors2,
-                                    5 k_beyond_cap+k_sort_lists, 6 all k_sweep launches,
+                                    1 k_cell_scan, 2 k_scatter_ids+k_sort_big_cells+k_slot_rank, 3 k_build_slots+k_slot_prep,
+                                    4 k_neighbors2, 5 the cap path (k_beyond_cap, k_back_alloc/_write/_sort, k_sort_lists),
+                                    6 all k_sweep launches with their k_sweep_heavy branches,
                                     7 k_writeback+k_pair_scan+k_pair_emit;
                                     always: 8 = the last frame on the device clock
                                     (%globaltimer, first to last kernel); 9 = a COUNT: capped rows
