@@ -1473,17 +1473,22 @@ k_sweep_heavy(GridDims g, const Params* __restrict__ pp, BySlot s, const float4*
     if ((fw & F_COLLIDER) == F_COLLIDER) {
       const uint32_t cnt = s.NCNT[e] >> 16;
       uint32_t lastStored = cnt ? (s.NST[(cnt - 1) * g.Npad + e] & NS_SLOT_MASK) : 0u;
-      // row words rp[0], rp[stride], ...: 32 at a time
+      // row words rp[0], rp[stride], ...: 32 at a time, two batches ahead — the words of batch i+2 and the partner
+      // records of batch i+1 are in flight while batch i is evaluated (the walk is a chain of dependent gathers)
       auto walk = [&](const uint32_t* __restrict__ rp, uint32_t stride, uint32_t n) {
+        auto word = [&](uint32_t kb) { const uint32_t k = kb + lane; return k < n ? rp[k * stride] : 0u; };
+        auto rec = [&](uint32_t wd) { return wd >= NS_OUT ? __ldg(slot_rec(Gin, wd & NS_SLOT_MASK)) : make_float4(0.f, 0.f, 0.f, 0.f); };
+        uint32_t wd0 = word(0), wd1 = word(32);
+        float4 gt0 = rec(wd0);
         for (uint32_t kb = 0; kb < n; kb += 32) {
-          const uint32_t k = kb + lane;
-          const uint32_t wd = k < n ? rp[k * stride] : 0u;
+          const float4 gt1 = rec(wd1);
+          const uint32_t wd2 = word(kb + 64);
+          const uint32_t wd = wd0;
+          const float4 gt = gt0;
           bool cand = wd >= NS_OUT;                                // OUT or BACK set (padding words carry neither)
           const uint32_t t = wd & NS_SLOT_MASK;
           const bool lower = (wd & NS_OUT) != 0;
-          float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
           if (cand) {
-            gt = __ldg(slot_rec(Gin, t));
             const uint32_t ft = __float_as_uint(gt.w);
             cand = (ft & F_COLLIDER) == F_COLLIDER && !surely_apart(x, y, r, gt.x, gt.y, gt.z) &&
                    (lower || in_row_of(s, ft, t, e));
@@ -1491,6 +1496,7 @@ k_sweep_heavy(GridDims g, const Params* __restrict__ pp, BySlot s, const float4*
           LaneMove lm; lm.hit = lm.out = lm.move = false; lm.ax = lm.ay = 0;
           if (cand) lm = lane_pair(p, s, frame, substep, e, x, y, r, fw, t, gt, lower);
           lanes_apply(lm, cand, acc);
+          wd0 = wd1; wd1 = wd2; gt0 = gt1;
         }
       };
       walk(s.NST + e, g.Npad, cnt);
