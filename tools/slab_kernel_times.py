@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Device time of the slab phases on ONE GPU: all slabs of a world in one process (SlabGroup),
+"""Device time of the slab phases on ONE GPU: all slabs of a world in one process (SlabGroup in its
+"nccl-buffers" mode: weed_slab_pack / weed_slab_apply with a device-to-device copy in between — the
+staging path, whose pack and apply kernels are the ones the peer-to-peer transport runs too),
 CUDA events on the shared stream around frame / pack / apply of slab 0.  Single process, so it
 may run under ncu."""
 import argparse
@@ -21,7 +23,7 @@ a = ap.parse_args()
 cfg, cols = bench.workload(a.workload, a.entities)
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
-    g = SlabGroup(cfg, cols, a.world, stream=stream.cuda_stream)
+    g = SlabGroup(cfg, cols, a.world, mode="nccl-buffers", stream=stream.cuda_stream)
     for _ in range(2):
         g.step()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
