@@ -1,17 +1,25 @@
 // weed_kernels.cuh — the per-frame kernels (sm_100a).  See DESIGN.md for the data flow.
 //
 //   id order   k_cell_key      K1  cell key + arrival rank (one L2 atomic per entity)
-//   cells      k_cell_scan     K2  exclusive scan, single pass, decoupled look-back
+//   cells      k_cell_scan     K2  exclusive scan, single pass, decoupled look-back; lists the cells above BIG_CELL
 //   id order   k_scatter_ids   K3a ids into their cell segment (arrival order)
-//   id order   k_slot_rank     K3b stable position inside the cell (ascending id)
+//   cells      k_sort_big_cells    the id lists of piles (cells above 128 entities), a block each
+//   id order   k_slot_rank     K3b stable position inside the cell (ascending id): count, or binary search in a sorted pile
 //   id order   k_build_slots   K3c Verlet integration (K5) + derived speed/angle fused, one 32 B
 //                                  slot record per entity (the only scattered write)
 //   slot order k_slot_prep     K3d query positions, candidate records, scan windows, list heads,
-//                                  first bounds pass
-//   slot order k_neighbors     K4  capped ordered gather, thread per entity, fp32 pre-filter,
-//                                  warp-cooperative coalesced row flush (k_neighbors_wide: warp
-//                                  per entity for long rows); k_capped_rescan, k_sort_lists K4b/c
-//   slot order k_substep<LAST> K6  circle-circle correction, J-order (+ next sweep's bounds)
+//                                  first bounds pass, first sweep's input
+//   slot order k_neighbors2    K4  capped ordered gather, thread per entity: float32 pre-filter into a queue, converged
+//                                  binary64 pass, API rows as slot-major planes (k_neighbors_wide: warp per entity
+//                                  for long rows)
+//   slot order k_beyond_cap    K4b lower-id partners a capped row lost.  Few capped rows: a warp per capped entity
+//                                  resumes its scan.  Many (a settled bed): reverse edges — every entity reports
+//                                  itself to the partners of its own row (count here, k_back_alloc, k_back_write,
+//                                  k_back_sort)
+//              k_sort_lists    K4c explicit (asymmetric) pair lists into slot order; parallel branch
+//   slot order k_sweep<F,L>    K6  circle-circle correction, J-order (+ next sweep's bounds); k_sweep_heavy beside it:
+//                                  a warp per entity with an overflow-pool row or a resumed scan
+//                                  (k_sweep_tile: the TMA-staged form, selectable, slower)
 //   id order   k_writeback     WB  gather results by id; per-tile outgoing pair counts
 //   tiles      k_pair_scan     K7a prefix of the tile counts, pair count
 //   id order   k_pair_emit     K7b collisionData emission by the tiles below the cap
