@@ -1012,7 +1012,8 @@ k_back_write(GridDims g, BySlot s, const uint32_t* __restrict__ cellStart, const
   }
 }
 
-static constexpr int BSORT_WARPS = 4, BSORT_CAP = 1024;      // room (at most 128) + XPOOL_ROW = 640 entries at most
+static constexpr int BSORT_WARPS = 4, BSORT_CAP = 1024;      // room (at most 128 + the padding of M to a multiple of 4) + XPOOL_ROW entries at most
+static_assert(BSORT_CAP >= 132 + (int)XPOOL_ROW, "k_back_sort stages a whole list (internal-row extension + pool row) in shared memory");
 // Latency-bound (gather the entries, sort, scatter them back: three dependent round trips per entity): as many
 // resident warps as the registers allow, one wave.  A thread-local network for the short lists was slower
 // (2.8 vs 2.0 ms at 16 M, frame 300): the lists of a pile are not short.
