@@ -9,6 +9,8 @@ entities) are therefore compared with the oracle, not only with themselves.
   config 4 at 400 k   mixed radii, clusters piled on the walls (cap path, explicit lists), 5 frames
   config 3 at 1 M     its full size, 5 frames
   config 2            10 000 prey + 500 predators, maxNeighbors 1500 (its real size), 4 frames
+  piles               200 / 1500 / 5000 entities in single cells over a dense scene: sorted cell lists, the reverse-edge
+                      cap path of the dense regime, the warp-per-entity sweep of pool / resumed-scan entities, 3 frames
   config 4 at 16 M    its full size, 2 frames: `pytest -m gpu --runslow` (about two minutes of CPU oracle)
 
 Tolerance: none for integer/position work (bit-exact); velocityAngle 1 float32 ulp (device atan2 vs
