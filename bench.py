@@ -170,7 +170,7 @@ def oracle_for(cfg, cols):
     return o
 
 
-def cpu_reference(name, steps, warmup, sample_entities, lockstep_frames=None):
+def cpu_reference(name, steps, warmup, sample_entities, lockstep_frames=None, budget_s=None):
     """The reference's CPU structure: ONE spatial worker thread + ONE physics worker thread,
     free-running on shared buffers (gameEngine.js:978-996, AbstractWorker.js:114-146),
     restated in C (oracle/weed_oracle.c).  sample_entities=None runs the workload at its full
@@ -179,7 +179,19 @@ def cpu_reference(name, steps, warmup, sample_entities, lockstep_frames=None):
     o = oracle_for(cfg, cols)
     S = cfg["physics"]["subStepCount"]
     active = int(cols["T.active"].sum())
-    if warmup:
+    asked = (steps, warmup)
+    if budget_s and warmup + steps > 1:
+        # a full-size frame costs seconds on the host: time the first warm-up frame and, if the whole run would not
+        # fit the budget, shorten the warm-up first (to one frame), then the timed frames (to two at least)
+        ts1, tp1 = o.bench(1, 1.0, freerun=True)
+        per1 = max(ts1, tp1)
+        fit = max(3, int(budget_s / max(per1, 1e-9)))          # frames the budget pays for, the first one included
+        if 1 + max(0, warmup - 1) + steps > fit:
+            warmup = 1
+            steps = max(2, min(steps, fit - 1))
+        if warmup > 1:
+            o.bench(warmup - 1, 1.0, freerun=True)
+    elif warmup:
         o.bench(warmup, 1.0, freerun=True)
     ts, tp = o.bench(steps, 1.0, freerun=True)
     t = max(ts, tp)
@@ -194,9 +206,10 @@ def cpu_reference(name, steps, warmup, sample_entities, lockstep_frames=None):
             else f"{name} at full size ({cfg['entityCount'] - 1} entities)")
     return {
         "value": active * S * steps / t, "unit": UNIT, "cores": 2, "kind": "port",
-        "sample": f"{what}, {steps} frames after {warmup} warm-up frames, "
+        "sample": f"{what}, {steps} frames after {warmup} warm-up frames"
+                  + (f" (asked for {asked[0]} after {asked[1]}: shortened to fit --ref-budget-s)" if (steps, warmup) != asked else "") + ", "
                   f"2 free-running threads (spatial {ts / steps * 1e3:.1f} ms/frame, physics {tp / steps * 1e3:.1f} ms/frame)" + lock_note,
-        "sampled": sampled, "sample_entities": cfg["entityCount"],
+        "sampled": sampled, "sample_entities": cfg["entityCount"], "steps_run": steps, "warmup_run": warmup,
         "host_cores_available": len(os.sched_getaffinity(0)),
     }, cfg, t / steps
 
@@ -209,7 +222,7 @@ def run_reference(args):
     # the reference arm runs the SAME workload as the GPU arm (config4 at 16M: ~6 s per frame on two host
     # threads); --cpu-sample N runs a scaled instance instead and is then labelled as such
     sample = args.cpu_sample if args.cpu_sample else args.entities
-    base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, sample, lockstep_frames=0)
+    base, cfg, per = cpu_reference(args.workload, args.steps, args.warmup, sample, lockstep_frames=0, budget_s=args.ref_budget_s)
     conf = describe(args.workload, cfg)
     if base["sampled"]:
         conf["workload"] += " [scaled sample of the workload: --cpu-sample]"
@@ -219,7 +232,7 @@ def run_reference(args):
             "config": conf,
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.time() - t0}
+            "gpu_launches": 0, "wall_s": time.time() - t0, "steps_run": base["steps_run"], "warmup_run": base["warmup_run"]}
     line["config"]["note"] = ("CPU restatement (C port) of the reference's JS spatial+physics workers; no JavaScript engine "
                               "exists in this image, so the original cannot be executed")
     print(json.dumps(line))
@@ -553,6 +566,9 @@ def main():
                     help="entities of a scaled CPU sample (default: 400000 for the cpu_baseline leg of the GPU arm; "
                          "--impl reference runs the full workload unless this is given)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--ref-budget-s", type=float, default=270.0,
+                    help="--impl reference: seconds of host time the oracle frames may take; a run that would not fit is shortened "
+                         "(warm-up first, then timed frames) and says so (0 = run exactly --steps after --warmup)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel timing pass, shorten the e2e pass (huge scenes)")
     ap.add_argument("--balance-rows", type=int, default=2, help="N>1: rows a cut may move per frame toward the slower slab (weed_slab_balance; 0 = static cuts)")

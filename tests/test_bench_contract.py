@@ -36,6 +36,19 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_shortens_a_run_that_exceeds_its_host_time_budget_and_says_so():
+    r = run_bench("--impl", "reference", "--steps", "6", "--warmup", "3", "--cpu-sample", "100000", "--ref-budget-s", "0.05")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["steps"] == 6 and d["warmup"] == 3                 # what was asked for
+    assert d["steps_run"] == 2 and d["warmup_run"] == 1          # what the budget paid for: never fewer than 1 + 2 frames
+    assert "shortened to fit --ref-budget-s" in d["cpu_baseline"]["sample"] and d["value"] > 0
+    # within the budget nothing changes
+    r = run_bench("--impl", "reference", "--steps", "3", "--warmup", "2", "--cpu-sample", "20000")
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["steps_run"] == 3 and d["warmup_run"] == 2 and "shortened" not in d["cpu_baseline"]["sample"]
+
+
 def test_reference_arm_on_other_ranks_prints_nothing():
     r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "5000", env={"RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and not r.stdout.strip()
