@@ -133,3 +133,23 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|oracle[/.]|libweedoracle|weed_oracle", src), \
                     f"{f} references the oracle"
+
+
+def test_library_holds_sm_100a_code_for_every_frame_kernel(L):
+    """The built library carries native sm_100a code (not PTX to be JIT-compiled for something else) for
+    every kernel of the frame, the settled-bed forms included, and the sweep keeps its register budget
+    (40 registers: 12 blocks of 128 threads per SM — the occupancy the measurements rest on)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(ROOT, "multithreadedgameengine_b200", "libweedgpu.so")
+    out = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    for k in ("k_cell_key", "k_cell_scan", "k_scatter_ids", "k_sort_big_cells", "k_slot_rank", "k_build_slots", "k_slot_prep",
+              "k_neighbors2", "k_neighbors_wide", "k_beyond_cap", "k_back_alloc", "k_back_write", "k_back_sort", "k_sort_lists",
+              "k_sweep", "k_sweep_heavy", "k_sweep_tile", "k_writeback", "k_pair_scan", "k_pair_emit",
+              "k_slab_pack", "k_slab_wait", "k_slab_unpack"):
+        assert re.search(r"Function _ZN4weed\d+%s[A-Z]" % k, out), k
+    sweep = re.findall(r"Function _ZN4weed7k_sweepILb[01]ELb[01]E\S*:\s*\n\s*REG:(\d+)", out)
+    assert len(sweep) == 4 and all(int(r) <= 40 for r in sweep), sweep
